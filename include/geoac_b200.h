@@ -1,0 +1,153 @@
+/* geoac_b200.h -- C ABI of the B200-native batched ray-tracing engine (libgeoac_b200.so).
+ *
+ * The drop-in boundary sits between the launch-angle loops of the reference's `-prop` front ends and everything
+ * inside them (reference: Code/GeoAc3D_main.cpp:226-304, Code/GeoAc2D_main.cpp:170-229,
+ * Code/GeoAcGlobal_main.cpp:241-322, Code/GeoAc3D.RngDep_main.cpp:244-323, Code/GeoAcGlobal.RngDep_main.cpp:251-331).
+ * One call to geoac_trace() replaces, for EVERY (theta, phi) launch angle of the batch:
+ *   GeoAc_SetInitialConditions        (Code/GeoAc/GeoAc.EquationSets.h:8-10)
+ *   GeoAc_Propagate_RK4               (Code/GeoAc/GeoAc.Solver.h:8)   incl. GeoAc_UpdateSources / GeoAc_EvalSrcEq /
+ *                                      GeoAc_Set_ds / GeoAc_BreakCheck / GeoAc_GroundCheck (EquationSets.h:15-23)
+ *   GeoAc_TravelTime[Segment], GeoAc_SB_Atten[Segment], GeoAc_Jacobian, GeoAc_Amplitude (EquationSets.h:25-30)
+ *   GeoAc_SetReflectionConditions / GeoAc_ApproximateIntercept         (EquationSets.h:12-13)
+ * and the atmosphere API they call (Code/Atmo/Atmo_State.h:11-36: rho,c,u,v,w + _diff/_ddiff, SuthBass_Alpha).
+ *
+ * Plain pointers and sizes only; the caller owns every host buffer; a context owns its device memory.
+ * There is NO CPU fallback: without an sm_100 device geoac_create() fails with GEOAC_ERR_NO_DEVICE.
+ */
+#ifndef GEOAC_B200_H_
+#define GEOAC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- variants (one per reference executable, makefile:10-23) ---- */
+enum {
+    GEOAC_2D            = 0,   /* GeoAc2D            : effective sound speed, EqCnt 3/6            */
+    GEOAC_3D            = 1,   /* GeoAc3D            : stratified moving medium, EqCnt 4/12        */
+    GEOAC_GLOBAL        = 2,   /* GeoAcGlobal        : spherical stratified, EqCnt 6/18            */
+    GEOAC_3D_RNGDEP     = 3,   /* GeoAc3D.RngDep     : Cartesian range dependent, EqCnt 6/18       */
+    GEOAC_GLOBAL_RNGDEP = 4    /* GeoAcGlobal.RngDep : spherical range dependent, EqCnt 6/18       */
+};
+
+/* ---- status codes ---- */
+enum {
+    GEOAC_OK = 0,
+    GEOAC_ERR_NO_DEVICE = 1,      /* no CUDA device / not sm_100                                   */
+    GEOAC_ERR_BAD_ARG   = 2,
+    GEOAC_ERR_NO_ATMO   = 3,      /* trace called before an atmosphere was set                     */
+    GEOAC_ERR_CUDA      = 4,      /* CUDA runtime error, text in geoac_last_error()                */
+    GEOAC_ERR_TOO_LARGE = 5,      /* table does not fit the kernel's staging (message says why)    */
+    GEOAC_ERR_IO        = 6
+};
+
+/* ---- arrival record fields: rec[field * n_slots + ray * n_rec + bounce], n_slots = n_rays * n_rec ---- */
+enum {
+    GEOAC_F_STATE0     = 0,    /* 0..17: state vector at index k (first sub-ground point),
+                                  layout per variant as in the reference's solution[k][*]; unused entries 0 */
+    GEOAC_F_TRAVELTIME = 18,   /* [s]   accumulated over bounces                                  */
+    GEOAC_F_ATTEN      = 19,   /* [dB]  Sutherland-Bass, accumulated, positive (host prints -atten)*/
+    GEOAC_F_TURNHEIGHT = 20,   /* [km]  running max altitude (accumulated or per bounce, App. A-3) */
+    GEOAC_F_AMPLITUDE  = 21,   /* linear GeoAc_Amplitude(solution,k); host prints 20*log10; 0 if !calc_amp */
+    GEOAC_F_INCLINATION= 22,   /* [deg] as printed by the variant's main (sign conventions App. A-16) */
+    GEOAC_F_BACKAZ     = 23,   /* [deg] as printed by the variant's main; 0 for 2D                 */
+    GEOAC_F_AUX        = 24,   /* Global variants: celerity [km/s]; otherwise 0                    */
+    GEOAC_F_MARGIN     = 25,   /* (z_k - z_grnd)/|z_k - z_{k-1}|  in (-1,0): how far into the last step the ground
+                                  was crossed; values within ~1e-9 of 0 or -1 flag near-threshold rays */
+    GEOAC_NFIELDS      = 26
+};
+
+/* per-slot status */
+enum {
+    GEOAC_ST_NONE    = 0,      /* ray ended before this bounce                                     */
+    GEOAC_ST_ARRIVAL = 1,      /* ground arrival; record fields valid                              */
+    GEOAC_ST_BREAK   = 2,      /* left the propagation region (no results row, ray ends; App. A-19)*/
+    GEOAC_ST_LIMIT   = 3       /* step limit reached                                               */
+};
+
+typedef struct geoac_params {
+    /* solver (Code/GeoAc/GeoAc.Parameters*.cpp) */
+    double ds_min;             /* 0.001                                                            */
+    double ds_max;             /* 0.5                                                              */
+    double ray_limit;          /* 5000 (Cartesian) / 10000 (Global); step_limit = ray_limit*int(1/(ds_min*10)) */
+    /* propagation region; set from the atmosphere by geoac_set_atmosphere_* exactly like GeoAc_SetPropRegion,
+       then overridable (alt_max= / rng_max= / x_min= ... of the mains) */
+    double vert_limit;         /* z_max of the table (Cartesian) or absolute r_max (Global)        */
+    double range_limit;        /* 10000 (2D/3D), 1500 (Global)                                     */
+    double box_min[2];         /* RngDep: x_min,y_min  or lat_min,lon_min [rad]                    */
+    double box_max[2];
+    /* medium */
+    double z_grnd;             /* ground elevation [km]                                            */
+    double tweak_abs;          /* abs_coeff, 0.3                                                   */
+    double freq;               /* Hz, 0.1                                                          */
+    /* source: (x,y,z) Cartesian; 2D uses src[2] only; Global: (z_src [km above sea level], lat [rad], lon [rad]) */
+    double src[3];
+    int32_t bounces;           /* max ground reflections; n_rec = bounces + 1                      */
+    int32_t calc_amp;          /* CalcAmp: integrate the auxiliary (Jacobian) equations            */
+    int32_t accum_per_segment; /* 1: WriteRays/WriteCaustics convention (segments 0..k-2, App. A-2; always for 2D)
+                                  0: GeoAc_TravelTime(solution,k) convention (segments 0..k-1)     */
+    int32_t reserved;
+} geoac_params;
+
+typedef struct geoac_ctx geoac_ctx;
+
+/* Create a context for `variant` on CUDA device `device` (ordinal). Fails (NULL, *status set) without sm_100. */
+geoac_ctx* geoac_create(int variant, int device, int* status);
+void       geoac_destroy(geoac_ctx* ctx);
+const char* geoac_last_error(const geoac_ctx* ctx);     /* ctx may be NULL: last create() error    */
+
+/* Fill `p` with the variant's defaults (Code/GeoAc/GeoAc.Parameters*.cpp, mains' local defaults). */
+int geoac_default_params(int variant, geoac_params* p);
+
+/* Stratified atmosphere (replaces Spline_Single_G2S, Code/Atmo/G2S_Spline1D.cpp:293-312 / G2S_GlobalSpline1D.cpp:305-322).
+ * Arrays are the loader's output: z [km, sea-level based, NOT offset by r_earth], T [K], u,v [km/s] AFTER the
+ * unit conversion and ground taper (use geoac_load_met_1d), rho [g/cm^3].  The spline slopes are computed inside
+ * with the reference's Thomas recurrences.  Resets ctx params' vert_limit/range_limit like GeoAc_SetPropRegion. */
+int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, const double* T,
+                            const double* u, const double* v, const double* rho);
+
+/* Range-dependent atmosphere (replaces Spline_Multi_G2S + GeoAc_SetPropRegion, Code/Atmo/G2S_MultiDimSpline3D.cpp).
+ * ax0/ax1: horizontal node coordinates (x,y [km] or lat,lon [rad]); axz: altitude [km, sea-level based];
+ * fields are dense [n0][n1][nz] (z fastest), winds already tapered and in km/s. */
+int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz,
+                            const double* ax0, const double* ax1, const double* axz,
+                            const double* T, const double* u, const double* v, const double* rho);
+
+int geoac_get_params(const geoac_ctx* ctx, geoac_params* p);
+int geoac_set_params(geoac_ctx* ctx, const geoac_params* p);
+
+/* Trace n_rays launch angles (radians; phi in the math convention pi/2 - azimuth, exactly the values the mains
+ * store in GeoAc_theta / GeoAc_phi).  HOST buffers; copies angles H2D, runs the kernels, copies records D2H.
+ *   rec     : GEOAC_NFIELDS * n_rays * (bounces+1) doubles (SoA, see field enum)
+ *   status  : n_rays * (bounces+1) int32
+ *   n_steps : n_rays * (bounces+1) int32  (k returned by GeoAc_Propagate_RK4 for that segment)            */
+int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                double* rec, int32_t* status, int32_t* n_steps);
+
+/* Same, but every pointer is a DEVICE pointer on ctx's device and the work is enqueued on `cuda_stream`
+ * (a cudaStream_t passed as void*, NULL = default stream); returns without synchronising. */
+int geoac_trace_device(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
+                       double* d_rec, int32_t* d_status, int32_t* d_n_steps, void* cuda_stream);
+
+/* Total RK4 steps of the last trace on this ctx (sum of n_steps), and milliseconds the kernel(s) took (CUDA events). */
+int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_ms);
+
+/* Host helper mirroring Load_G2S (Code/Atmo/G2S_Spline1D.cpp:109-142): read a .met profile ("zTuvdp" or "zuvwTdp"),
+ * convert winds m/s -> km/s and apply the ground taper with `z_grnd_taper` (the mains always use 0, App. A-10).
+ * `global_taper` selects the Global file's arithmetic (z is offset by r_earth before the taper, which changes
+ * rounding).  Arrays must hold `cap` entries; *n receives the row count. */
+int geoac_load_met_1d(const char* path, const char* format, double z_grnd_taper, int global_taper,
+                      int cap, int* n, double* z, double* T, double* u, double* v, double* rho);
+
+/* Number of state equations for (variant, calc_amp): GeoAc_SetEqCnt, Code/GeoAc/GeoAc.Interface.cpp:21-41. */
+int geoac_eq_count(int variant, int calc_amp);
+
+/* FP64 DFMA micro-benchmark on ctx's device: returns measured TFLOP/s (2 flops per DFMA) -- the roofline denominator. */
+double geoac_measure_fp64_peak(geoac_ctx* ctx, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GEOAC_B200_H_ */

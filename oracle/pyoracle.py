@@ -1,0 +1,139 @@
+"""TEST INFRASTRUCTURE: ctypes binding of the CPU oracle (oracle/liboracle.so) and readers for the dumps written by
+oracle/_ref/ref_<variant>.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module; the product package geoac_b200 never does."""
+import ctypes as C
+import json
+import os
+import subprocess
+
+import numpy as np
+
+from geoac_b200 import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+
+
+def build(force=False):
+    so = os.path.join(HERE, "liboracle.so")
+    if force or not os.path.exists(so):
+        subprocess.check_call(["make", "-s", "-C", HERE, "port"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.orc_atmo1d_create.restype = C.c_void_p
+        L.orc_atmo1d_create.argtypes = [C.c_int, C.c_int, dp, dp, dp, dp, dp]
+        L.orc_atmo3d_create.restype = C.c_void_p
+        L.orc_atmo3d_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp]
+        L.orc_atmo_destroy.argtypes = [C.c_void_p]
+        L.orc_trace.restype = C.c_int64
+        L.orc_trace.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams), C.c_int64, dp, dp, dp, ip, ip]
+        L.orc_set_prop_region.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams)]
+        L.geoac_default_params_oracle.argtypes = [C.c_int, C.POINTER(abi.GeoacParams)]
+        L.orc_load_met_1d.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), dp, dp, dp, dp, dp]
+        L.orc_suthbass_alpha.restype = C.c_double
+        L.orc_suthbass_alpha.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(dp)
+
+
+def load_met_1d(path, fmt="zTuvdp", z_grnd_taper=0.0, global_taper=False, cap=200000):
+    arrs = [np.zeros(cap) for _ in range(5)]
+    n = C.c_int(0)
+    rc = lib().orc_load_met_1d(path.encode(), fmt.encode(), z_grnd_taper, int(global_taper), cap, C.byref(n), *[_p(a) for a in arrs])
+    if rc != 0:
+        raise IOError(f"orc_load_met_1d({path}) -> {rc}")
+    return [a[: n.value].copy() for a in arrs]   # z, T, u, v, rho
+
+
+class Atmo:
+    def __init__(self, handle):
+        self.h = handle
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_atmo_destroy(self.h)
+            self.h = None
+
+
+def atmo1d(is_global, z, T, u, v, rho):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (z, T, u, v, rho)]
+    return Atmo(lib().orc_atmo1d_create(int(is_global), len(arrs[0]), *[_p(a) for a in arrs]))
+
+
+def atmo3d(is_global, ax0, ax1, axz, T, u, v, rho):
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, axz, T, u, v, rho)]
+    h = lib().orc_atmo3d_create(int(is_global), len(arrs[0]), len(arrs[1]), len(arrs[2]), *[_p(a) for a in arrs])
+    if not h:
+        raise RuntimeError("orc_atmo3d_create failed")
+    return Atmo(h)
+
+
+def default_params(variant, atmo=None):
+    p = abi.GeoacParams()
+    lib().geoac_default_params_oracle(variant, C.byref(p))
+    if atmo is not None:
+        lib().orc_set_prop_region(variant, atmo.h, C.byref(p))
+    return p
+
+
+def trace(variant, atmo, params, theta, phi):
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    n = len(theta)
+    n_rec = params.bounces + 1
+    rec = np.zeros((abi.NFIELDS, n, n_rec))
+    status = np.zeros((n, n_rec), dtype=np.int32)
+    n_steps = np.zeros((n, n_rec), dtype=np.int32)
+    total = lib().orc_trace(variant, atmo.h, C.byref(params), n, _p(theta), _p(phi), _p(rec),
+                            status.ctypes.data_as(ip), n_steps.ctypes.data_as(ip))
+    if total < 0:
+        raise RuntimeError("orc_trace failed")
+    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": int(total)}
+
+
+# ---------------------------------------------------------------- reference dumps (oracle/_ref/ref_<variant>)
+REF_NF = 32
+REF_F_STATUS, REF_F_NSTEPS = 26, 27
+
+
+def ref_binary(variant):
+    return os.path.join(HERE, "_ref", "ref_" + abi.VARIANT_NAMES[variant])
+
+
+def run_ref(variant, profile_args, out_path, **kv):
+    """Run the unmodified reference through oracle/ref_driver.cpp; returns (records dict, timing json)."""
+    cmd = [ref_binary(variant), out_path] + list(profile_args) + [f"{k}={v}" for k, v in kv.items()]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
+    info = json.loads(out.strip().splitlines()[-1])
+    return read_ref_bin(out_path), info
+
+
+def read_ref_bin(path):
+    raw = np.fromfile(path, dtype=np.float64)
+    assert raw[0] == 20251018.0, "bad magic"
+    n, n_rec, nf, eq = int(raw[1]), int(raw[2]), int(raw[3]), int(raw[4])
+    ang = raw[8: 8 + 2 * n].reshape(n, 2)
+    recs = raw[8 + 2 * n:].reshape(n, n_rec, nf)
+    rec = np.ascontiguousarray(np.transpose(recs[:, :, : abi.NFIELDS], (2, 0, 1)))
+    return {"theta_deg": ang[:, 0].copy(), "phi_deg": ang[:, 1].copy(), "rec": rec,
+            "status": recs[:, :, REF_F_STATUS].astype(np.int32), "n_steps": recs[:, :, REF_F_NSTEPS].astype(np.int32),
+            "eq_cnt": eq, "total_steps": int(raw[5]), "t_rk4_s": raw[6], "t_post_s": raw[7]}
+
+
+def angles_rad(theta_deg, phi_deg):
+    """deg -> rad exactly as the mains do (Code/GeoAc3D_main.cpp:228-229)."""
+    Pi = 3.141592653589793238462643
+    theta_deg = np.asarray(theta_deg, dtype=np.float64)
+    phi_deg = np.asarray(phi_deg, dtype=np.float64)
+    return theta_deg * Pi / 180.0, Pi / 2.0 - phi_deg * Pi / 180.0
