@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the batched ray-tracing hot path on BASELINE.json's config 2
+(GeoAc3D, ToyAtmo.met, theta 1-60 deg step 1 x azimuth 0-359.9 deg step 0.1 = 216 000 rays, 2 bounces, CalcAmp on,
+WriteRays=False), one pass over the whole launch-angle grid = one "step".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config1|smallgrid]
+
+N > 1 is launched by torchrun, one rank per GPU; the launch-angle grid is replicated per rank with a rank-specific
+azimuth offset (weak scaling, no data-path collective: rays are independent).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TOY = os.path.join(ROOT, "tests", "golden", "ToyAtmo.met")
+# ALGORITHMIC FP64 operations per RK4 step (de-duplicated, CalcAmp on, incl. travel-time + absorption bookkeeping);
+# convention and derivation in DESIGN.md section "flop counting" (add/sub/mul/div/sqrt/transcendental = 1, fma = 2)
+ALGO_FLOPS_PER_STEP = {"config2": 2200.0, "config1": 1400.0, "smallgrid": 2200.0}
+
+
+def workload_angles(name, rank=0):
+    from geoac_b200 import api
+    if name == "config2":
+        grid = (1.0, 60.5, 1.0, 0.0, 359.95, 0.1)
+    elif name == "smallgrid":
+        grid = (1.0, 60.5, 1.0, 0.0, 359.5, 5.0)
+    elif name == "config1":
+        grid = (0.5, 45.0, 0.5, -90.0, -90.0, 1.0)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    th_deg, ph_deg, _, _ = api.prop_angles(*grid)
+    ph_deg = ph_deg + 0.05 * rank / 8.0 * (name != "config1")       # weak scaling: same grid, rank-specific rotation
+    Pi = 3.141592653589793238462643
+    return grid, th_deg, ph_deg, th_deg * Pi / 180.0, Pi / 2.0 - ph_deg * Pi / 180.0
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi style clock / throttle-reason sampling DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if not self.nv:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_run(workload, target_rays, n_proc):
+    """Time the reference's own CPU implementation (oracle/_ref/ref_3d: the unmodified reference sources + a driver
+    main) or, when it is not built, the C restatement, on every `stride`-th ray of the workload, split over n_proc
+    processes with disjoint ray sets.  Returns dict(rays, steps, seconds, kind, cores, sample)."""
+    from geoac_b200 import abi
+    variant = abi.GEOAC_2D if workload == "config1" else abi.GEOAC_3D
+    grid, th_deg, _, _, _ = workload_angles(workload)
+    total = len(th_deg)
+    import math
+    stride = max(1, total // max(1, target_rays // n_proc))
+    stride = max(stride, n_proc) if total > n_proc else 1
+    while stride > 1 and math.gcd(stride, 60) != 1:      # theta is the fast axis (60 values): keep the sample unbiased
+        stride += 1
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_" + abi.VARIANT_NAMES[variant])
+    keys = dict(theta_min=grid[0], theta_max=grid[1], theta_step=grid[2], bounces=2)
+    if variant == abi.GEOAC_3D:
+        keys.update(phi_min=grid[3], phi_max=grid[4], phi_step=grid[5], accum_mode=0)
+    if os.path.exists(ref_bin):
+        kind = "reference"
+        with tempfile.TemporaryDirectory() as td:
+            procs = []
+            t0 = time.perf_counter()
+            for i in range(n_proc):
+                # process i takes rays with index % (stride) == i * (stride // n_proc): disjoint, evenly spread
+                off = (i * (stride // n_proc)) % stride
+                cmd = [ref_bin, os.path.join(td, f"o{i}.bin"), TOY] + [f"{k}={v}" for k, v in keys.items()] + [f"stride={stride}", f"offset={off}"]
+                procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True))
+            outs = [p.communicate()[0] for p in procs]
+            secs = time.perf_counter() - t0
+        infos = [json.loads(o.strip().splitlines()[-1]) for o in outs]
+        rays = sum(i["rays"] for i in infos)
+        steps = sum(i["steps"] for i in infos)
+        trace_secs = max(i["t_trace_s"] for i in infos)          # slowest process, excluding profile load
+        secs = trace_secs
+    else:
+        kind = "port"
+        from multiprocessing import Pool
+        idx = np.arange(total)
+        shards = [idx[(idx % stride) == ((i * (stride // n_proc)) % stride)] for i in range(n_proc)]
+        t0 = time.perf_counter()
+        with Pool(n_proc) as pool:
+            res = pool.starmap(_port_worker, [(workload, variant, s) for s in shards])
+        secs = time.perf_counter() - t0
+        rays = sum(r[0] for r in res)
+        steps = sum(r[1] for r in res)
+    return {"rays": rays, "steps": steps, "seconds": secs, "kind": kind, "cores": n_proc,
+            "sample": f"every {stride}th ray of {workload} ({rays} of {total} rays, {steps} RK4 steps), {n_proc} process(es)"}
+
+
+def _port_worker(workload, variant, idx):
+    from oracle import pyoracle as po
+    _, _, _, th, ph = workload_angles(workload)
+    at = po.atmo1d(False, *po.load_met_1d(TOY))
+    p = po.default_params(variant, at)
+    out = po.trace(variant, at, p, th[idx], ph[idx])
+    return len(idx), out["total_steps"]
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    per_step = []
+    res = None
+    for i in range(args.warmup + args.steps):
+        res = cpu_reference_run(args.workload, target_rays=cores * 24, n_proc=cores)
+        if i >= args.warmup:
+            per_step.append(res)
+    secs = sum(r["seconds"] for r in per_step)
+    rays = sum(r["rays"] for r in per_step)
+    steps = sum(r["steps"] for r in per_step)
+    val = rays / secs
+    line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "rk4_steps_per_sec": steps / secs,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic launch-angle grid, ToyAtmo.met profile",
+            "config": {"workload": workload_desc(args.workload), "sample": res["sample"]},
+            "cpu_baseline": {"value": val, "unit": "rays/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
+                             "rk4_steps_per_sec": steps / secs},
+            "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_desc(name):
+    return {"config2": "BASELINE config 2: GeoAc3D stratified, ToyAtmo.met, theta 1..60 step 1 x azimuth 0..359.9 step 0.1 (216000 rays), bounces=2, CalcAmp on, WriteRays=False",
+            "config1": "BASELINE config 1: GeoAc2D, ToyAtmo.met, theta 0.5..45 step 0.5, azimuth -90 (90 rays), bounces=2",
+            "smallgrid": "reduced grid for debugging: GeoAc3D, theta 1..60 x azimuth 0..355 step 5 (4320 rays)"}[name]
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import geoac_b200 as g
+    from geoac_b200 import abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    variant = abi.GEOAC_2D if args.workload == "config1" else abi.GEOAC_3D
+    grid, th_deg, ph_deg, th, ph = workload_angles(args.workload, rank)
+    n = len(th)
+    tr = g.Tracer(variant, local)
+    tr.set_atmosphere_1d(*g.load_met_1d(TOY))
+    p = tr.params
+    p.bounces, p.calc_amp, p.accum_per_segment = 2, 1, (1 if variant == abi.GEOAC_2D else 0)
+    tr.params = p
+    n_rec = p.bounces + 1
+    n_slots = n * n_rec
+
+    # ---- device-resident leg: inputs already in HBM, outputs stay in HBM ----
+    d_th = torch.from_numpy(th).to(dev)
+    d_ph = torch.from_numpy(ph).to(dev)
+    d_rec = torch.empty((abi.NFIELDS, n_slots), dtype=torch.float64, device=dev)
+    d_status = torch.empty(n_slots, dtype=torch.int32, device=dev)
+    d_nsteps = torch.empty(n_slots, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def one_pass():
+        flush.zero_()                                                    # L2 flush between iterations
+        tr.trace_device(n, d_th.data_ptr(), d_ph.data_ptr(), d_rec.data_ptr(), d_status.data_ptr(), d_nsteps.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        one_pass()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        flush.zero_()
+        kev[i][0].record(stream)
+        tr.trace_device(n, d_th.data_ptr(), d_ph.data_ptr(), d_rec.data_ptr(), d_status.data_ptr(), d_nsteps.data_ptr(), stream.cuda_stream)
+        kev[i][1].record(stream)
+        ev[i][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    sampler.join()
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps        # trace kernel (+4 memsets) per launch
+    total_steps, _ = tr.last_stats()                                    # RK4 steps of one pass on this rank
+    arrivals = int((d_status == abi.ST_ARRIVAL).sum().item())
+
+    t = torch.tensor([dev_ms, float(total_steps), float(n)], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms_max, steps_all, rays_all = tmax[0].item(), tsum[1].item(), tsum[2].item()
+    else:
+        dev_ms_max, steps_all, rays_all = dev_ms, float(total_steps), float(n)
+    secs = dev_ms_max * 1e-3
+    rays_per_s = rays_all * args.steps / secs
+    steps_per_s = steps_all * args.steps / secs
+
+    # ---- end-to-end leg: HOST (pinned) buffers through the public C-ABI call, H2D + D2H inside the timed region ----
+    h_th = torch.from_numpy(th).pin_memory(); h_ph = torch.from_numpy(ph).pin_memory()
+    h_rec = torch.empty((abi.NFIELDS, n, n_rec), dtype=torch.float64).pin_memory()
+    h_status = torch.empty((n, n_rec), dtype=torch.int32).pin_memory()
+    h_nsteps = torch.empty((n, n_rec), dtype=torch.int32).pin_memory()
+    out = {"rec": h_rec.numpy(), "status": h_status.numpy(), "n_steps": h_nsteps.numpy()}
+    tr.trace(h_th.numpy(), h_ph.numpy(), out)                           # warm-up (allocates staging)
+    barrier()
+    e0 = time.perf_counter()
+    e2e_k = max(1, min(args.steps, 3))
+    for _ in range(e2e_k):
+        tr.trace(h_th.numpy(), h_ph.numpy(), out)                       # synchronous: returns with results on the host
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_rays = rays_all * e2e_k / te.item()
+    h2d = 2 * n * 8
+    d2h = abi.NFIELDS * n_slots * 8 + 2 * n_slots * 4 + 16
+
+    if rank == 0:
+        peak_tf, peak_ms = tr.measure_fp64_peak()
+        flops_step = ALGO_FLOPS_PER_STEP[args.workload]
+        achieved_tf = flops_step * total_steps / (kern_ms * 1e-3) / 1e12
+        line = {
+            "metric": "rays/sec", "value": rays_per_s, "unit": "rays/s", "rk4_steps_per_sec": steps_per_s,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic launch-angle grid, ToyAtmo.met profile (the reference's shipped fixture)",
+            "config": {"workload": workload_desc(args.workload), "rays_per_gpu": n, "rk4_steps_per_pass_per_gpu": total_steps,
+                       "arrival_records_per_pass": arrivals, "l2": "256 MiB buffer written between iterations (L2 flush); "
+                       "the kernel's working set is the 112 KB table in shared memory", "multi_gpu": "replicated grid per rank, azimuth offset by rank"},
+            "e2e": {"value": e2e_rays, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "passes": e2e_k},
+            "gpu_launches": args.steps,
+            "clocks": sampler.summary(),
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
+                         "traffic": None, "kernel": "geoac::trace_kernel<Eq3D<true>,256,true>", "kernel_ms_per_launch": kern_ms,
+                         "algorithmic_flops_per_rk4_step": flops_step,
+                         "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
+                                        "HBM is not the bound: ~0.03 B/step of record traffic"},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_reference_run(args.workload, target_rays=120, n_proc=1)
+            line["cpu_baseline"] = {"value": cb["rays"] / cb["seconds"], "unit": "rays/s", "cores": 1, "kind": cb["kind"],
+                                    "sample": cb["sample"], "rk4_steps_per_sec": cb["steps"] / cb["seconds"]}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "smallgrid"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

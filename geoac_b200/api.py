@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference's `-prop` interface on top of the C ABI (include/geoac_b200.h).
+
+The product path is: Python (or the C++ front ends) -> libgeoac_b200.so (extern "C") -> sm_100a CUDA kernels.
+There is no CPU implementation behind this module: if the library is missing or no B200 is present, it raises.
+Reference call sites this replaces: Code/GeoAc3D_main.cpp:226-304 and the four sibling mains.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+from .abi import GeoacParams
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_LIB = None
+
+
+class GeoAcError(RuntimeError):
+    pass
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libgeoac_b200.so")
+
+
+def lib():
+    """Load libgeoac_b200.so (built by geoac_b200.build.build()); fail loudly if it is absent."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise GeoAcError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                             "There is no CPU fallback.")
+        L = C.CDLL(path)
+        L.geoac_create.restype = C.c_void_p
+        L.geoac_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.geoac_destroy.argtypes = [C.c_void_p]
+        L.geoac_last_error.restype = C.c_char_p
+        L.geoac_last_error.argtypes = [C.c_void_p]
+        L.geoac_default_params.argtypes = [C.c_int, C.POINTER(GeoacParams)]
+        L.geoac_set_atmosphere_1d.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.geoac_set_atmosphere_3d.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.geoac_get_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
+        L.geoac_set_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
+        L.geoac_trace.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip]
+        L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
+        L.geoac_load_met_1d.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp]
+        L.geoac_eq_count.argtypes = [C.c_int, C.c_int]
+        L.geoac_measure_fp64_peak.restype = C.c_double
+        L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        _LIB = L
+    return _LIB
+
+
+EXPORTED_SYMBOLS = [
+    "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
+    "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_device",
+    "geoac_last_trace_stats", "geoac_load_met_1d", "geoac_eq_count", "geoac_measure_fp64_peak",
+]
+
+
+def _p(a):
+    return a.ctypes.data_as(_dp)
+
+
+def load_met_1d(path, fmt="zTuvdp", z_grnd_taper=0.0, global_taper=False, cap=200000):
+    """Load_G2S mirror (reference Code/Atmo/G2S_Spline1D.cpp:109-142): returns z, T, u, v, rho (winds tapered, km/s)."""
+    arrs = [np.zeros(cap) for _ in range(5)]
+    n = C.c_int(0)
+    rc = lib().geoac_load_met_1d(os.fsencode(path), fmt.encode(), z_grnd_taper, int(global_taper), cap, C.byref(n), *[_p(a) for a in arrs])
+    if rc != abi.GEOAC_OK:
+        raise GeoAcError(f"geoac_load_met_1d({path}) failed with status {rc}")
+    return [a[: n.value].copy() for a in arrs]
+
+
+def default_params(variant):
+    p = GeoacParams()
+    lib().geoac_default_params(variant, C.byref(p))
+    return p
+
+
+def prop_angles(theta_min, theta_max, theta_step, phi_min, phi_max, phi_step):
+    """Enumerate launch angles exactly like the mains' loops `for(double a=min; a<=max; a+=step)` (phi outer, theta
+    inner; reference Code/GeoAc3D_main.cpp:226-229) and convert to the radians stored in GeoAc_theta/GeoAc_phi."""
+    Pi = 3.141592653589793238462643
+    thetas, phis = [], []
+    t = float(theta_min)
+    while t <= theta_max:
+        thetas.append(t)
+        t += theta_step
+    p = float(phi_min)
+    while p <= phi_max:
+        phis.append(p)
+        p += phi_step
+    th = np.tile(np.array(thetas), len(phis))
+    ph = np.repeat(np.array(phis), len(thetas))
+    return th, ph, th * Pi / 180.0, Pi / 2.0 - ph * Pi / 180.0
+
+
+class Tracer:
+    """One context = one variant on one GPU (geoac_create ... geoac_destroy)."""
+
+    def __init__(self, variant, device=0):
+        st = C.c_int(0)
+        self._h = lib().geoac_create(variant, device, C.byref(st))
+        if not self._h:
+            raise GeoAcError(f"geoac_create failed ({st.value}): {lib().geoac_last_error(None).decode()}")
+        self.variant = variant
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().geoac_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != abi.GEOAC_OK:
+            raise GeoAcError(f"{what} failed ({rc}): {lib().geoac_last_error(self._h).decode()}")
+
+    def set_atmosphere_1d(self, z, T, u, v, rho):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (z, T, u, v, rho)]
+        self._check(lib().geoac_set_atmosphere_1d(self._h, len(arrs[0]), *[_p(a) for a in arrs]), "geoac_set_atmosphere_1d")
+
+    def set_atmosphere_3d(self, ax0, ax1, axz, T, u, v, rho):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, axz, T, u, v, rho)]
+        self._check(lib().geoac_set_atmosphere_3d(self._h, len(arrs[0]), len(arrs[1]), len(arrs[2]), *[_p(a) for a in arrs]),
+                    "geoac_set_atmosphere_3d")
+
+    @property
+    def params(self):
+        p = GeoacParams()
+        self._check(lib().geoac_get_params(self._h, C.byref(p)), "geoac_get_params")
+        return p
+
+    @params.setter
+    def params(self, p):
+        self._check(lib().geoac_set_params(self._h, C.byref(p)), "geoac_set_params")
+
+    def trace(self, theta, phi, out=None):
+        """Host buffers in, host buffers out (H2D + kernels + D2H inside). Returns dict(rec, status, n_steps)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        n = len(theta)
+        n_rec = self.params.bounces + 1
+        if out is None:
+            out = {"rec": np.empty((abi.NFIELDS, n, n_rec)), "status": np.empty((n, n_rec), dtype=np.int32),
+                   "n_steps": np.empty((n, n_rec), dtype=np.int32)}
+        self._check(lib().geoac_trace(self._h, n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip),
+                                      out["n_steps"].ctypes.data_as(_ip)), "geoac_trace")
+        return out
+
+    def trace_device(self, n, d_theta, d_phi, d_rec, d_status, d_n_steps, stream=0):
+        """Device pointers (ints) in/out, enqueued on `stream` (cudaStream_t as int); no synchronisation."""
+        self._check(lib().geoac_trace_device(self._h, n, d_theta, d_phi, d_rec, d_status, d_n_steps, stream), "geoac_trace_device")
+
+    def last_stats(self):
+        s = C.c_int64(0)
+        ms = C.c_double(0)
+        self._check(lib().geoac_last_trace_stats(self._h, C.byref(s), C.byref(ms)), "geoac_last_trace_stats")
+        return s.value, ms.value
+
+    def measure_fp64_peak(self):
+        ms = C.c_double(0)
+        return lib().geoac_measure_fp64_peak(self._h, C.byref(ms)), ms.value

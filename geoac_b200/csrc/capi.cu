@@ -1,0 +1,409 @@
+// capi.cu -- the extern "C" boundary of libgeoac_b200.so (declared in include/geoac_b200.h).
+//
+// Host side only: context management, table construction (the reference's Thomas recurrences,
+// Code/Atmo/G2S_Spline1D.cpp:161-196, so the slope tables are bit-identical), kernel launches, H2D/D2H staging.
+// There is deliberately NO CPU implementation of the trace here: without an sm_100 device every entry point fails.
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+
+#include "core.cuh"
+#include "eq_cartesian.cuh"
+#if __has_include("eq_global.cuh")
+#include "eq_global.cuh"
+#define GEOAC_HAVE_GLOBAL 1
+#endif
+#include "trace_kernel.cuh"
+
+using namespace geoac;
+
+static thread_local std::string g_create_error;
+
+struct geoac_ctx {
+    int variant = 0, device = 0, sm_count = 0;
+    geoac_params prm{};
+    std::string err;
+    // 1-D table
+    bool have_atmo = false;
+    int n = 0, n_pad = 0;
+    double xmin = 0, xmax = 0;
+    std::vector<double> h_table;
+    double* d_table = nullptr;
+    LaunchConsts* d_consts = nullptr;
+    unsigned long long* d_counters = nullptr;     // [0] ray counter, [1] total steps
+    // staging for the host-buffer entry point
+    double *d_theta = nullptr, *d_phi = nullptr, *d_rec = nullptr;
+    int32_t *d_status = nullptr, *d_nsteps = nullptr;
+    int64_t cap_rays = 0, cap_slots = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t last_steps = 0; double last_ms = 0.0;
+    bool consts_dirty = true;
+};
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); return GEOAC_ERR_CUDA; } } while (0)
+
+static int fail(geoac_ctx* ctx, int code, const std::string& msg) { if (ctx) ctx->err = msg; return code; }
+
+extern "C" int geoac_eq_count(int variant, int calc_amp) {          // Code/GeoAc/GeoAc.Interface.cpp:21-41
+    switch (variant) {
+        case GEOAC_2D: return calc_amp ? 6 : 3;
+        case GEOAC_3D: return calc_amp ? 12 : 4;
+        case GEOAC_GLOBAL: case GEOAC_3D_RNGDEP: case GEOAC_GLOBAL_RNGDEP: return calc_amp ? 18 : 6;
+    }
+    return -1;
+}
+
+extern "C" int geoac_default_params(int variant, geoac_params* p) {
+    if (!p || variant < 0 || variant > GEOAC_GLOBAL_RNGDEP) return GEOAC_ERR_BAD_ARG;
+    std::memset(p, 0, sizeof *p);
+    const bool glob = (variant == GEOAC_GLOBAL || variant == GEOAC_GLOBAL_RNGDEP);
+    p->ds_min = 0.001; p->ds_max = 0.5;                   // GeoAc.Parameters.cpp:20-21
+    p->ray_limit = glob ? 10000.0 : 5000.0;              // GeoAc.Parameters.cpp:24 / .Global.cpp
+    p->vert_limit = 200.0; p->range_limit = 2000.0;
+    p->z_grnd = 0.0; p->tweak_abs = 0.3; p->freq = 0.1;
+    p->bounces = 2; p->calc_amp = 1;
+    p->accum_per_segment = (variant == GEOAC_2D) ? 1 : 0;
+    if (variant == GEOAC_GLOBAL) { p->src[1] = 30.0 * kPi / 180.0; p->src[2] = 0.0; }   // GeoAcGlobal_main.cpp:120
+    return GEOAC_OK;
+}
+
+extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
+    auto bail = [&](int code, const std::string& m) -> geoac_ctx* { g_create_error = m; if (status) *status = code; return nullptr; };
+    if (variant < 0 || variant > GEOAC_GLOBAL_RNGDEP) return bail(GEOAC_ERR_BAD_ARG, "unknown variant");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return bail(GEOAC_ERR_NO_DEVICE, "no CUDA device (this library has no CPU path)");
+    if (device < 0 || device >= ndev) return bail(GEOAC_ERR_BAD_ARG, "device ordinal out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(GEOAC_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return bail(GEOAC_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", kernels are built for sm_100a only");
+    geoac_ctx* ctx = new geoac_ctx();
+    ctx->variant = variant; ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    geoac_default_params(variant, &ctx->prm);
+    cudaSetDevice(device);
+    bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess
+           && cudaMalloc(&ctx->d_consts, sizeof(LaunchConsts)) == cudaSuccess
+           && cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
+    if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); delete ctx; return bail(GEOAC_ERR_CUDA, "context allocation failed: " + m); }
+    if (status) *status = GEOAC_OK;
+    return ctx;
+}
+
+extern "C" void geoac_destroy(geoac_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* geoac_last_error(const geoac_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int geoac_get_params(const geoac_ctx* ctx, geoac_params* p) { if (!ctx || !p) return GEOAC_ERR_BAD_ARG; *p = ctx->prm; return GEOAC_OK; }
+extern "C" int geoac_set_params(geoac_ctx* ctx, const geoac_params* p) {
+    if (!ctx || !p) return GEOAC_ERR_BAD_ARG;
+    if (p->bounces < 0 || p->ds_min <= 0.0 || p->ray_limit <= 0.0) return fail(ctx, GEOAC_ERR_BAD_ARG, "bad params");
+    ctx->prm = *p; ctx->consts_dirty = true; return GEOAC_OK;
+}
+
+// ---- knot slopes of the natural spline: same tridiagonal recurrences as G2S_Spline1D.cpp:161-196 ----
+static void natural_slopes(const std::vector<double>& x, const double* f, double* s) {
+    const int n = (int)x.size();
+    std::vector<double> cp(n), dp(n);
+    double lo, di, up, rh;
+    di = 2.0 / (x[1] - x[0]); up = 1.0 / (x[1] - x[0]);
+    rh = 3.0 * (f[1] - f[0]) / std::pow(x[1] - x[0], 2);
+    cp[0] = up / di; dp[0] = rh / di;
+    for (int i = 1; i < n - 1; i++) {
+        lo = 1.0 / (x[i] - x[i - 1]);
+        di = 2.0 * (1.0 / (x[i] - x[i - 1]) + 1.0 / (x[i + 1] - x[i]));
+        up = 1.0 / (x[i + 1] - x[i]);
+        rh = 3.0 * ((f[i] - f[i - 1]) / std::pow(x[i] - x[i - 1], 2) + (f[i + 1] - f[i]) / std::pow(x[i + 1] - x[i], 2));
+        cp[i] = up / (di - cp[i - 1] * lo);
+        dp[i] = (rh - dp[i - 1] * lo) / (di - cp[i - 1] * lo);
+    }
+    lo = 1.0 / (x[n - 1] - x[n - 2]); di = 2.0 / (x[n - 1] - x[n - 2]);
+    rh = 3.0 * (f[n - 1] - f[n - 2]) / std::pow(x[n - 1] - x[n - 2], 2);
+    dp[n - 1] = (rh - dp[n - 2] * lo) / (di - cp[n - 2] * lo);
+    s[n - 1] = dp[n - 1];
+    for (int i = n - 2; i > -1; i--) s[i] = dp[i] - cp[i] * s[i + 1];
+}
+
+extern "C" int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, const double* T,
+                                       const double* u, const double* v, const double* rho) {
+    if (!ctx) return GEOAC_ERR_BAD_ARG;
+    if (ctx->variant != GEOAC_2D && ctx->variant != GEOAC_3D && ctx->variant != GEOAC_GLOBAL)
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "variant needs geoac_set_atmosphere_3d");
+    if (n < 3 || !z || !T || !u || !v || !rho) return fail(ctx, GEOAC_ERR_BAD_ARG, "need >= 3 levels and non-null arrays");
+    for (int i = 1; i < n; i++) if (!(z[i] > z[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "altitudes must be strictly increasing");
+    cudaSetDevice(ctx->device);
+    const bool glob = ctx->variant == GEOAC_GLOBAL;
+    const int n_pad = (n + 1) & ~1;                       // keep every array 16-byte aligned for the bulk copy
+    std::vector<double> x(n);
+    for (int i = 0; i < n; i++) { x[i] = z[i]; if (glob) x[i] += kREarth; }   // r_vals[nr] += r_earth
+    ctx->h_table.assign((size_t)TAB_NARR * n_pad, 0.0);
+    double* tb = ctx->h_table.data();
+    for (int i = 0; i < n; i++) {
+        tb[TAB_X * n_pad + i] = x[i];
+        tb[TAB_INVH * n_pad + i] = (i + 1 < n) ? 1.0 / (x[i + 1] - x[i]) : 0.0;
+        tb[TAB_T * n_pad + i] = T[i]; tb[TAB_U * n_pad + i] = u[i]; tb[TAB_V * n_pad + i] = v[i]; tb[TAB_RHO * n_pad + i] = rho[i];
+    }
+    natural_slopes(x, tb + TAB_T * n_pad, tb + TAB_ST * n_pad);
+    natural_slopes(x, tb + TAB_U * n_pad, tb + TAB_SU * n_pad);
+    natural_slopes(x, tb + TAB_V * n_pad, tb + TAB_SV * n_pad);
+    natural_slopes(x, tb + TAB_RHO * n_pad, tb + TAB_SRHO * n_pad);
+    cudaFree(ctx->d_table); ctx->d_table = nullptr;
+    CK(cudaMalloc(&ctx->d_table, ctx->h_table.size() * sizeof(double)));
+    CK(cudaMemcpy(ctx->d_table, tb, ctx->h_table.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->n = n; ctx->n_pad = n_pad; ctx->xmin = x[0]; ctx->xmax = x[n - 1];
+    // GeoAc_SetPropRegion: G2S_Spline1D.cpp:22-28 / G2S_GlobalSpline1D.cpp:22-30
+    ctx->prm.vert_limit = ctx->xmax;
+    ctx->prm.range_limit = glob ? 1500.0 : 10000.0;
+    if (glob) { ctx->prm.box_min[0] = -kPi / 2.0; ctx->prm.box_max[0] = kPi / 2.0; ctx->prm.box_min[1] = -kPi; ctx->prm.box_max[1] = kPi; }
+    ctx->have_atmo = true; ctx->consts_dirty = true;
+    return GEOAC_OK;
+}
+
+extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int, int, int, const double*, const double*, const double*,
+                                       const double*, const double*, const double*, const double*) {
+    return fail(ctx, GEOAC_ERR_BAD_ARG, "range-dependent atmospheres are not built into this library yet");
+}
+
+// ---- per-launch invariants, computed on the device with the same spline routines the kernel uses ----
+__global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, const double* table, int n, int n_pad,
+                                    double xmin, double xmax, int variant) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    LaunchConsts L = in;
+    Table1D T; T.base = table; T.n = n; T.n_pad = n_pad; T.xmin = xmin; T.xmax = xmax;
+    const bool glob = (variant == GEOAC_GLOBAL);
+    int cur = 0;
+    auto sample = [&](double x, double& c, double& u, double& v, double& rho, double& dc, double& du, double& dv) {
+        const SegPos sp = seg_locate(T, clampd(x, xmin, xmax), cur);
+        double Tv, dT, ddT, d2;
+        spl_f2(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT, ddT);
+        spl_f2(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du, d2);
+        spl_f2(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv, d2);
+        rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+        c = sqrt(kGamR * Tv);
+        dc = kGamR / (2.0 * c) * dT;
+    };
+    double c, u, v, rho, dc, du, dv;
+    L.ground = glob ? kREarth + L.z_grnd : L.z_grnd;
+    const double x_src = glob ? L.src[0] + kREarth : L.src[2];
+    sample(x_src, c, u, v, rho, dc, du, dv);
+    L.c_src = c; L.u_src = u; L.v_src = v; L.rho_src = rho;
+    sample(0.0, c, u, v, rho, dc, du, dv);
+    L.c_000 = c;
+    sample(L.ground, c, u, v, rho, dc, du, dv);
+    L.c_gnd = c; L.rho_gnd = rho; L.dc_gnd = dc; L.du_gnd = du; L.dv_gnd = dv;
+    // Sutherland-Bass reference state: c,rho at (0,0,z_grnd) (Cartesian, Absorption.cpp:33-34) or at r = z_grnd,
+    // i.e. clamped to the lowest level (Global, Absorption.Global.cpp:31-32)
+    sample(glob ? L.z_grnd : L.z_grnd, c, u, v, rho, dc, du, dv);
+    suthbass_setup(L, c, rho);
+    *out = L;
+}
+
+static int refresh_consts(geoac_ctx* ctx) {
+    if (!ctx->consts_dirty) return GEOAC_OK;
+    const geoac_params& p = ctx->prm;
+    LaunchConsts L; std::memset(&L, 0, sizeof L);
+    L.ds_min = p.ds_min; L.ds_max = p.ds_max; L.vert_limit = p.vert_limit; L.range_limit = p.range_limit;
+    L.z_grnd = p.z_grnd; L.tweak_abs = p.tweak_abs; L.freq = p.freq;
+    for (int i = 0; i < 2; i++) { L.box_min[i] = p.box_min[i]; L.box_max[i] = p.box_max[i]; }
+    for (int i = 0; i < 3; i++) L.src[i] = p.src[i];
+    if (ctx->variant == GEOAC_2D || ctx->variant == GEOAC_3D) L.src[2] = std::max(p.z_grnd, p.src[2]);   // z_src = max(z_grnd, z_src)
+    else L.src[0] = std::max(p.z_grnd, p.src[0]);
+    L.bounces = p.bounces; L.calc_amp = p.calc_amp;
+    L.seg_mode = (ctx->variant == GEOAC_2D) ? 1 : (p.accum_per_segment ? 1 : 0);                          // App. A-2
+    L.step_limit = (int)(p.ray_limit * (int)(1.0 / (p.ds_min * 10)));                                     // Solver.cpp:14
+    L.per_bounce_zmax = (ctx->variant == GEOAC_3D_RNGDEP || ctx->variant == GEOAC_GLOBAL_RNGDEP);         // App. A-3
+    setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->n_pad, ctx->xmin, ctx->xmax, ctx->variant);
+    CK(cudaGetLastError());
+    ctx->consts_dirty = false;
+    return GEOAC_OK;
+}
+
+// ---- kernel launch ----
+template <class EQ, int BLOCK>
+static int launch_trace(geoac_ctx* ctx, const TraceArgs& a, cudaStream_t st) {
+    const size_t fixed = ((sizeof(LaunchConsts) + 15) / 16) * 16 + 16 + (size_t)EQ::NEQ * BLOCK * sizeof(double);
+    const size_t tab_bytes = (size_t)TAB_NARR * ctx->n_pad * sizeof(double);
+    int max_optin = 0;
+    CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const bool in_smem = fixed + tab_bytes <= (size_t)max_optin;
+    // never launch more lanes than rays (small batches: one warp per CTA first)
+    int64_t warps_needed = (a.n_rays + 31) / 32;
+    int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32)));
+    if (in_smem) {
+        auto k = trace_kernel<EQ, BLOCK, true>;
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixed + tab_bytes)));
+        k<<<grid, BLOCK, fixed + tab_bytes, st>>>(a);
+    } else {
+        auto k = trace_kernel<EQ, BLOCK, false>;     // table too large for shared memory: read it through L1/L2
+        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fixed));
+        k<<<grid, BLOCK, fixed, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    return GEOAC_OK;
+}
+
+static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
+                         double* d_rec, int32_t* d_status, int32_t* d_n_steps, cudaStream_t st) {
+    if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");
+    int rc = refresh_consts(ctx);
+    if (rc) return rc;
+    if (st != ctx->stream) {       // consts were written on ctx->stream: order the caller's stream after it
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(cudaStreamWaitEvent(st, ctx->ev0, 0));
+    }
+    const int n_rec = ctx->prm.bounces + 1;
+    const int64_t n_slots = n_rays * n_rec;
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(d_rec, 0, sizeof(double) * GEOAC_NFIELDS * n_slots, st));
+    CK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_slots, st));
+    CK(cudaMemsetAsync(d_n_steps, 0, sizeof(int32_t) * n_slots, st));
+    TraceArgs a;
+    a.table = ctx->d_table; a.table_n = ctx->n; a.table_npad = ctx->n_pad; a.table_xmin = ctx->xmin; a.table_xmax = ctx->xmax;
+    a.consts = ctx->d_consts; a.theta = d_theta; a.phi = d_phi; a.n_rays = n_rays; a.n_rec = n_rec;
+    a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
+    a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1;
+    const bool amp = ctx->prm.calc_amp != 0;
+    switch (ctx->variant) {
+        case GEOAC_2D:     return amp ? launch_trace<Eq2D<true>, 512>(ctx, a, st)     : launch_trace<Eq2D<false>, 512>(ctx, a, st);
+        case GEOAC_3D:     return amp ? launch_trace<Eq3D<true>, 256>(ctx, a, st)     : launch_trace<Eq3D<false>, 512>(ctx, a, st);
+#ifdef GEOAC_HAVE_GLOBAL
+        case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 256>(ctx, a, st) : launch_trace<EqGlobal<false>, 256>(ctx, a, st);
+#endif
+    }
+    return fail(ctx, GEOAC_ERR_BAD_ARG, "variant not implemented");
+}
+
+extern "C" int geoac_trace_device(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
+                                  double* d_rec, int32_t* d_status, int32_t* d_n_steps, void* cuda_stream) {
+    if (!ctx || n_rays < 0) return GEOAC_ERR_BAD_ARG;
+    if (n_rays == 0) return GEOAC_OK;
+    cudaSetDevice(ctx->device);
+    return enqueue_trace(ctx, n_rays, d_theta, d_phi, d_rec, d_status, d_n_steps, (cudaStream_t)cuda_stream);
+}
+
+extern "C" int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                           double* rec, int32_t* status, int32_t* n_steps) {
+    if (!ctx || n_rays < 0 || (n_rays > 0 && (!theta || !phi || !rec || !status || !n_steps))) return GEOAC_ERR_BAD_ARG;
+    if (n_rays == 0) return GEOAC_OK;
+    cudaSetDevice(ctx->device);
+    const int n_rec = ctx->prm.bounces + 1;
+    const int64_t n_slots = n_rays * n_rec;
+    if (n_rays > ctx->cap_rays) {
+        cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); ctx->d_theta = ctx->d_phi = nullptr; ctx->cap_rays = 0;
+        CK(cudaMalloc(&ctx->d_theta, sizeof(double) * n_rays)); CK(cudaMalloc(&ctx->d_phi, sizeof(double) * n_rays));
+        ctx->cap_rays = n_rays;
+    }
+    if (n_slots > ctx->cap_slots) {
+        cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
+        ctx->d_rec = nullptr; ctx->d_status = ctx->d_nsteps = nullptr; ctx->cap_slots = 0;
+        CK(cudaMalloc(&ctx->d_rec, sizeof(double) * GEOAC_NFIELDS * n_slots));
+        CK(cudaMalloc(&ctx->d_status, sizeof(int32_t) * n_slots)); CK(cudaMalloc(&ctx->d_nsteps, sizeof(int32_t) * n_slots));
+        ctx->cap_slots = n_slots;
+    }
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemcpyAsync(ctx->d_theta, theta, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_phi, phi, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
+    int rc = refresh_consts(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, st));
+    rc = enqueue_trace(ctx, n_rays, ctx->d_theta, ctx->d_phi, ctx->d_rec, ctx->d_status, ctx->d_nsteps, st);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(rec, ctx->d_rec, sizeof(double) * GEOAC_NFIELDS * n_slots, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, ctx->d_status, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_steps, ctx->d_nsteps, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, st));
+    unsigned long long cnt[2] = { 0, 0 };
+    CK(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms; ctx->last_steps = (int64_t)cnt[1];
+    return GEOAC_OK;
+}
+
+extern "C" int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_ms) {
+    if (!ctx) return GEOAC_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    unsigned long long cnt[2] = { 0, 0 };
+    CK(cudaMemcpy(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost));   // also valid after geoac_trace_device + sync
+    ctx->last_steps = (int64_t)cnt[1];
+    if (total_steps) *total_steps = ctx->last_steps;
+    if (kernel_ms) *kernel_ms = ctx->last_ms;
+    return GEOAC_OK;
+}
+
+// ---- Load_G2S: Code/Atmo/G2S_Spline1D.cpp:109-142 (Cartesian), G2S_GlobalSpline1D.cpp:113-152 (Global taper arithmetic) ----
+extern "C" int geoac_load_met_1d(const char* path, const char* format, double z_grnd_taper, int global_taper,
+                                 int cap, int* n, double* z, double* T, double* u, double* v, double* rho) {
+    if (!path || !format || !n || !z || !T || !u || !v || !rho) return GEOAC_ERR_BAD_ARG;
+    int fmt = !std::strncmp(format, "zTuvdp", 6) ? 0 : (!std::strncmp(format, "zuvwTdp", 7) ? 1 : -1);
+    if (fmt < 0) return GEOAC_ERR_BAD_ARG;
+    FILE* f = std::fopen(path, "r");
+    if (!f) return GEOAC_ERR_IO;
+    // file_length(): number of newline-terminated rows (G2S_Spline1D.cpp:53-71)
+    long rows = 0; for (int ch; (ch = std::fgetc(f)) != EOF;) if (ch == '\n') rows++;
+    std::rewind(f);
+    int cnt = 0; double tmp, tmp2;
+    while (cnt < cap && cnt < rows) {
+        int got = fmt == 0 ? std::fscanf(f, "%lf %lf %lf %lf %lf %lf", &z[cnt], &T[cnt], &u[cnt], &v[cnt], &rho[cnt], &tmp)
+                           : std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf", &z[cnt], &u[cnt], &v[cnt], &tmp, &T[cnt], &rho[cnt], &tmp2);
+        if (got != (fmt == 0 ? 6 : 7)) break;
+        double arg;
+        if (global_taper) { const double r = z[cnt] + kREarth; arg = -(r - kREarth - z_grnd_taper) / 0.2; }
+        else arg = -(z[cnt] - z_grnd_taper) / 0.2;
+        u[cnt] *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;      // m/s -> km/s and ground taper (App. A-10)
+        v[cnt] *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
+        cnt++;
+    }
+    std::fclose(f);
+    *n = cnt;
+    return cnt >= 3 ? GEOAC_OK : GEOAC_ERR_IO;
+}
+
+// ---- FP64 roofline denominator: dependent-chain-free DFMA loop, 8 independent accumulators per thread ----
+__global__ void dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-9, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0, x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+extern "C" double geoac_measure_fp64_peak(geoac_ctx* ctx, double* out_ms) {
+    if (!ctx) return -1.0;
+    cudaSetDevice(ctx->device);
+    const int block = 512, grid = ctx->sm_count * 4, iters = 4096;
+    double* d = nullptr;
+    if (cudaMalloc(&d, sizeof(double) * block * grid) != cudaSuccess) return -1.0;
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        dfma_peak_kernel<<<grid, block, 0, ctx->stream>>>(d, iters, 0.999999, 1e-7);
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        float ms = 0; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    if (out_ms) *out_ms = best;
+    const double flops = 2.0 * 64.0 * (double)iters * (double)block * (double)grid;
+    return flops / (best * 1e-3) / 1e12;
+}

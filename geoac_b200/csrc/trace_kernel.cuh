@@ -1,0 +1,209 @@
+// trace_kernel.cuh -- the persistent one-thread-per-ray RK4 kernel, generic over the equation set.
+//
+// Replaces, for a whole batch of launch angles, the body of the reference's `-prop` loops
+// (Code/GeoAc3D_main.cpp:226-304 and siblings) including GeoAc_Propagate_RK4 (Code/GeoAc/GeoAc.Solver.cpp:12-72).
+//
+// Design (B200-first, not a translation):
+//  * ONE resident CTA per SM; the spline table is pulled into shared memory by a single TMA bulk copy
+//    (cp.async.bulk + mbarrier) and stays there for the life of the kernel.
+//  * a lane owns one ray at a time and advances it by exactly ONE RK4 step (+ its travel-time / absorption
+//    segment) per trip round a flat loop, so all lanes of a warp execute the same instruction stream no matter how
+//    far along their rays are.  Bounces / arrivals / breaks are handled in a rare divergent tail of the trip.
+//  * finished lanes are refilled at the top of the trip: a warp ballot counts the idle lanes, one lane claims that
+//    many ray indices from a global counter with a single atomicAdd, the indices are handed out by lane rank.
+//  * only three states are ever needed (k-2, k-1, k): y_k and y_{k+1} live in registers, y_{k-1} is parked in a
+//    per-thread shared-memory column (conflict-free [eq][thread] layout).  The reference stores 500 000 x EqCnt.
+//  * RK4 combination in the reference's association order  y + k1/6 + k2/3 + k3/3 + k4/6  (Solver.cpp:54), built
+//    on the fly so no k_i is kept.
+#pragma once
+#include "core.cuh"
+
+namespace geoac {
+
+struct TraceArgs {
+    const double* table;        // global copy of the table (TAB_NARR * n_pad doubles, 16-byte aligned)
+    int table_n, table_npad;
+    double table_xmin, table_xmax;
+    const LaunchConsts* consts; // device
+    const double* theta;        // [n_rays]
+    const double* phi;
+    int64_t n_rays;
+    int n_rec;                  // bounces + 1
+    double* rec;                // [GEOAC_NFIELDS][n_rays*n_rec]
+    int32_t* status;            // [n_rays*n_rec]
+    int32_t* n_steps;
+    unsigned long long* counter;      // next unclaimed ray
+    unsigned long long* total_steps;  // RK4 steps taken (all rays)
+};
+
+#ifdef __CUDACC__
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// stage `bytes` (multiple of 16) from global to shared with one TMA bulk copy issued by thread 0
+__device__ __forceinline__ void tma_stage_table(double* dst, const double* src, uint32_t bytes, uint64_t* bar) {
+    const uint32_t bar_a = smem_u32(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // the mbarrier transaction count is limited to 2^20-1 bytes: issue in chunks, all against the same phase
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        uint32_t off = 0;
+        while (off < bytes) {
+            uint32_t chunk = min(bytes - off, 65536u);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_u32((const char*)dst + off)), "l"((const char*)src + off), "r"(chunk), "r"(bar_a)
+                         : "memory");
+            off += chunk;
+        }
+    }
+    // everyone waits for phase 0 to complete
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar_a) : "memory");
+    }
+}
+
+template <class EQ, int BLOCK, bool TABLE_IN_SMEM>
+__global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const TraceArgs a) {
+    constexpr int NEQ = EQ::NEQ;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    // layout: [LaunchConsts][mbarrier][prev: NEQ*BLOCK doubles][table]
+    LaunchConsts* Ls = reinterpret_cast<LaunchConsts*>(smem_raw);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(LaunchConsts) + 15) / 16) * 16);
+    double* prev = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bar) + 16);
+    double* tab_s = prev + NEQ * BLOCK;
+
+    for (int i = threadIdx.x; i < (int)(sizeof(LaunchConsts) / 8); i += BLOCK)
+        reinterpret_cast<double*>(Ls)[i] = reinterpret_cast<const double*>(a.consts)[i];
+    Table1D T;
+    T.n = a.table_n; T.n_pad = a.table_npad; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
+    if (TABLE_IN_SMEM) {
+        tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_npad * sizeof(double)), bar);
+        T.base = tab_s;
+    } else {
+        T.base = a.table;
+    }
+    __syncthreads();
+    const LaunchConsts& L = *Ls;
+
+    const unsigned lane = threadIdx.x & 31;
+    double* myprev = prev + threadIdx.x;                 // element i at myprev[i*BLOCK]
+    const int64_t n_slots = a.n_rays * a.n_rec;
+    const int step_cap = L.step_limit - 1;              // RK4 loop bound of Solver.cpp:25
+
+    // per-lane ray state
+    double y[NEQ];
+    typename EQ::RayC rc;
+    int cur = 0;
+    int64_t ray = -1;
+    int bounce = 0, ksteps = 0;
+    double tt_total = 0.0, att_total = 0.0, tt_b = 0.0, att_b = 0.0, zmax = 0.0;
+    bool have_ray = false, exhausted = false;
+    unsigned long long my_steps = 0;
+
+    while (true) {
+        // ---------------- refill idle lanes (warp-aggregated claim) ----------------
+        const bool want = !have_ray && !exhausted;
+        const unsigned wmask = __ballot_sync(0xffffffffu, want);
+        if (wmask) {
+            unsigned long long base = 0;
+            const int leader = __ffs(wmask) - 1;
+            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(wmask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                const int64_t idx = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
+                if (idx < a.n_rays) {
+                    ray = idx; have_ray = true; bounce = 0; ksteps = 0; cur = 0;
+                    tt_total = att_total = tt_b = att_b = zmax = 0.0;
+                    EQ::init(L, T, a.theta[idx], a.phi[idx], rc, y, cur);
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have_ray)) break;
+
+        if (have_ray) {
+            // ---------------- one RK4 step ----------------
+            zmax = fmax(zmax, EQ::altitude(y));        // running turning height over m < k (App. A-3)
+            const double ds = EQ::step_size(L, y);
+            double acc[NEQ], p[NEQ], f[NEQ];
+#pragma unroll
+            for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = y[i]; }
+#pragma unroll 1
+            for (int s = 0; s < 4; s++) {
+                EQ::rhs(L, T, rc, p, f, cur);
+                const double wa = (s == 2) ? 1.0 : 0.5;
+                const double wb = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+#pragma unroll
+                for (int i = 0; i < NEQ; i++) {
+                    const double k = ds * f[i];
+                    acc[i] += k * wb;
+                    p[i] = y[i] + k * wa;
+                }
+            }
+            ksteps++; my_steps++;
+            // ---------------- travel time + absorption of the segment y -> acc ----------------
+            double dtt, datt;
+            EQ::segment(L, T, rc, y, acc, cur, dtt, datt);
+            const bool brk = EQ::left_region(L, acc);                    // BreakCheck first (Solver.cpp:57-64)
+            const bool gnd = !brk && EQ::below_ground(L, acc);
+            const bool lim = !brk && !gnd && (ksteps >= step_cap);
+            if (L.seg_mode) { if (!(brk || gnd || lim)) { tt_total += dtt; att_total += datt; } }
+            else            { tt_b += dtt; att_b += datt; }
+
+            if (brk || gnd || lim) {
+                // ---------------- rare tail: end of a bounce segment ----------------
+                const int64_t slot = ray * a.n_rec + bounce;
+                if (!gnd) {
+                    a.status[slot] = brk ? GEOAC_ST_BREAK : GEOAC_ST_LIMIT;
+                    a.n_steps[slot] = brk ? ksteps : L.step_limit;
+                    have_ray = false;
+                } else {
+                    if (!L.seg_mode) { tt_total += tt_b; att_total += att_b; tt_b = 0.0; att_b = 0.0; }
+                    double ym2[NEQ];
+#pragma unroll
+                    for (int i = 0; i < NEQ; i++) ym2[i] = myprev[i * BLOCK];
+                    double amp, incl, baz, aux, margin;
+                    EQ::arrival(L, T, rc, y, acc, tt_total, cur, amp, incl, baz, aux, margin);
+#pragma unroll
+                    for (int i = 0; i < NEQ; i++) a.rec[(int64_t)i * n_slots + slot] = acc[i];
+                    a.rec[(int64_t)GEOAC_F_TRAVELTIME * n_slots + slot] = tt_total;
+                    a.rec[(int64_t)GEOAC_F_ATTEN * n_slots + slot] = att_total;
+                    a.rec[(int64_t)GEOAC_F_TURNHEIGHT * n_slots + slot] = zmax;
+                    a.rec[(int64_t)GEOAC_F_AMPLITUDE * n_slots + slot] = amp;
+                    a.rec[(int64_t)GEOAC_F_INCLINATION * n_slots + slot] = incl;
+                    a.rec[(int64_t)GEOAC_F_BACKAZ * n_slots + slot] = baz;
+                    a.rec[(int64_t)GEOAC_F_AUX * n_slots + slot] = aux;
+                    a.rec[(int64_t)GEOAC_F_MARGIN * n_slots + slot] = margin;
+                    a.status[slot] = GEOAC_ST_ARRIVAL;
+                    a.n_steps[slot] = ksteps;
+                    if (bounce < L.bounces) {
+                        double y0[NEQ];
+                        EQ::reflect(L, T, rc, ym2, y, acc, y0, cur);
+#pragma unroll
+                        for (int i = 0; i < NEQ; i++) y[i] = y0[i];
+                        bounce++; ksteps = 0;
+                        if (L.per_bounce_zmax) zmax = 0.0;
+                    } else {
+                        have_ray = false;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < NEQ; i++) { myprev[i * BLOCK] = y[i]; y[i] = acc[i]; }
+            }
+        }
+    }
+    // one atomic per warp for the step count
+    for (int o = 16; o > 0; o >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, o);
+    if (lane == 0 && my_steps) atomicAdd(a.total_steps, my_steps);
+}
+
+#endif  // __CUDACC__
+}  // namespace geoac

@@ -1,0 +1,76 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds for sm_100a, loads, exports every symbol declared in
+include/geoac_b200.h, and REFUSES to run without a B200 (no CPU fallback).  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from geoac_b200 import abi, api
+from tests import util
+
+HDR = os.path.join(util.ROOT, "include", "geoac_b200.h")
+
+
+def declared_symbols():
+    txt = open(HDR).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(geoac_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(api.EXPORTED_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    lib = C.CDLL(built_lib)
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/geoac_b200.h but not exported"
+
+
+def test_params_struct_layout_matches_header():
+    # 15 doubles + 4 int32 = 136 bytes, no padding
+    assert C.sizeof(abi.GeoacParams) == 15 * 8 + 4 * 4
+    p = api.default_params(abi.GEOAC_GLOBAL) if os.path.exists(api.library_path()) else None
+    if p is not None:
+        assert p.ray_limit == 10000.0 and p.ds_min == 0.001 and p.bounces == 2 and p.calc_amp == 1
+        assert abs(p.src[1] - 30.0 * util.PI / 180.0) < 1e-15
+
+
+def test_defaults_match_reference_parameters(built_lib):
+    p2, p3 = api.default_params(abi.GEOAC_2D), api.default_params(abi.GEOAC_3D)
+    assert (p3.ds_min, p3.ds_max, p3.ray_limit) == (0.001, 0.5, 5000.0)       # GeoAc.Parameters.cpp:20-24
+    assert p2.accum_per_segment == 1 and p3.accum_per_segment == 0
+    assert (p3.freq, p3.tweak_abs, p3.z_grnd) == (0.1, 0.3, 0.0)
+    for v, (a, n) in {abi.GEOAC_2D: (6, 3), abi.GEOAC_3D: (12, 4), abi.GEOAC_GLOBAL: (18, 6)}.items():
+        assert api.lib().geoac_eq_count(v, 1) == a and api.lib().geoac_eq_count(v, 0) == n
+
+
+def test_host_loader_matches_oracle_loader(built_lib, oracle):
+    for glob in (False, True):
+        a = api.load_met_1d(util.TOY, global_taper=glob)
+        b = oracle.load_met_1d(util.TOY, global_taper=glob)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+    assert len(a[0]) == 1400
+
+
+def test_prop_angles_reproduce_the_mains_loops():
+    th_deg, ph_deg, th, ph = api.prop_angles(0.5, 45.0, 0.5, -90.0, -90.0, 1.0)       # GeoAc2D defaults: 90 rays
+    assert len(th) == 90 and th_deg[0] == 0.5 and ph_deg[0] == -90.0
+    d, _ = util.load_case("2d_config1")
+    assert np.array_equal(th_deg, d["theta_deg"])
+    # config 2 grid: 60 x 3600
+    th_deg, ph_deg, _, _ = api.prop_angles(1, 60.5, 1, 0, 359.95, 0.1)
+    assert len(th_deg) == 60 * 3600
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the library must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(api.GeoAcError) as e:
+        api.Tracer(abi.GEOAC_3D, 0)
+    assert "no CUDA device" in str(e.value) or "failed (1)" in str(e.value)

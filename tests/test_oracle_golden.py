@@ -1,0 +1,44 @@
+"""CPU tests: the C oracle (oracle/liboracle.so) must reproduce the committed golden vectors -- which were dumped from
+the unmodified reference by tests/golden/make_golden.py -- BIT FOR BIT.  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from geoac_b200 import abi
+from tests import util
+
+
+def _run_oracle(po, name):
+    d, kv = util.load_case(name)
+    variant = int(d["variant"])
+    z, T, u, v, rho = po.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+    at = po.atmo1d(util.is_global(variant), z, T, u, v, rho)
+    p = util.apply_keys(variant, po.default_params(variant, at), kv)
+    th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
+    return d, variant, p, po.trace(variant, at, p, th, ph)
+
+
+@pytest.mark.parametrize("name", [c for c in util.golden_cases() if not c.startswith(("3drngdep", "globalrngdep"))])
+def test_oracle_bit_exact_vs_reference(oracle, name):
+    d, variant, p, out = _run_oracle(oracle, name)
+    assert np.array_equal(out["status"], d["status"])
+    assert np.array_equal(out["n_steps"], d["n_steps"])
+    neq = abi.eq_count(variant, p.calc_amp)
+    exact = list(range(neq)) + [abi.F_TRAVELTIME, abi.F_ATTEN, abi.F_TURNHEIGHT, abi.F_AMPLITUDE, abi.F_MARGIN, abi.F_AUX]
+    if variant != abi.GEOAC_2D:
+        exact.append(abi.F_INCLINATION)
+    for f in exact:
+        assert np.array_equal(out["rec"][f], d["rec"][f]), f"field {f} not bit-identical to the reference"
+    # inclination (2D) / back azimuth (3D) are echoes of the launch angles that the mains print from their degree loop
+    # variables; through the radian ABI they round-trip to within an ulp or two
+    for f in (abi.F_INCLINATION, abi.F_BACKAZ):
+        assert np.allclose(out["rec"][f], d["rec"][f], rtol=1e-13, atol=1e-12)
+
+
+def test_golden_has_reference_invariants():
+    """Sanity of the fixtures themselves: stratified reciprocity (2-D bounce ranges r_n ~ (n+1) r_0)."""
+    d, _ = util.load_case("2d_config1")
+    ok = (d["status"] == abi.ST_ARRIVAL).all(axis=1)
+    r = d["rec"][0][ok]
+    assert ok.sum() > 50
+    assert np.allclose(r[:, 1] / r[:, 0], 2.0, rtol=2e-3)
+    assert np.allclose(r[:, 2] / r[:, 0], 3.0, rtol=2e-3)

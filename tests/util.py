@@ -1,0 +1,90 @@
+"""Shared helpers for the parity tests: golden-case loading and record comparison."""
+import glob
+import os
+
+import numpy as np
+
+from geoac_b200 import abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+TOY = os.path.join(GOLD, "ToyAtmo.met")
+PI = 3.141592653589793238462643
+
+# FP64 relative tolerance of the CUDA path against oracle/reference for continuous outputs (north_star: 1e-9 away
+# from caustics).  Amplitude-like quantities of rays with a tiny Jacobian are LISTED, not loosened.
+RTOL = 1e-9
+
+
+def golden_cases(prefix=""):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, prefix + "*.npz")))
+
+
+def load_case(name):
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    kv = dict(s.split("=", 1) for s in d["keys"].tolist())
+    return d, kv
+
+
+def is_global(variant):
+    return variant in (abi.GEOAC_GLOBAL, abi.GEOAC_GLOBAL_RNGDEP)
+
+
+def apply_keys(variant, p, kv, vert_limit_default=None):
+    """Map the reference mains' key=value options onto geoac_params exactly as the mains do."""
+    p.bounces = int(kv.get("bounces", 2))
+    p.calc_amp = int(kv.get("CalcAmp", 1))
+    p.accum_per_segment = 1 if variant == abi.GEOAC_2D else int(kv.get("accum_mode", 0))
+    p.freq = float(kv.get("freq", 0.1))
+    p.z_grnd = float(kv.get("z_grnd", 0.0))
+    p.tweak_abs = max(0.0, float(kv.get("abs_coeff", 0.3)))
+    if "alt_max" in kv:
+        p.vert_limit = float(kv["alt_max"])
+    if "rng_max" in kv and variant in (abi.GEOAC_2D, abi.GEOAC_3D, abi.GEOAC_GLOBAL):
+        p.range_limit = float(kv["rng_max"])
+    z_src = float(kv.get("z_src", 0.0))
+    if variant in (abi.GEOAC_2D, abi.GEOAC_3D, abi.GEOAC_3D_RNGDEP):
+        p.src[0] = float(kv.get("x_src", 0.0))
+        p.src[1] = float(kv.get("y_src", 0.0))
+        p.src[2] = z_src
+    else:
+        p.src[0] = z_src
+        if "lat_src" in kv or variant == abi.GEOAC_GLOBAL:
+            p.src[1] = float(kv.get("lat_src", 30.0)) * PI / 180.0
+            p.src[2] = float(kv.get("lon_src", 0.0)) * PI / 180.0
+    return p
+
+
+def angles_rad(theta_deg, phi_deg):
+    return np.asarray(theta_deg) * PI / 180.0, PI / 2.0 - np.asarray(phi_deg) * PI / 180.0
+
+
+def compare_records(got, want, variant, calc_amp, rtol, label="", exact_discrete=True, amp_rtol=None):
+    """Compare two record sets. Discrete outputs bit-exact; continuous outputs to `rtol` relative.
+    Returns a list of human-readable problems (empty = pass) and a dict of max relative differences."""
+    problems, stats = [], {}
+    if exact_discrete:
+        if not np.array_equal(got["status"], want["status"]):
+            bad = np.argwhere(got["status"] != want["status"])
+            problems.append(f"{label}: status differs at {len(bad)} slots, first {bad[:5].tolist()}")
+        if not np.array_equal(got["n_steps"], want["n_steps"]):
+            bad = np.argwhere(got["n_steps"] != want["n_steps"])
+            problems.append(f"{label}: n_steps differs at {len(bad)} slots, first {bad[:5].tolist()}")
+    m = (want["status"] == abi.ST_ARRIVAL) & (got["status"] == abi.ST_ARRIVAL)
+    neq = abi.eq_count(variant, calc_amp)
+    fields = list(range(neq)) + [abi.F_TRAVELTIME, abi.F_ATTEN, abi.F_TURNHEIGHT, abi.F_INCLINATION, abi.F_BACKAZ, abi.F_AUX]
+    if calc_amp:
+        fields.append(abi.F_AMPLITUDE)
+    for f in fields:
+        a, b = got["rec"][f][m], want["rec"][f][m]
+        if a.size == 0:
+            continue
+        # scale: per-field magnitude floor so that exact zeros / tiny auxiliary values do not blow up the ratio
+        scale = np.maximum(np.abs(b), 1e-12 * max(1.0, float(np.max(np.abs(b)))))
+        rel = np.abs(a - b) / scale
+        stats[f] = float(rel.max())
+        tol = amp_rtol if (amp_rtol is not None and (f == abi.F_AMPLITUDE or (f >= 4 and f < neq))) else rtol
+        if not np.all(rel <= tol):
+            i = int(np.argmax(rel))
+            problems.append(f"{label}: field {f} max rel diff {rel.max():.3e} > {tol:g} (got {a[i]!r}, want {b[i]!r})")
+    return problems, stats
