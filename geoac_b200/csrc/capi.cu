@@ -182,33 +182,9 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int, int, int, const doub
 __global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, const double* table, int n, int n_pad,
                                     double xmin, double xmax, int variant) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    LaunchConsts L = in;
     Table1D T; T.base = table; T.n = n; T.n_pad = n_pad; T.xmin = xmin; T.xmax = xmax;
-    const bool glob = (variant == GEOAC_GLOBAL);
-    int cur = 0;
-    auto sample = [&](double x, double& c, double& u, double& v, double& rho, double& dc, double& du, double& dv) {
-        const SegPos sp = seg_locate(T, clampd(x, xmin, xmax), cur);
-        double Tv, dT, ddT, d2;
-        spl_f2(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT, ddT);
-        spl_f2(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du, d2);
-        spl_f2(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv, d2);
-        rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
-        c = sqrt(kGamR * Tv);
-        dc = kGamR / (2.0 * c) * dT;
-    };
-    double c, u, v, rho, dc, du, dv;
-    L.ground = glob ? kREarth + L.z_grnd : L.z_grnd;
-    const double x_src = glob ? L.src[0] + kREarth : L.src[2];
-    sample(x_src, c, u, v, rho, dc, du, dv);
-    L.c_src = c; L.u_src = u; L.v_src = v; L.rho_src = rho;
-    sample(0.0, c, u, v, rho, dc, du, dv);
-    L.c_000 = c;
-    sample(L.ground, c, u, v, rho, dc, du, dv);
-    L.c_gnd = c; L.rho_gnd = rho; L.dc_gnd = dc; L.du_gnd = du; L.dv_gnd = dv;
-    // Sutherland-Bass reference state: c,rho at (0,0,z_grnd) (Cartesian, Absorption.cpp:33-34) or at r = z_grnd,
-    // i.e. clamped to the lowest level (Global, Absorption.Global.cpp:31-32)
-    sample(glob ? L.z_grnd : L.z_grnd, c, u, v, rho, dc, du, dv);
-    suthbass_setup(L, c, rho);
+    LaunchConsts L = in;
+    fill_launch_consts_1d(L, T, variant);
     *out = L;
 }
 

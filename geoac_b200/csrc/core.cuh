@@ -152,11 +152,11 @@ GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double 
 
     const double z2 = z * z, z3 = z2 * z, z4 = z2 * z2, z5 = z4 * z;
     double X0, X1, X3, X4, X5, X6;
-    const double X2 = 3.9994457341391493e-04;                              // 10^-3.3979
+    const double X2 = 0.00040003685104612505;                              // 10^-3.3979
     if (z > 90.) X0 = g_exp10(49.296 - (1.5524 * z) + (1.8714E-2 * z2) - (1.1069E-4 * z3) + (3.199E-7 * z4) - (3.6211E-10 * z5));
-    else         X0 = 0.20947510246588891;                                 // 10^-0.67887
+    else         X0 = 0.20947393930547747;                                 // 10^-0.67887
     if (z > 76.) X1 = g_exp10((1.3972E-1) - (5.6269E-3 * z) + (3.9407E-5 * z2) - (1.0737E-7 * z3));
-    else         X1 = 0.78083647687505061;                                 // 10^-0.10744
+    else         X1 = 0.780836309209143;                                   // 10^-0.10744
     if (z > 80.) X3 = g_exp10(-4.234 - (3.0975E-2 * z));
     else         X3 = g_exp10(-19.027 + (1.3093 * z) - (4.6496E-2 * z2) + (7.8543E-4 * z3) - (6.5169E-6 * z4) + (2.1343E-8 * z5));
     if (z > 95.) X4 = g_exp10(-3.2456 + (4.6642E-2 * z) - (2.6894E-4 * z2) + (5.264E-7 * z3));
@@ -170,8 +170,8 @@ GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double 
     const double Zr0 = 54.1 * exp(-17.3 * cb), Zr1 = 63.3 * exp(-16.7 * cb);
     const double Z_rot_ = (Zr0 * Zr1) / (X1 * Zr0 + X0 * Zr1);             // 1/(X1/Zr1 + X0/Zr0)
 
-    const double sigma = 1.0910894511799618;                               // 5/sqrt(21)
-    const double nn = 0.52372293656638159 * Z_rot_;                        // (4/5) sqrt(3/7) Z_rot_
+    const double sigma = 1.091089451179962;                                // 5/sqrt(21)
+    const double nn = 0.5237229365663817 * Z_rot_;                         // (4/5) sqrt(3/7) Z_rot_
     const double chi = 0.75 * nn * nu;
     const double cchi = 2.36 * chi;
 

@@ -101,7 +101,7 @@ struct Eq3D {
     }
 
     // BreakCheck / GroundCheck, 3DStratified.cpp:327-343 (strict inequalities on the unclamped state)
-    GEOAC_HD static bool left_region(const LaunchConsts& L, const double* y) {
+    GEOAC_HD static bool left_region(const LaunchConsts& L, const RayC&, const double* y) {
         const double r2 = y[0] * y[0] + y[1] * y[1];
         return (y[2] > L.vert_limit) || (sqrt(r2) > L.range_limit);
     }
@@ -240,7 +240,7 @@ struct Eq2D {
         }
     }
 
-    GEOAC_HD static bool left_region(const LaunchConsts& L, const double* y) {   // 2DStratified.cpp:194-203
+    GEOAC_HD static bool left_region(const LaunchConsts& L, const RayC&, const double* y) {   // 2DStratified.cpp:194-203
         return (y[1] > L.vert_limit) || (y[0] > L.range_limit);
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[1] < L.z_grnd; }

@@ -1,0 +1,58 @@
+// tests/host_emul/host_emul.cpp -- TEST-ONLY debugging aid (never part of libgeoac_b200.so, never a fallback).
+// Compiles the per-ray state machine of geoac_b200/csrc (Lane<EQ>::advance and the equation sets, all GEOAC_HD) with
+// g++ so that the de-duplicated device math can be checked against the oracle in the build container, where there
+// is no GPU.  The real parity gate is tests/test_gpu_parity.py on a B200.
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <algorithm>
+#include "../../geoac_b200/csrc/core.cuh"
+#include "../../geoac_b200/csrc/eq_cartesian.cuh"
+#if __has_include("../../geoac_b200/csrc/eq_global.cuh")
+#include "../../geoac_b200/csrc/eq_global.cuh"
+#define HAVE_GLOBAL 1
+#endif
+#include "../../geoac_b200/csrc/trace_kernel.cuh"
+
+using namespace geoac;
+
+template <class EQ>
+static long run(const LaunchConsts& L, const Table1D& T, long n, const double* th, const double* ph, RecOut o) {
+    long steps = 0;
+    std::vector<double> prev(EQ::NEQ, 0.0);
+    for (long i = 0; i < n; i++) {
+        Lane<EQ> ln;
+        ln.start(L, T, i, th[i], ph[i]);
+        while (ln.advance(L, T, prev.data(), 1, o)) steps++;
+        steps++;
+    }
+    return steps;
+}
+
+extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, int n_pad, const double* table, long n_rays,
+                              const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps) {
+    Table1D T; T.base = table; T.n = n; T.n_pad = n_pad; T.xmin = table[TAB_X * n_pad]; T.xmax = table[TAB_X * n_pad + n - 1];
+    LaunchConsts L; std::memset(&L, 0, sizeof L);
+    L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
+    L.z_grnd = p->z_grnd; L.tweak_abs = p->tweak_abs; L.freq = p->freq;
+    for (int i = 0; i < 2; i++) { L.box_min[i] = p->box_min[i]; L.box_max[i] = p->box_max[i]; }
+    for (int i = 0; i < 3; i++) L.src[i] = p->src[i];
+    if (variant == GEOAC_2D || variant == GEOAC_3D) L.src[2] = std::max(p->z_grnd, p->src[2]); else L.src[0] = std::max(p->z_grnd, p->src[0]);
+    L.bounces = p->bounces; L.calc_amp = p->calc_amp;
+    L.seg_mode = (variant == GEOAC_2D) ? 1 : (p->accum_per_segment ? 1 : 0);
+    L.step_limit = (int)(p->ray_limit * (int)(1.0 / (p->ds_min * 10)));
+    L.per_bounce_zmax = 0;
+    fill_launch_consts_1d(L, T, variant);
+    RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
+    std::fill(rec, rec + (size_t)GEOAC_NFIELDS * o.n_slots, 0.0);
+    std::fill(status, status + o.n_slots, 0); std::fill(n_steps, n_steps + o.n_slots, 0);
+    const bool amp = p->calc_amp != 0;
+    switch (variant) {
+        case GEOAC_2D: return amp ? run<Eq2D<true>>(L, T, n_rays, th, ph, o) : run<Eq2D<false>>(L, T, n_rays, th, ph, o);
+        case GEOAC_3D: return amp ? run<Eq3D<true>>(L, T, n_rays, th, ph, o) : run<Eq3D<false>>(L, T, n_rays, th, ph, o);
+#ifdef HAVE_GLOBAL
+        case GEOAC_GLOBAL: return amp ? run<EqGlobal<true>>(L, T, n_rays, th, ph, o) : run<EqGlobal<false>>(L, T, n_rays, th, ph, o);
+#endif
+    }
+    return -1;
+}
