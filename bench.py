@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 TOY = os.path.join(ROOT, "tests", "golden", "ToyAtmo.met")
 # ALGORITHMIC FP64 operations per RK4 step (de-duplicated, CalcAmp on, incl. travel-time + absorption bookkeeping);
 # convention and derivation in DESIGN.md section "flop counting" (add/sub/mul/div/sqrt/transcendental = 1, fma = 2)
-ALGO_FLOPS_PER_STEP = {"config2": 2200.0, "config1": 1400.0, "smallgrid": 2200.0}
+ALGO_FLOPS_PER_STEP = {"config2": 2200.0, "config1": 1400.0, "smallgrid": 2200.0, "midgrid": 2200.0}
 
 
 def workload_angles(name, rank=0):
@@ -34,6 +34,8 @@ def workload_angles(name, rank=0):
         grid = (1.0, 60.5, 1.0, 0.0, 359.95, 0.1)
     elif name == "smallgrid":
         grid = (1.0, 60.5, 1.0, 0.0, 359.5, 5.0)
+    elif name == "midgrid":
+        grid = (1.0, 60.5, 1.0, 0.0, 359.75, 0.5)
     elif name == "config1":
         grid = (0.5, 45.0, 0.5, -90.0, -90.0, 1.0)
     else:
@@ -168,7 +170,8 @@ def run_reference_arm(args):
 def workload_desc(name):
     return {"config2": "BASELINE config 2: GeoAc3D stratified, ToyAtmo.met, theta 1..60 step 1 x azimuth 0..359.9 step 0.1 (216000 rays), bounces=2, CalcAmp on, WriteRays=False",
             "config1": "BASELINE config 1: GeoAc2D, ToyAtmo.met, theta 0.5..45 step 0.5, azimuth -90 (90 rays), bounces=2",
-            "smallgrid": "reduced grid for debugging: GeoAc3D, theta 1..60 x azimuth 0..355 step 5 (4320 rays)"}[name]
+            "smallgrid": "reduced grid for debugging: GeoAc3D, theta 1..60 x azimuth 0..355 step 5 (4320 rays)",
+            "midgrid": "reduced grid for ncu captures: GeoAc3D, theta 1..60 x azimuth 0..359.5 step 0.5 (43200 rays)"}[name]
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -311,7 +314,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "smallgrid"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "smallgrid", "midgrid"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

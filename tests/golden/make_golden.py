@@ -27,6 +27,11 @@ CASES = {
     "3d_sub": (abi.GEOAC_3D, [TOY], dict(theta_min=1, theta_max=60.5, theta_step=4, phi_min=-90, phi_max=90, phi_step=45, bounces=2)),
     "3d_segmode": (abi.GEOAC_3D, [TOY], dict(theta_min=3, theta_max=45, theta_step=7, phi_min=-135, phi_max=180, phi_step=105, bounces=2, accum_mode=1)),
     "3d_noamp": (abi.GEOAC_3D, [TOY], dict(theta_min=2, theta_max=50, theta_step=8, phi_min=0, phi_max=300, phi_step=100, bounces=1, CalcAmp=0)),
+    # spherical stratified (config 3's variant) on the shipped profile: default source lat 30 lon 0, both accumulation modes
+    "global_sub": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=3, theta_max=48, theta_step=9, phi_min=-90, phi_max=135, phi_step=75, bounces=3)),
+    "global_segmode": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=5, theta_max=35, theta_step=10, phi_min=20, phi_max=290, phi_step=135, bounces=1, accum_mode=1,
+                                                       lat_src=-45, lon_src=170, rng_max=800, z_src=3.5, freq=0.7)),
+    "global_noamp": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=4, theta_max=40, theta_step=12, phi_min=45, phi_max=225, phi_step=180, bounces=2, CalcAmp=0)),
     "3d_elevated": (abi.GEOAC_3D, [TOY], dict(theta_min=-10, theta_max=40, theta_step=10, azimuth=-60, bounces=2, z_src=12.5, z_grnd=1.2, freq=0.5, rng_max=600, alt_max=120)),
 }
 
