@@ -68,6 +68,11 @@ double orc_suthbass_alpha(orc_atmo* a, double x0, double x1, double x2, double f
 int orc_load_met_1d(const char* path, const char* format, double z_grnd_taper, int global_taper,
                     int cap, int* n, double* z, double* T, double* u, double* v, double* rho);
 
+/* Mirror of Load_G2S_Multi (Code/Atmo/G2S_MultiDimSpline3D.cpp:139-189, G2S_GlobalMultiDimSpline3D.cpp:142-199). */
+int orc_load_met_grid(const char* prefix, const char* loc0, const char* loc1, const char* format, int global,
+                      int cap0, int cap1, int capz, int* n0, int* n1, int* nz,
+                      double* ax0, double* ax1, double* axz, double* T, double* u, double* v, double* rho);
+
 /* Same contract as geoac_trace() of include/geoac_b200.h but on the CPU, single thread.
  * `limits_from_atmo` != 0 applies GeoAc_SetPropRegion to a copy of *p first. Returns total RK4 steps (<0 on error). */
 int64_t orc_trace(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_rays,

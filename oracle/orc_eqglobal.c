@@ -25,6 +25,7 @@ typedef struct srcg {                       /* GeoAc_Sources, Global.cpp:24-58 *
 /* range-dependent fast paths (orc_mspline.c): f, 3 first derivatives [, 6 second derivatives] in one call */
 void orc_mspline_allorder1(orc_atmo* a, int field, double q0, double q1, double q2, double* f, double d[3]);
 void orc_mspline_allorder2(orc_atmo* a, int field, double q0, double q1, double q2, double* f, double d[3], double dd[3][3]);
+void orc_mspline_sync_accel(orc_atmo* a);      /* Windu/Windv cursors := Temp's, GlobalRngDep.cpp:236-239, 284-287 */
 
 /* GeoAc_SetInitialConditions, Global.cpp:76-136 */
 static void initg(orc_ray* r, double* y) {
@@ -172,6 +173,7 @@ static void updategr(orc_ray* r, const double* y) {
     double temp, dtemp[3];
     if (!r->calc_amp) {
         orc_mspline_allorder1(a, 0, rr, t, p, &temp, dtemp);
+        orc_mspline_sync_accel(a);
         orc_mspline_allorder1(a, 1, rr, t, p, &s->u, s->du);
         orc_mspline_allorder1(a, 2, rr, t, p, &s->v, s->dv);
         s->w = 0.0;
@@ -181,6 +183,7 @@ static void updategr(orc_ray* r, const double* y) {
         double ddT[3][3], ddU[3][3], ddV[3][3];
         double R[2][3] = { { y[6], y[7], y[8] }, { y[12], y[13], y[14] } };
         orc_mspline_allorder2(a, 0, rr, t, p, &temp, dtemp, ddT);
+        orc_mspline_sync_accel(a);
         orc_mspline_allorder2(a, 1, rr, t, p, &s->u, s->du, ddU);
         orc_mspline_allorder2(a, 2, rr, t, p, &s->v, s->dv, ddV);
         s->w = 0.0;

@@ -37,6 +37,8 @@ def lib():
         L.orc_set_prop_region.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams)]
         L.geoac_default_params_oracle.argtypes = [C.c_int, C.POINTER(abi.GeoacParams)]
         L.orc_load_met_1d.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), dp, dp, dp, dp, dp]
+        L.orc_load_met_grid.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), dp, dp, dp, dp, dp, dp, dp]
         L.orc_suthbass_alpha.restype = C.c_double
         L.orc_suthbass_alpha.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double]
         _LIB = L
@@ -54,6 +56,22 @@ def load_met_1d(path, fmt="zTuvdp", z_grnd_taper=0.0, global_taper=False, cap=20
     if rc != 0:
         raise IOError(f"orc_load_met_1d({path}) -> {rc}")
     return [a[: n.value].copy() for a in arrs]   # z, T, u, v, rho
+
+
+def load_met_grid(prefix, loc0, loc1, fmt="zTuvdp", is_global=False, cap0=512, cap1=512, capz=4096):
+    """Load_G2S_Multi mirror: returns ax0, ax1, axz, T, u, v, rho (fields [n0][n1][nz], winds tapered, km/s)."""
+    import re
+    n0g = len(open(loc0).read().split())
+    n1g = len(open(loc1).read().split())
+    nzg = sum(1 for _ in open(f"{prefix}0.met"))
+    ax0, ax1, axz = np.zeros(n0g), np.zeros(n1g), np.zeros(nzg)
+    fields = [np.zeros(n0g * n1g * nzg) for _ in range(4)]
+    n0, n1, nz = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().orc_load_met_grid(prefix.encode(), loc0.encode(), loc1.encode(), fmt.encode(), int(is_global), n0g, n1g, nzg,
+                                 C.byref(n0), C.byref(n1), C.byref(nz), _p(ax0), _p(ax1), _p(axz), *[_p(f) for f in fields])
+    if rc != 0 or (n0.value, n1.value, nz.value) != (n0g, n1g, nzg):
+        raise IOError(f"orc_load_met_grid({prefix}) -> {rc} ({n0.value},{n1.value},{nz.value})")
+    return [ax0, ax1, axz] + [f.reshape(n0g, n1g, nzg) for f in fields]
 
 
 class Atmo:

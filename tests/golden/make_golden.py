@@ -15,10 +15,19 @@ sys.path.insert(0, ROOT)
 from geoac_b200 import abi            # noqa: E402
 from oracle import pyoracle as po     # noqa: E402
 
+from tests.golden import make_grid   # noqa: E402
+
 GOLD = os.path.join(ROOT, "tests", "golden")
 TOY = os.path.join(GOLD, "ToyAtmo.met")
 
-# name -> (variant, profile args, reference-driver keys)
+# synthetic range-dependent grids (tests/golden/make_grid.py); sources are placed OFF the node lines on purpose: on a
+# node line the reference's cell choice depends on the spline cursor left behind by earlier look-ups
+GRIDS = {
+    "grid_cart": dict(is_global=False, build=lambda d: make_grid.write_cartesian(d, np.arange(-500.0, 501.0, 200.0), np.arange(-450.0, 451.0, 150.0))),
+    "grid_glob": dict(is_global=True, build=lambda d: make_grid.write_global(d, np.arange(20.0, 51.0, 6.0), np.arange(-15.0, 16.0, 5.0))),
+}
+
+# name -> (variant, profile args | grid name, reference-driver keys)
 CASES = {
     # config 1 of BASELINE.json in full: GeoAc2D -prop ToyAtmo.met (90 rays, 2 bounces)
     "2d_config1": (abi.GEOAC_2D, [TOY], dict()),
@@ -32,6 +41,15 @@ CASES = {
     "global_segmode": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=5, theta_max=35, theta_step=10, phi_min=20, phi_max=290, phi_step=135, bounces=1, accum_mode=1,
                                                        lat_src=-45, lon_src=170, rng_max=800, z_src=3.5, freq=0.7)),
     "global_noamp": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=4, theta_max=40, theta_step=12, phi_min=45, phi_max=225, phi_step=180, bounces=2, CalcAmp=0)),
+    # range-dependent variants on the synthetic grids above (config 4 / 5 style perturbations, tiny node counts)
+    "3drngdep_sub": (abi.GEOAC_3D_RNGDEP, "grid_cart", dict(theta_min=5, theta_max=36, theta_step=10, phi_min=-60, phi_max=165, phi_step=105, bounces=1,
+                                                            x_src=13.7, y_src=-21.3)),
+    "3drngdep_noamp": (abi.GEOAC_3D_RNGDEP, "grid_cart", dict(theta_min=8, theta_max=30, theta_step=11, phi_min=30, phi_max=300, phi_step=135, bounces=1,
+                                                              x_src=-120.4, y_src=88.8, CalcAmp=0, accum_mode=1, z_src=2.5)),
+    "globalrngdep_sub": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(theta_min=5, theta_max=36, theta_step=10, phi_min=-60, phi_max=165, phi_step=105, bounces=1,
+                                                                    lat_src=33.3, lon_src=1.7)),
+    "globalrngdep_noamp": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(theta_min=8, theta_max=30, theta_step=11, phi_min=30, phi_max=300, phi_step=135, bounces=1,
+                                                                      lat_src=36.1, lon_src=-3.4, CalcAmp=0, accum_mode=1, z_src=2.5)),
     "3d_elevated": (abi.GEOAC_3D, [TOY], dict(theta_min=-10, theta_max=40, theta_step=10, azimuth=-60, bounces=2, z_src=12.5, z_grnd=1.2, freq=0.5, rng_max=600, alt_max=120)),
 }
 
@@ -39,10 +57,19 @@ CASES = {
 def main(names):
     for name in names:
         variant, prof, kv = CASES[name]
-        with tempfile.TemporaryDirectory() as td:
+        extra = {}
+        with tempfile.TemporaryDirectory(dir="/tmp", prefix="g") as td:       # short paths: the reference's name buffers are char[50]
+            if isinstance(prof, str):
+                grid = GRIDS[prof]
+                files = list(grid["build"](td))
+                gpath = os.path.join(GOLD, prof + ".npz")
+                arrs = po.load_met_grid(*files, is_global=grid["is_global"])
+                np.savez_compressed(gpath, **dict(zip(["ax0", "ax1", "axz", "T", "u", "v", "rho"], arrs)))
+                extra["grid"] = prof
+                prof = files
             ref, info = po.run_ref(variant, prof, os.path.join(td, "o.bin"), **kv)
         out = os.path.join(GOLD, name + ".npz")
-        np.savez_compressed(out, variant=variant, keys=np.array(sorted(f"{k}={v}" for k, v in kv.items())),
+        np.savez_compressed(out, variant=variant, **extra, keys=np.array(sorted(f"{k}={v}" for k, v in kv.items())),
                             theta_deg=ref["theta_deg"], phi_deg=ref["phi_deg"], rec=ref["rec"], status=ref["status"],
                             n_steps=ref["n_steps"], eq_cnt=ref["eq_cnt"], vert_limit=info["vert_limit"])
         print(f"{name}: {len(ref['theta_deg'])} rays, {ref['total_steps']} steps, arrivals {(ref['status'] == 1).sum()}, "

@@ -10,14 +10,17 @@ from tests import util
 def _run_oracle(po, name):
     d, kv = util.load_case(name)
     variant = int(d["variant"])
-    z, T, u, v, rho = po.load_met_1d(util.TOY, global_taper=util.is_global(variant))
-    at = po.atmo1d(util.is_global(variant), z, T, u, v, rho)
+    if util.is_rngdep(variant):
+        at = po.atmo3d(util.is_global(variant), *util.load_grid(d))
+    else:
+        z, T, u, v, rho = po.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+        at = po.atmo1d(util.is_global(variant), z, T, u, v, rho)
     p = util.apply_keys(variant, po.default_params(variant, at), kv)
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
     return d, variant, p, po.trace(variant, at, p, th, ph)
 
 
-@pytest.mark.parametrize("name", [c for c in util.golden_cases() if not c.startswith(("3drngdep", "globalrngdep"))])
+@pytest.mark.parametrize("name", util.golden_cases())
 def test_oracle_bit_exact_vs_reference(oracle, name):
     d, variant, p, out = _run_oracle(oracle, name)
     assert np.array_equal(out["status"], d["status"])

@@ -17,7 +17,18 @@ RTOL = 1e-9
 
 
 def golden_cases(prefix=""):
-    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, prefix + "*.npz")))
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, prefix + "*.npz")))
+    return [n for n in names if not n.startswith("grid_")]
+
+
+def is_rngdep(variant):
+    return variant in (abi.GEOAC_3D_RNGDEP, abi.GEOAC_GLOBAL_RNGDEP)
+
+
+def load_grid(d):
+    """The synthetic range-dependent grid a golden case was traced on: ax0, ax1, axz, T, u, v, rho (as the loader returns them)."""
+    g = np.load(os.path.join(GOLD, str(d["grid"]) + ".npz"))
+    return [g[k] for k in ("ax0", "ax1", "axz", "T", "u", "v", "rho")]
 
 
 def load_case(name):
@@ -38,7 +49,7 @@ def apply_keys(variant, p, kv, vert_limit_default=None):
     p.freq = float(kv.get("freq", 0.1))
     p.z_grnd = float(kv.get("z_grnd", 0.0))
     p.tweak_abs = max(0.0, float(kv.get("abs_coeff", 0.3)))
-    if "alt_max" in kv:
+    if "alt_max" in kv and not is_rngdep(variant):      # RngDep mains: SetPropRegion runs after parsing and overwrites it
         p.vert_limit = float(kv["alt_max"])
     if "rng_max" in kv and variant in (abi.GEOAC_2D, abi.GEOAC_3D, abi.GEOAC_GLOBAL):
         p.range_limit = float(kv["rng_max"])
