@@ -48,6 +48,8 @@ def lib():
         L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.geoac_load_met_1d.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp]
+        L.geoac_load_met_grid.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                          C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.geoac_eq_count.argtypes = [C.c_int, C.c_int]
         L.geoac_measure_fp64_peak.restype = C.c_double
         L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
@@ -58,7 +60,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_device",
-    "geoac_last_trace_stats", "geoac_load_met_1d", "geoac_eq_count", "geoac_measure_fp64_peak",
+    "geoac_last_trace_stats", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
 ]
 
 
@@ -74,6 +76,22 @@ def load_met_1d(path, fmt="zTuvdp", z_grnd_taper=0.0, global_taper=False, cap=20
     if rc != abi.GEOAC_OK:
         raise GeoAcError(f"geoac_load_met_1d({path}) failed with status {rc}")
     return [a[: n.value].copy() for a in arrs]
+
+
+def load_met_grid(prefix, loc0, loc1, fmt="zTuvdp", is_global=False):
+    """Load_G2S_Multi mirror (reference Code/Atmo/G2S_MultiDimSpline3D.cpp:139-189): returns ax0, ax1, axz, T, u, v, rho with
+    fields shaped [n0][n1][nz] (winds tapered, km/s; Global node coordinates in radians)."""
+    n0g = len(open(loc0).read().split())
+    n1g = len(open(loc1).read().split())
+    nzg = sum(1 for _ in open(f"{prefix}0.met"))
+    ax0, ax1, axz = np.zeros(n0g), np.zeros(n1g), np.zeros(nzg)
+    fields = [np.zeros(n0g * n1g * nzg) for _ in range(4)]
+    n0, n1, nz = C.c_int(0), C.c_int(0), C.c_int(0)
+    rc = lib().geoac_load_met_grid(os.fsencode(prefix), os.fsencode(loc0), os.fsencode(loc1), fmt.encode(), int(is_global), n0g, n1g, nzg,
+                                   C.byref(n0), C.byref(n1), C.byref(nz), _p(ax0), _p(ax1), _p(axz), *[_p(f) for f in fields])
+    if rc != abi.GEOAC_OK or (n0.value, n1.value, nz.value) != (n0g, n1g, nzg):
+        raise GeoAcError(f"geoac_load_met_grid({prefix}) failed with status {rc}")
+    return [ax0, ax1, axz] + [f.reshape(n0g, n1g, nzg) for f in fields]
 
 
 def default_params(variant):

@@ -10,6 +10,8 @@
 #include <cmath>
 #include <string>
 #include <vector>
+#include <algorithm>
+#include <type_traits>
 
 #include "core.cuh"
 #include "eq_cartesian.cuh"
@@ -17,7 +19,9 @@
 #include "eq_global.cuh"
 #define GEOAC_HAVE_GLOBAL 1
 #endif
+#include "eq_rngdep.cuh"
 #include "trace_kernel.cuh"
+#include "host_tables.hpp"
 
 using namespace geoac;
 
@@ -33,6 +37,10 @@ struct geoac_ctx {
     double xmin = 0, xmax = 0;
     std::vector<double> h_table;
     double* d_table = nullptr;
+    // range-dependent grid
+    bool is_grid = false;
+    Grid3D grid{};
+    double *d_tuv = nullptr, *d_rho = nullptr, *d_ax = nullptr;
     LaunchConsts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;     // [0] ray counter, [1] total steps
     // staging for the host-buffer entry point
@@ -43,6 +51,7 @@ struct geoac_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t last_steps = 0; double last_ms = 0.0;
     bool consts_dirty = true;
+    bool src_set = false;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -99,6 +108,7 @@ extern "C" void geoac_destroy(geoac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -112,7 +122,7 @@ extern "C" int geoac_get_params(const geoac_ctx* ctx, geoac_params* p) { if (!ct
 extern "C" int geoac_set_params(geoac_ctx* ctx, const geoac_params* p) {
     if (!ctx || !p) return GEOAC_ERR_BAD_ARG;
     if (p->bounces < 0 || p->ds_min <= 0.0 || p->ray_limit <= 0.0) return fail(ctx, GEOAC_ERR_BAD_ARG, "bad params");
-    ctx->prm = *p; ctx->consts_dirty = true; return GEOAC_OK;
+    ctx->prm = *p; ctx->consts_dirty = true; ctx->src_set = true; return GEOAC_OK;
 }
 
 // ---- knot slopes of the natural spline: same tridiagonal recurrences as G2S_Spline1D.cpp:161-196 ----
@@ -173,9 +183,43 @@ extern "C" int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, c
     return GEOAC_OK;
 }
 
-extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int, int, int, const double*, const double*, const double*,
-                                       const double*, const double*, const double*, const double*) {
-    return fail(ctx, GEOAC_ERR_BAD_ARG, "range-dependent atmospheres are not built into this library yet");
+extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, const double* ax0, const double* ax1, const double* axz,
+                                       const double* T, const double* u, const double* v, const double* rho) {
+    if (!ctx) return GEOAC_ERR_BAD_ARG;
+    if (ctx->variant != GEOAC_3D_RNGDEP && ctx->variant != GEOAC_GLOBAL_RNGDEP)
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "variant needs geoac_set_atmosphere_1d");
+    if (n0 < 2 || n1 < 2 || nz < 3 || !ax0 || !ax1 || !axz || !T || !u || !v || !rho)
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "need >= 2 x 2 x 3 nodes and non-null arrays");
+    for (int i = 1; i < n0; i++) if (!(ax0[i] > ax0[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "axis 0 must be strictly increasing");
+    for (int i = 1; i < n1; i++) if (!(ax1[i] > ax1[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "axis 1 must be strictly increasing");
+    for (int i = 1; i < nz; i++) if (!(axz[i] > axz[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "altitudes must be strictly increasing");
+    const size_t nodes = (size_t)n0 * n1 * nz;
+    if (nodes * MS_STRIDE >= (size_t)1 << 32) return fail(ctx, GEOAC_ERR_TOO_LARGE, "grid exceeds 2^32/12 nodes (32-bit element offsets in the kernel)");
+    cudaSetDevice(ctx->device);
+    const bool glob = ctx->variant == GEOAC_GLOBAL_RNGDEP;
+    std::vector<double> z, tuv, rh;
+    build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, T, u, v, rho, z, tuv, rh);
+    cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax); ctx->d_tuv = ctx->d_rho = ctx->d_ax = nullptr;
+    CK(cudaMalloc(&ctx->d_tuv, tuv.size() * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_rho, rh.size() * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_ax, (size_t)(n0 + n1 + nz) * sizeof(double)));
+    CK(cudaMemcpy(ctx->d_tuv, tuv.data(), tuv.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_rho, rh.data(), rh.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ax, ax0, n0 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ax + n0, ax1, n1 * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ax + n0 + n1, z.data(), nz * sizeof(double), cudaMemcpyHostToDevice));
+    Grid3D& g = ctx->grid;
+    g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + n0; g.axz = ctx->d_ax + n0 + n1;
+    g.n0 = n0; g.n1 = n1; g.nz = nz;
+    g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
+    // GeoAc_SetPropRegion: G2S_MultiDimSpline3D.cpp:22-33 / G2S_GlobalMultiDimSpline3D.cpp:22-33
+    ctx->prm.vert_limit = g.zmax;
+    ctx->prm.box_min[0] = g.amin; ctx->prm.box_max[0] = g.amax; ctx->prm.box_min[1] = g.bmin; ctx->prm.box_max[1] = g.bmax;
+    if (glob && !ctx->src_set) {      // GeoAcGlobal.RngDep_main.cpp:135-137: default source = grid midpoint
+        ctx->prm.src[1] = (g.amin + g.amax) / 2.0; ctx->prm.src[2] = (g.bmin + g.bmax) / 2.0;
+    }
+    ctx->is_grid = true; ctx->have_atmo = true; ctx->consts_dirty = true;
+    return GEOAC_OK;
 }
 
 // ---- per-launch invariants, computed on the device with the same spline routines the kernel uses ----
@@ -188,6 +232,13 @@ __global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, co
     *out = L;
 }
 
+__global__ void setup_consts_grid_kernel(LaunchConsts* out, const LaunchConsts in, const Grid3D g, int variant) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    LaunchConsts L = in;
+    fill_launch_consts_3d(L, g, variant);
+    *out = L;
+}
+
 static int refresh_consts(geoac_ctx* ctx) {
     if (!ctx->consts_dirty) return GEOAC_OK;
     const geoac_params& p = ctx->prm;
@@ -196,13 +247,14 @@ static int refresh_consts(geoac_ctx* ctx) {
     L.z_grnd = p.z_grnd; L.tweak_abs = p.tweak_abs; L.freq = p.freq;
     for (int i = 0; i < 2; i++) { L.box_min[i] = p.box_min[i]; L.box_max[i] = p.box_max[i]; }
     for (int i = 0; i < 3; i++) L.src[i] = p.src[i];
-    if (ctx->variant == GEOAC_2D || ctx->variant == GEOAC_3D) L.src[2] = std::max(p.z_grnd, p.src[2]);   // z_src = max(z_grnd, z_src)
+    if (ctx->variant == GEOAC_2D || ctx->variant == GEOAC_3D || ctx->variant == GEOAC_3D_RNGDEP) L.src[2] = std::max(p.z_grnd, p.src[2]);   // z_src = max(z_grnd, z_src)
     else L.src[0] = std::max(p.z_grnd, p.src[0]);
     L.bounces = p.bounces; L.calc_amp = p.calc_amp;
     L.seg_mode = (ctx->variant == GEOAC_2D) ? 1 : (p.accum_per_segment ? 1 : 0);                          // App. A-2
     L.step_limit = (int)(p.ray_limit * (int)(1.0 / (p.ds_min * 10)));                                     // Solver.cpp:14
     L.per_bounce_zmax = (ctx->variant == GEOAC_3D_RNGDEP || ctx->variant == GEOAC_GLOBAL_RNGDEP);         // App. A-3
-    setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->n_pad, ctx->xmin, ctx->xmax, ctx->variant);
+    if (ctx->is_grid) setup_consts_grid_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->grid, ctx->variant);
+    else setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->n_pad, ctx->xmin, ctx->xmax, ctx->variant);
     CK(cudaGetLastError());
     ctx->consts_dirty = false;
     return GEOAC_OK;
@@ -211,24 +263,24 @@ static int refresh_consts(geoac_ctx* ctx) {
 // ---- kernel launch ----
 template <class EQ, int BLOCK>
 static int launch_trace(geoac_ctx* ctx, const TraceArgs& a, cudaStream_t st) {
+    constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
     const size_t fixed = ((sizeof(LaunchConsts) + 15) / 16) * 16 + 16 + (size_t)EQ::NEQ * BLOCK * sizeof(double);
-    const size_t tab_bytes = (size_t)TAB_NARR * ctx->n_pad * sizeof(double);
+    const size_t tab_bytes = kGrid ? 0 : (size_t)TAB_NARR * ctx->n_pad * sizeof(double);
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    const bool in_smem = fixed + tab_bytes <= (size_t)max_optin;
-    // never launch more lanes than rays (small batches: one warp per CTA first)
-    int64_t warps_needed = (a.n_rays + 31) / 32;
-    int grid = (int)std::min<int64_t>(ctx->sm_count, std::max<int64_t>(1, (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32)));
-    if (in_smem) {
-        auto k = trace_kernel<EQ, BLOCK, true>;
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(fixed + tab_bytes)));
-        k<<<grid, BLOCK, fixed + tab_bytes, st>>>(a);
-    } else {
-        auto k = trace_kernel<EQ, BLOCK, false>;     // table too large for shared memory: read it through L1/L2
-        CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fixed));
-        k<<<grid, BLOCK, fixed, st>>>(a);
-    }
-    CK(cudaGetLastError());
+    const bool in_smem = !kGrid && fixed + tab_bytes <= (size_t)max_optin;
+    const size_t smem = in_smem ? fixed + tab_bytes : fixed;
+    const void* fn = in_smem ? (const void*)trace_kernel<EQ, BLOCK, true> : (const void*)trace_kernel<EQ, BLOCK, false>;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BLOCK, smem));
+    if (per_sm < 1) return fail(ctx, GEOAC_ERR_CUDA, "trace kernel does not fit on an SM");
+    // persistent grid: every resident CTA slot of every SM, but never more lanes than rays
+    const int64_t warps_needed = (a.n_rays + 31) / 32;
+    const int64_t ctas_needed = std::max<int64_t>(1, (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32));
+    const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, ctas_needed);
+    void* args[] = { (void*)&a };
+    CK(cudaLaunchKernel(fn, dim3(grid), dim3(BLOCK), args, smem, st));
     return GEOAC_OK;
 }
 
@@ -248,6 +300,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     CK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_slots, st));
     CK(cudaMemsetAsync(d_n_steps, 0, sizeof(int32_t) * n_slots, st));
     TraceArgs a;
+    a.grid = ctx->grid;
     a.table = ctx->d_table; a.table_n = ctx->n; a.table_npad = ctx->n_pad; a.table_xmin = ctx->xmin; a.table_xmax = ctx->xmax;
     a.consts = ctx->d_consts; a.theta = d_theta; a.phi = d_phi; a.n_rays = n_rays; a.n_rec = n_rec;
     a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
@@ -259,6 +312,8 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
 #ifdef GEOAC_HAVE_GLOBAL
         case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 256>(ctx, a, st) : launch_trace<EqGlobal<false>, 256>(ctx, a, st);
 #endif
+        case GEOAC_3D_RNGDEP:     return amp ? launch_trace<Eq3DRD<true>, 128>(ctx, a, st)     : launch_trace<Eq3DRD<false>, 128>(ctx, a, st);
+        case GEOAC_GLOBAL_RNGDEP: return amp ? launch_trace<EqGlobalRD<true>, 128>(ctx, a, st) : launch_trace<EqGlobalRD<false>, 128>(ctx, a, st);
     }
     return fail(ctx, GEOAC_ERR_BAD_ARG, "variant not implemented");
 }
@@ -347,6 +402,47 @@ extern "C" int geoac_load_met_1d(const char* path, const char* format, double z_
     std::fclose(f);
     *n = cnt;
     return cnt >= 3 ? GEOAC_OK : GEOAC_ERR_IO;
+}
+
+// ---- Load_G2S_Multi: Code/Atmo/G2S_MultiDimSpline3D.cpp:139-189 (Cartesian), G2S_GlobalMultiDimSpline3D.cpp:142-199 (Global) ----
+extern "C" int geoac_load_met_grid(const char* prefix, const char* loc0, const char* loc1, const char* format, int global,
+                                   int cap0, int cap1, int capz, int* n0, int* n1, int* nz,
+                                   double* ax0, double* ax1, double* axz, double* T, double* u, double* v, double* rho) {
+    if (!prefix || !loc0 || !loc1 || !format || !n0 || !n1 || !nz || !ax0 || !ax1 || !axz || !T || !u || !v || !rho) return GEOAC_ERR_BAD_ARG;
+    int fmt = !std::strncmp(format, "zTuvdp", 6) ? 0 : (!std::strncmp(format, "zuvwTdp", 7) ? 1 : -1);
+    if (fmt < 0) return GEOAC_ERR_BAD_ARG;
+    auto read_axis = [&](const char* path, double* out, int cap) -> int {
+        FILE* f = std::fopen(path, "r"); if (!f) return -1;
+        int c = 0; while (c < cap && std::fscanf(f, "%lf", &out[c]) == 1) c++;
+        std::fclose(f); return c;
+    };
+    const int c0 = read_axis(loc0, ax0, cap0), c1 = read_axis(loc1, ax1, cap1);
+    if (c0 < 2 || c1 < 2) return GEOAC_ERR_IO;
+    if (global) { for (int i = 0; i < c0; i++) ax0[i] *= kPi / 180.0; for (int i = 0; i < c1; i++) ax1[i] *= kPi / 180.0; }   // degrees -> radians
+    int cz = -1;
+    std::string path;
+    for (int i = 0; i < c0; i++) for (int j = 0; j < c1; j++) {
+        path = std::string(prefix) + std::to_string(i * c1 + j) + ".met";          // <prefix><i0*n1+i1>.met
+        FILE* f = std::fopen(path.c_str(), "r"); if (!f) return GEOAC_ERR_IO;
+        int k = 0; double zz, tt, uu, vv, rr, t1, t2;
+        for (;;) {
+            const bool ok = fmt == 0 ? std::fscanf(f, "%lf %lf %lf %lf %lf %lf", &zz, &tt, &uu, &vv, &rr, &t1) == 6
+                                     : std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf", &zz, &uu, &vv, &t1, &tt, &rr, &t2) == 7;
+            if (!ok || k >= capz || (cz >= 0 && k >= cz)) break;
+            double arg;                                                             // ground taper: width 0.05 Cartesian, 0.2 Global; z_grnd = 0 at load
+            if (global) { const double r = zz + kREarth; arg = -(r - kREarth - 0.0) / 0.2; }
+            else        arg = -(zz - 0.0) / 0.05;
+            uu *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
+            vv *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
+            const size_t id = ((size_t)i * c1 + j) * (size_t)(cz >= 0 ? cz : capz) + k;
+            axz[k] = zz; T[id] = tt; u[id] = uu; v[id] = vv; rho[id] = rr;
+            k++;
+        }
+        std::fclose(f);
+        if (cz < 0) cz = k; else if (k != cz) return GEOAC_ERR_IO;
+    }
+    *n0 = c0; *n1 = c1; *nz = cz;
+    return cz >= 3 ? GEOAC_OK : GEOAC_ERR_IO;
 }
 
 // ---- FP64 roofline denominator: dependent-chain-free DFMA loop, 8 independent accumulators per thread ----

@@ -116,6 +116,10 @@ GEOAC_HD double sound_speed0(double T) { return sqrt(kGamR * T); }
 // ---------------------------------------------------------------------------------------------------------------
 // per-launch invariants (filled by a one-thread setup kernel from the same device routines, then read-only)
 // ---------------------------------------------------------------------------------------------------------------
+// reference state of the Sutherland-Bass model (T_o, P_o): per launch for the Cartesian variants and the stratified
+// Global one, per step for Global.RngDep (its reference point follows the ray's latitude / longitude, App. A-14)
+struct SBRef { double invTo, cbrtTo, visc_num, invPo; };
+
 struct LaunchConsts {
     // parameters (copy of geoac_params + derived)
     double ds_min, ds_max, vert_limit, range_limit, z_grnd, tweak_abs, freq;
@@ -129,15 +133,14 @@ struct LaunchConsts {
     double c_gnd, rho_gnd;                    // at z_grnd (2D amplitude / reflection)
     double dc_gnd, du_gnd, dv_gnd;            // vertical derivatives at z_grnd (stratified reflection)
     // Sutherland-Bass invariants
-    double sb_invTo, sb_cbrtTo, sb_visc_num;  // 1/T_o, T_o^(1/3), (1 + S/T_o)
-    double sb_invPo;
+    SBRef sb;                                 // 1/T_o, T_o^(1/3), (1 + S/T_o), 1/P_o
     double sb_w;                              // 2*pi*freq
 };
 
 // Sutherland-Bass absorption [dB/km] at altitude z [km] with local sound speed c [km/s] (and 1/c) and density rho.
 // Restructured from Atmo_State.Absorption.cpp:14-143: constants folded, pow(10,.) -> exp10, pow(T,-1/3) -> rcbrt,
 // exp(9.17 Tr) = 1/exp(-9.17 Tr), common factors hoisted.  Branch thresholds are the reference's (strict >).
-GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double c, double inv_c, double rho) {
+GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho) {
     const double mu_o = 18.192E-6, S = 117.0;
     const double c1000 = c * 1000.0;
     const double c2 = c1000 * c1000;
@@ -146,7 +149,7 @@ GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double 
     const double inv_Tz = 1.0 / T_z;
     const double inv_Pz = 1.0 / P_z;
 
-    const double mu_ratio = sqrt(T_z * L.sb_invTo) * (L.sb_visc_num / (1.0 + S * inv_Tz));     // mu/mu_o
+    const double mu_ratio = sqrt(T_z * R.invTo) * (R.visc_num / (1.0 + S * inv_Tz));     // mu/mu_o
     const double mu = mu_o * mu_ratio;
     const double nu = (8.0 * kPi * L.freq * mu) * inv_Pz * (1.0 / 3.0);
 
@@ -187,7 +190,7 @@ GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double 
     const double a_rot = w_c * X_ON * ((sigma * sigma - 1.0) * chi * (0.5 / sigma)) * sqrt(0.5 * (s1 + 1.0) / (nu2p1 * cchi2p1));
     const double a_diff = 0.003 * a_cl;
 
-    const double Tr = cb * L.sb_cbrtTo - 1.0;                              // (T_z/T_o)^(-1/3) - 1
+    const double Tr = cb * R.cbrtTo - 1.0;                              // (T_z/T_o)^(-1/3) - 1
     const double A1 = (X0 + X1) * 24.0 * exp(-9.16 * Tr);
     const double A2 = (X4 + X5) * 2400.0;
     const double B  = 40400.0 * exp(10.0 * Tr);
@@ -204,7 +207,7 @@ GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double 
     const double Lx = exp(-7.72 * Tr);
     const double ZZ = H * X2 + I * (X0 + 0.5 * X4) + J * (X1 + 0.5 * X5) + K * (X6 + X3);
     const double hu = 100.0 * (X3 + X6);
-    const double pm = (P_z * L.sb_invPo) / mu_ratio;                       // (P_z/P_o)(mu_o/mu)
+    const double pm = (P_z * R.invPo) / mu_ratio;                       // (P_z/P_o)(mu_o/mu)
     double fv[4];
     fv[0] = pm * (A1 + A2 + B * hu * (C + hu) * (D + hu));
     fv[1] = pm * (E + F * X3 + G * X6);
@@ -230,12 +233,16 @@ GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, double z, double 
 }
 
 // fill the Sutherland-Bass invariants from the reference state (c, rho at the reference level)
-GEOAC_HD void suthbass_setup(LaunchConsts& L, double c_ref, double rho_ref) {
+GEOAC_HD void suthbass_ref(SBRef& R, double c_ref, double rho_ref) {
     const double c1000 = c_ref * 1000.0;
     const double T_o = c1000 * c1000 / (kR * kGam);
     const double P_o = rho_ref * (c1000 * c1000) / kGam * 1000.0;
-    L.sb_invTo = 1.0 / T_o; L.sb_cbrtTo = cbrt(T_o); L.sb_visc_num = 1.0 + 117.0 / T_o;
-    L.sb_invPo = 1.0 / P_o; L.sb_w = 2.0 * kPi * L.freq;
+    R.invTo = 1.0 / T_o; R.cbrtTo = cbrt(T_o); R.visc_num = 1.0 + 117.0 / T_o;
+    R.invPo = 1.0 / P_o;
+}
+GEOAC_HD void suthbass_setup(LaunchConsts& L, double c_ref, double rho_ref) {
+    suthbass_ref(L.sb, c_ref, rho_ref);
+    L.sb_w = 2.0 * kPi * L.freq;
 }
 
 }  // namespace geoac

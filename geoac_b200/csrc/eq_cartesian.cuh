@@ -15,6 +15,8 @@ namespace geoac {
 template <bool AMP>
 struct Eq3D {
     static constexpr int NEQ = AMP ? 12 : 4;
+    using Atmo = Table1D;
+    using Cursor = int;
     static constexpr int VARIANT = GEOAC_3D;
     static constexpr bool QUADRATIC_INTERCEPT = true;
 
@@ -125,7 +127,7 @@ struct Eq3D {
         const double cn = c / nu_mag;
         const double cp0 = cn * rc.nx + u, cp1 = cn * rc.ny + v, cp2 = cn * nz;
         dtt = ds * g_rsqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
-        datt = suthbass_alpha(L, zm, c, inv_c, rho) * ds;
+        datt = suthbass_alpha(L, L.sb, zm, c, inv_c, rho) * ds;
     }
 
     // GeoAc_ApproximateIntercept + GeoAc_SetReflectionConditions, 3DStratified.cpp:136-186
@@ -187,6 +189,8 @@ struct Eq3D {
 template <bool AMP>
 struct Eq2D {
     static constexpr int NEQ = AMP ? 6 : 3;
+    using Atmo = Table1D;
+    using Cursor = int;
     static constexpr int VARIANT = GEOAC_2D;
     static constexpr bool QUADRATIC_INTERCEPT = true;
 
@@ -259,7 +263,7 @@ struct Eq2D {
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         dtt = ds / (c + u * rc.cphi + v * rc.sphi);
-        datt = suthbass_alpha(L, zm, c, inv_c, rho) * ds;
+        datt = suthbass_alpha(L, L.sb, zm, c, inv_c, rho) * ds;
     }
 
     // GeoAc_ApproximateIntercept + GeoAc_SetReflectionConditions, 2DStratified.cpp:74-117

@@ -16,6 +16,8 @@ namespace geoac {
 template <bool AMP>
 struct EqGlobal {
     static constexpr int NEQ = AMP ? 18 : 6;
+    using Atmo = Table1D;
+    using Cursor = int;
     static constexpr int VARIANT = GEOAC_GLOBAL;
 
     struct RayC {
@@ -154,7 +156,7 @@ struct EqGlobal {
         const double cn = c * g_rsqrt(n0 * n0 + n1 * n1 + n2 * n2);
         const double c0 = cn * n0, c1 = cn * n1 + v, c2 = cn * n2 + u;
         dtt = ds_tt * g_rsqrt(c0 * c0 + c1 * c1 + c2 * c2);
-        datt = suthbass_alpha(L, rm - kREarth, c, inv_c, rho) * ds_sb;
+        datt = suthbass_alpha(L, L.sb, rm - kREarth, c, inv_c, rho) * ds_sb;
     }
 
     // GeoAc_ApproximateIntercept (first order only, App. A-7) + GeoAc_SetReflectionConditions, Global.cpp:140-205

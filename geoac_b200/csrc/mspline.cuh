@@ -1,0 +1,288 @@
+// mspline.cuh -- range-dependent atmosphere sampler for one thread per ray.
+//
+// What the reference computes (Code/Atmo/G2S_MultiDimSpline3D.cpp:1156-1593, G2S_GlobalMultiDimSpline3D.cpp:1047-1461;
+// behavioural spec in SURVEY App. E): natural cubic splines in the vertical at every horizontal node, and per query five
+// bicubic Hermite patches whose corner data are centred finite differences of vertical-spline values, each pushed
+// through a dense 16x16 matrix -- 148 vertical-spline calls and ~95 k floating-point operations per field triple.
+//
+// What this file does instead: the Hermite patch with finite-difference corner data is a TENSOR PRODUCT of 1-D
+// operators, so every output is a small bilinear form over the 4x4 node block
+//     HX(Q) = h00 Q1 + h01 Q2 + dx (h10 r0 (Q2-Q0) + h11 r1 (Q3-Q1))         (1-D Hermite with FD slopes)
+//     FX(V,G) = h00 r0 (V2-V0) + h01 r1 (V3-V1) + dx (h10 r0 (G2-G0) + h11 r1 (G3-G1))   (values dV/dx, slopes dG/dx)
+// applied along ax0 inside a row and accumulated over the four rows with the matching ax1 weights.  One pass over the
+// 16 nodes yields the value, the gradient and the six second derivatives of T, u and v (~4 k flops instead of ~95 k),
+// identical to the reference up to rounding.  The reference's formula slips are kept: the
+// Cartesian wrappers / d2f/dz2 block scale the ax1 slope data by dx, the Global vertical-derivative columns drop their
+// leading term, and Global second derivatives are not divided by the cell size.
+//
+// Node data layout in HBM (read through L1/L2; a ray stays in one cell for tens of steps):
+//     tuv[((i0*n1 + i1)*nz + k)*12 + 4*field + {0: f, 1: df/dz slope, 2: d(df/dax0)/dz slope, 3: d(df/dax1)/dz slope}]
+//     rho[((i0*n1 + i1)*nz + k)*2  + {0: f, 1: slope}]
+// so the two levels a column needs are 2 x 96 contiguous bytes for all three fields.
+#pragma once
+#include "core.cuh"
+
+namespace geoac {
+
+struct Grid3D {
+    const double* tuv;
+    const double* rho;
+    const double* ax0; const double* ax1; const double* axz;
+    int n0, n1, nz;
+    double amin, amax, bmin, bmax, zmin, zmax;
+};
+
+struct Cur3 { int ka, kb, kz; };
+
+constexpr int MS_STRIDE = 12;
+
+// Find_Segment from a cold cursor (both reference files): alternate a search from the bottom and from the top, so a point
+// exactly on knot m lands in cell m-1 in the lower half of the axis and in cell m in the upper half.
+GEOAC_HD int ms_find_cold(const double* x, int n, double xq) {
+    for (int i = 0; i < n; i++) {
+        if (xq >= x[i] && xq <= x[i + 1]) return i;
+        if (xq >= x[n - 2 - i] && xq < x[n - 1 - i]) return n - 2 - i;
+    }
+    return 0;
+}
+// warm cursor: stay in the current cell when the point is on one of its knots (the reference's first test)
+GEOAC_HD int ms_find_warm(const double* x, int n, double xq, int k) {
+    k = (k < 0) ? 0 : ((k > n - 2) ? n - 2 : k);
+    while (xq < x[k]) --k;
+    while (xq > x[k + 1]) ++k;
+    return k;
+}
+
+struct MsAxis {
+    unsigned off[4], offu[4], offd[4];   // element offsets of the 4 slot nodes (k-1, k, k+1, k+2 clamped) and of their FD neighbours
+    double rg[4];                        // 1 / (x[up] - x[dn]) of the finite difference centred on each slot node
+    double d, t;                         // cell width, scaled coordinate
+};
+
+GEOAC_HD void ms_axis(MsAxis& A, const double* x, int n, int k, double xq, unsigned stride) {
+    const int i[4] = { (k - 1 < 0) ? 0 : k - 1, k, k + 1, (k + 2 > n - 1) ? n - 1 : k + 2 };
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        const int iu = (i[a] + 1 > n - 1) ? n - 1 : i[a] + 1, id = (i[a] - 1 < 0) ? 0 : i[a] - 1;
+        A.off[a] = (unsigned)i[a] * stride; A.offu[a] = (unsigned)iu * stride; A.offd[a] = (unsigned)id * stride;
+        A.rg[a] = 1.0 / (x[iu] - x[id]);
+    }
+    const double x0 = x[k];
+    A.d = x[k + 1] - x0;
+    A.t = (xq - x0) / A.d;
+}
+
+// 1-D weights of one axis: Hermite basis at t (and its t-derivative) combined with the corner finite differences
+struct MsW {
+    double h00, h01, S0, S1;       // value basis; slope basis times the cell width
+    double p, q, P, Q;             // h00 r0, h01 r1, S0 r0, S1 r1
+    double e00, e01, T0, T1;       // derivatives of the above with respect to t
+    double pd, qd, Pd, Qd;
+};
+GEOAC_HD void ms_weights(MsW& w, const MsAxis& A, double slope_scale) {
+    const double t = A.t, u = 1.0 - t;
+    w.h00 = (1.0 + 2.0 * t) * u * u; w.h01 = t * t * (3.0 - 2.0 * t);
+    w.S0 = slope_scale * (t * u * u); w.S1 = slope_scale * (t * t * (t - 1.0));
+    w.e00 = 6.0 * t * (t - 1.0); w.e01 = -w.e00;
+    w.T0 = slope_scale * (u * (1.0 - 3.0 * t)); w.T1 = slope_scale * (t * (3.0 * t - 2.0));
+    const double r0 = A.rg[1], r1 = A.rg[2];
+    w.p = w.h00 * r0; w.q = w.h01 * r1; w.P = w.S0 * r0; w.Q = w.S1 * r1;
+    w.pd = w.e00 * r0; w.qd = w.e01 * r1; w.Pd = w.T0 * r0; w.Qd = w.T1 * r1;
+}
+// row operators along one axis (Q0..Q3 = quantity on the four slot nodes)
+GEOAC_HD double ms_HX(const MsW& w, double Q0, double Q1, double Q2, double Q3)  { return w.h00 * Q1 + w.h01 * Q2 + w.P * (Q2 - Q0) + w.Q * (Q3 - Q1); }
+GEOAC_HD double ms_HXd(const MsW& w, double Q0, double Q1, double Q2, double Q3) { return w.e00 * Q1 + w.e01 * Q2 + w.Pd * (Q2 - Q0) + w.Qd * (Q3 - Q1); }
+
+// vertical position shared by every column of a query
+struct MsZ { int kz; double X, omX, XomX, om2X, h, invh; };
+GEOAC_HD void ms_zpos(MsZ& Z, const Grid3D& g, double z, int kz) {
+    const double z0 = g.axz[kz];
+    Z.kz = kz; Z.h = g.axz[kz + 1] - z0; Z.invh = 1.0 / Z.h;
+    Z.X = (z - z0) / Z.h; Z.omX = 1.0 - Z.X; Z.XomX = Z.X * Z.omX; Z.om2X = 1.0 - 2.0 * Z.X;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Eval_Spline_AllOrder1 / AllOrder2 for T, u and v in one pass.  out[field][..] in GRID-axis order:
+//   0 f, 1 d/da, 2 d/db, 3 d/dz, 4 d2/da2, 5 d2/db2, 6 d2/dz2, 7 d2/dadb, 8 d2/dadz, 9 d2/dbdz   (a = ax0, b = ax1, z = vertical)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool GLOBAL, bool ORDER2>
+GEOAC_HD void ms_sample_tuv(const Grid3D& g, double a_in, double b_in, double z_in, Cur3& cur, double (&out)[3][10]) {
+    const double a = clampd(a_in, g.amin, g.amax), b = clampd(b_in, g.bmin, g.bmax), z = clampd(z_in, g.zmin, g.zmax);
+    cur.ka = ms_find_warm(g.ax0, g.n0, a, cur.ka);
+    cur.kb = ms_find_warm(g.ax1, g.n1, b, cur.kb);
+    cur.kz = ms_find_warm(g.axz, g.nz, z, cur.kz);
+    MsAxis A, B; MsZ Z;
+    ms_axis(A, g.ax0, g.n0, cur.ka, a, (unsigned)(g.n1 * g.nz * MS_STRIDE));
+    ms_axis(B, g.ax1, g.n1, cur.kb, b, (unsigned)(g.nz * MS_STRIDE));
+    ms_zpos(Z, g, z, cur.kz);
+    MsW wa, wb;
+    ms_weights(wa, A, A.d);
+    ms_weights(wb, B, B.d);
+    // d2f/dz2 block: the Cartesian file scales the ax1 slope data by dx (App. A-8); Global uses dp
+    const double qs = GLOBAL ? 1.0 : A.d / B.d;
+    const unsigned kofs = (unsigned)cur.kz * MS_STRIDE;
+    const double inv2 = 2.0 * Z.invh * Z.invh;
+
+#pragma unroll 1
+    for (int F = 0; F < 3; F++) {
+        double acc[10];
+#pragma unroll
+        for (int i = 0; i < 10; i++) acc[i] = 0.0;
+        const double* base = g.tuv + kofs + 4 * F;
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++) {
+            double V[4], Vz[4], Vzz[4], Ga[4], Gb[4], Gaz[4], Gbz[4];
+#pragma unroll
+            for (int ia = 0; ia < 4; ia++) {
+                const double* n0p = base + (A.off[ia] + B.off[jb]);
+                const double f0 = n0p[0], s0 = n0p[1], sa0 = n0p[2], sb0 = n0p[3];
+                const double f1 = n0p[MS_STRIDE], s1 = n0p[MS_STRIDE + 1], sa1 = n0p[MS_STRIDE + 2], sb1 = n0p[MS_STRIDE + 3];
+                const double df = f1 - f0;
+                const double Ac = s0 * Z.h - df, Bc = df - s1 * Z.h, Pc = Ac * Z.omX + Bc * Z.X;
+                V[ia] = Z.omX * f0 + Z.X * f1 + Z.XomX * Pc;
+                Vz[ia] = (df + Z.om2X * Pc + Z.XomX * (Bc - Ac)) * Z.invh;
+                if (ORDER2) Vzz[ia] = (Bc - 2.0 * Ac + 3.0 * (Ac - Bc) * Z.X) * inv2;
+                {   // column of the ax0 finite difference (Eval_Vert_Spline_dfdx / ddfdxdz)
+                    const double* up = base + (A.offu[ia] + B.off[jb]); const double* dn = base + (A.offd[ia] + B.off[jb]);
+                    const double d0 = (up[0] - dn[0]) * A.rg[ia], d1 = (up[MS_STRIDE] - dn[MS_STRIDE]) * A.rg[ia];
+                    const double dd = d1 - d0, A2 = sa0 * Z.h - dd, B2 = dd - sa1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
+                    Ga[ia] = Z.omX * d0 + Z.X * d1 + Z.XomX * P2;
+                    Gaz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;      // Global: App. A-9
+                }
+                {   // column of the ax1 finite difference
+                    const double* up = base + (A.off[ia] + B.offu[jb]); const double* dn = base + (A.off[ia] + B.offd[jb]);
+                    const double d0 = (up[0] - dn[0]) * B.rg[jb], d1 = (up[MS_STRIDE] - dn[MS_STRIDE]) * B.rg[jb];
+                    const double dd = d1 - d0, A2 = sb0 * Z.h - dd, B2 = dd - sb1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
+                    Gb[ia] = Z.omX * d0 + Z.X * d1 + Z.XomX * P2;
+                    Gbz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;
+                }
+            }
+            // ax1 weights of this row (slot jb): tensor weight, its derivative, FD-of-values weight, FD-of-slopes weight
+            const double ey  = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
+            const double eyd = (jb == 1) ? wb.e00 : ((jb == 2) ? wb.e01 : 0.0);
+            const double sy  = (jb == 1) ? wb.S0 : ((jb == 2) ? wb.S1 : 0.0);
+            const double syd = (jb == 1) ? wb.T0 : ((jb == 2) ? wb.T1 : 0.0);
+            const double al  = (jb == 0) ? -wb.p  : ((jb == 1) ? -wb.q  : ((jb == 2) ? wb.p  : wb.q));
+            const double ald = (jb == 0) ? -wb.pd : ((jb == 1) ? -wb.qd : ((jb == 2) ? wb.pd : wb.qd));
+            const double be  = (jb == 0) ? -wb.P  : ((jb == 1) ? -wb.Q  : ((jb == 2) ? wb.P  : wb.Q));
+            const double bed = (jb == 0) ? -wb.Pd : ((jb == 1) ? -wb.Qd : ((jb == 2) ? wb.Pd : wb.Qd));
+            const double wy = ey + be, wyd = eyd + bed;
+
+            const double Fv = ms_HX(wa, V[0], V[1], V[2], V[3]);
+            const double dV0 = V[2] - V[0], dV1 = V[3] - V[1], dG0 = Ga[2] - Ga[0], dG1 = Ga[3] - Ga[1];
+            const double FXv = wa.p * dV0 + wa.q * dV1 + wa.P * dG0 + wa.Q * dG1;
+            const double FGb = ms_HX(wa, Gb[0], Gb[1], Gb[2], Gb[3]);
+            const double EVz = wa.h00 * Vz[1] + wa.h01 * Vz[2];
+            const double BVz = wa.P * (Vz[2] - Vz[0]) + wa.Q * (Vz[3] - Vz[1]);
+            const double GXZ = wa.S0 * Gaz[1] + wa.S1 * Gaz[2];          // used only on the corner rows (ey != 0)
+            const double GYZ = wa.h00 * Gbz[1] + wa.h01 * Gbz[2];
+            acc[0] += wy * Fv;
+            acc[1] += wy * FXv;
+            acc[2] += al * Fv + be * FGb;
+            acc[3] += ey * (EVz + GXZ) + be * BVz + sy * GYZ;
+            if (ORDER2) {
+                const double FXd = wa.pd * dV0 + wa.qd * dV1 + wa.Pd * dG0 + wa.Qd * dG1;
+                const double EVzd = wa.e00 * Vz[1] + wa.e01 * Vz[2];
+                const double BVzd = wa.Pd * (Vz[2] - Vz[0]) + wa.Qd * (Vz[3] - Vz[1]);
+                const double GXZd = wa.T0 * Gaz[1] + wa.T1 * Gaz[2];
+                const double GYZd = wa.e00 * Gbz[1] + wa.e01 * Gbz[2];
+                acc[4] += wy * FXd;
+                acc[5] += ald * Fv + bed * FGb;
+                {   // d2f/dz2 block: only its Py data carry the dx-for-dy slip, the Pxy data are scaled by dx*dy
+                    const double EVzz = wa.h00 * Vzz[1] + wa.h01 * Vzz[2];
+                    const double BVzz = wa.P * (Vzz[2] - Vzz[0]) + wa.Q * (Vzz[3] - Vzz[1]);
+                    acc[6] += ey * (EVzz + BVzz) + (be * qs) * EVzz + be * BVzz;
+                }
+                acc[7] += wyd * FXv;
+                acc[8] += ey * (EVzd + GXZd) + be * BVzd + sy * GYZd;
+                acc[9] += eyd * (EVz + GXZ) + bed * BVz + syd * GYZ;
+            }
+        }
+        if (ORDER2 && !GLOBAL) {            // Global leaves the second derivatives in scaled units (App. A-9)
+            const double ida = 1.0 / A.d, idb = 1.0 / B.d;
+            acc[4] *= ida; acc[5] *= idb; acc[7] *= idb; acc[8] *= ida; acc[9] *= idb;
+        }
+#pragma unroll
+        for (int i = 0; i < 10; i++) out[F][i] = acc[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The scalar wrappers c(), u(), v(), rho() (Eval_Spline_f: Cartesian scales the ax1 slope data by dx, App. A-8) and the
+// vertical derivative wrappers c_diff / u_diff / v_diff (Eval_Spline_df with the same scaling) -- used by travel time,
+// absorption, amplitude, reflection and the per-launch invariants.  vals: T, u, v, rho;  dz: dT/dz, du/dz, dv/dz.
+// ---------------------------------------------------------------------------------------------------------------
+template <bool GLOBAL, bool WITH_RHO, bool WITH_DZ>
+GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in, Cur3& cur, double (&vals)[4], double (&dz)[3]) {
+    const double a = clampd(a_in, g.amin, g.amax), b = clampd(b_in, g.bmin, g.bmax), z = clampd(z_in, g.zmin, g.zmax);
+    cur.ka = ms_find_warm(g.ax0, g.n0, a, cur.ka);
+    cur.kb = ms_find_warm(g.ax1, g.n1, b, cur.kb);
+    cur.kz = ms_find_warm(g.axz, g.nz, z, cur.kz);
+    MsAxis A, B; MsZ Z;
+    ms_axis(A, g.ax0, g.n0, cur.ka, a, (unsigned)(g.n1 * g.nz * MS_STRIDE));
+    ms_axis(B, g.ax1, g.n1, cur.kb, b, (unsigned)(g.nz * MS_STRIDE));
+    ms_zpos(Z, g, z, cur.kz);
+    MsW wa, wb;
+    ms_weights(wa, A, A.d);
+    ms_weights(wb, B, GLOBAL ? B.d : A.d);              // the quirk: ax1 slope data times dx
+    const unsigned kofs = (unsigned)cur.kz * MS_STRIDE;
+#pragma unroll 1
+    for (int F = 0; F < (WITH_RHO ? 4 : 3); F++) {
+        const bool is_rho = (F == 3);
+        const double* base = is_rho ? g.rho : g.tuv + 4 * F;
+        const int lvl = is_rho ? 2 : MS_STRIDE;          // doubles between vertical levels
+        const unsigned ko = is_rho ? (unsigned)cur.kz * 2u : kofs;
+        const unsigned shr = is_rho ? 6u : 1u;           // node offsets were built for the 12-double layout: /6 for the 2-double one
+        double accv = 0.0, accz = 0.0;
+#pragma unroll
+        for (int jb = 0; jb < 4; jb++) {
+            double V[4], Vz[4], Gaz[4], Gbz[4];
+#pragma unroll
+            for (int ia = 0; ia < 4; ia++) {
+                const unsigned o = (A.off[ia] + B.off[jb]) / shr;
+                const double* n0p = base + ko + o;
+                const double f0 = n0p[0], s0 = n0p[1], f1 = n0p[lvl], s1 = n0p[lvl + 1];
+                const double df = f1 - f0;
+                const double Ac = s0 * Z.h - df, Bc = df - s1 * Z.h, Pc = Ac * Z.omX + Bc * Z.X;
+                V[ia] = Z.omX * f0 + Z.X * f1 + Z.XomX * Pc;
+                if (WITH_DZ && !is_rho) {
+                    Vz[ia] = (df + Z.om2X * Pc + Z.XomX * (Bc - Ac)) * Z.invh;
+                    const double sa0 = n0p[2], sb0 = n0p[3], sa1 = n0p[lvl + 2], sb1 = n0p[lvl + 3];
+                    {
+                        const double* up = base + ko + (A.offu[ia] + B.off[jb]); const double* dn = base + ko + (A.offd[ia] + B.off[jb]);
+                        const double d0 = (up[0] - dn[0]) * A.rg[ia], d1 = (up[lvl] - dn[lvl]) * A.rg[ia];
+                        const double dd = d1 - d0, A2 = sa0 * Z.h - dd, B2 = dd - sa1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
+                        Gaz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;
+                    }
+                    {
+                        const double* up = base + ko + (A.off[ia] + B.offu[jb]); const double* dn = base + ko + (A.off[ia] + B.offd[jb]);
+                        const double d0 = (up[0] - dn[0]) * B.rg[jb], d1 = (up[lvl] - dn[lvl]) * B.rg[jb];
+                        const double dd = d1 - d0, A2 = sb0 * Z.h - dd, B2 = dd - sb1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
+                        Gbz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;
+                    }
+                }
+            }
+            const double ey = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
+            const double sy = (jb == 1) ? wb.S0 : ((jb == 2) ? wb.S1 : 0.0);
+            const double be = (jb == 0) ? -wb.P : ((jb == 1) ? -wb.Q : ((jb == 2) ? wb.P : wb.Q));
+            // the Pxy block of Eval_Spline_f / _df is scaled by dx*dy, only the Py block by the slipped scale: separate the two
+            const double be_true = GLOBAL ? be : be * (B.d / A.d);
+            {
+                const double EV = wa.h00 * V[1] + wa.h01 * V[2];
+                const double BV = wa.P * (V[2] - V[0]) + wa.Q * (V[3] - V[1]);
+                accv += ey * (EV + BV) + be * EV + be_true * BV;
+            }
+            if (WITH_DZ && !is_rho) {
+                const double EVz = wa.h00 * Vz[1] + wa.h01 * Vz[2];
+                const double BVz = wa.P * (Vz[2] - Vz[0]) + wa.Q * (Vz[3] - Vz[1]);
+                const double GXZ = wa.S0 * Gaz[1] + wa.S1 * Gaz[2];
+                const double GYZ = wa.h00 * Gbz[1] + wa.h01 * Gbz[2];
+                accz += ey * (EVz + GXZ) + be_true * BVz + sy * GYZ;
+            }
+        }
+        vals[F] = accv;
+        if (WITH_DZ && !is_rho) dz[F] = accz;
+    }
+}
+
+}  // namespace geoac

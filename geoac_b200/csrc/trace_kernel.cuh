@@ -16,11 +16,14 @@
 //  * RK4 combination in the reference's association order  y + k1/6 + k2/3 + k3/3 + k4/6  (Solver.cpp:54), built
 //    on the fly so no k_i is kept.
 #pragma once
+#include <type_traits>
 #include "core.cuh"
+#include "mspline.cuh"
 
 namespace geoac {
 
 struct TraceArgs {
+    Grid3D grid;                // range-dependent variants: node tables in global memory (L1/L2 resident working set)
     const double* table;        // global copy of the table (TAB_NARR * n_pad doubles, 16-byte aligned)
     int table_n, table_npad;
     double table_xmin, table_xmax;
@@ -77,18 +80,19 @@ struct Lane {
     static constexpr int NEQ = EQ::NEQ;
     double y[NEQ];
     typename EQ::RayC rc;
-    int cur, bounce, ksteps;
+    typename EQ::Cursor cur;
+    int bounce, ksteps;
     int64_t ray;
     double tt_total, att_total, tt_b, att_b, zmax;
 
-    GEOAC_HD void start(const LaunchConsts& L, const Table1D& T, int64_t idx, double theta, double phi) {
-        ray = idx; bounce = 0; ksteps = 0; cur = 0;
+    GEOAC_HD void start(const LaunchConsts& L, const typename EQ::Atmo& T, int64_t idx, double theta, double phi) {
+        ray = idx; bounce = 0; ksteps = 0; cur = typename EQ::Cursor{};
         tt_total = att_total = tt_b = att_b = zmax = 0.0;
         EQ::init(L, T, theta, phi, rc, y, cur);
     }
 
     // prev[i * pstride] holds y_{k-1}[i]; returns false when the ray has ended
-    GEOAC_HD bool advance(const LaunchConsts& L, const Table1D& T, double* prev, int pstride, const RecOut& o) {
+    GEOAC_HD bool advance(const LaunchConsts& L, const typename EQ::Atmo& T, double* prev, int pstride, const RecOut& o) {
         zmax = fmax(zmax, EQ::altitude(y));                    // running turning height over m < k (App. A-3)
         const double ds = EQ::step_size(L, y);
         double acc[NEQ], p[NEQ], f[NEQ];
@@ -186,7 +190,7 @@ __device__ __forceinline__ void tma_stage_table(double* dst, const double* src, 
 }
 
 template <class EQ, int BLOCK, bool TABLE_IN_SMEM>
-__global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__ TraceArgs a) {
     constexpr int NEQ = EQ::NEQ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [LaunchConsts][mbarrier][prev: NEQ*BLOCK doubles][table]
@@ -197,13 +201,17 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const TraceArgs a) {
 
     for (int i = threadIdx.x; i < (int)(sizeof(LaunchConsts) / 8); i += BLOCK)
         reinterpret_cast<double*>(Ls)[i] = reinterpret_cast<const double*>(a.consts)[i];
-    Table1D T;
-    T.n = a.table_n; T.n_pad = a.table_npad; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
-    if (TABLE_IN_SMEM) {
-        tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_npad * sizeof(double)), bar);
-        T.base = tab_s;
+    typename EQ::Atmo T;
+    if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) {
+        T = a.grid;
     } else {
-        T.base = a.table;
+        T.n = a.table_n; T.n_pad = a.table_npad; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
+        if (TABLE_IN_SMEM) {
+            tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_npad * sizeof(double)), bar);
+            T.base = tab_s;
+        } else {
+            T.base = a.table;
+        }
     }
     __syncthreads();
     const LaunchConsts& L = *Ls;

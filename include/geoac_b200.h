@@ -141,6 +141,15 @@ int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_
 int geoac_load_met_1d(const char* path, const char* format, double z_grnd_taper, int global_taper,
                       int cap, int* n, double* z, double* T, double* u, double* v, double* rho);
 
+/* Host helper mirroring Load_G2S_Multi (Code/Atmo/G2S_MultiDimSpline3D.cpp:139-189, G2S_GlobalMultiDimSpline3D.cpp:142-199):
+ * reads `<prefix><i0*n1+i1>.met` for every horizontal node plus the two node-coordinate files (x/y [km], or lat/lon
+ * [deg] converted to radians when `global`), converts winds m/s -> km/s and applies the loader's ground taper.
+ * Outputs are what geoac_set_atmosphere_3d expects; fields are [n0][n1][nz] with nz taken from the first profile
+ * (T, u, v, rho must hold cap0*cap1*capz doubles if the node counts are not known in advance). */
+int geoac_load_met_grid(const char* prefix, const char* loc0, const char* loc1, const char* format, int global,
+                        int cap0, int cap1, int capz, int* n0, int* n1, int* nz,
+                        double* ax0, double* ax1, double* axz, double* T, double* u, double* v, double* rho);
+
 /* Number of state equations for (variant, calc_amp): GeoAc_SetEqCnt, Code/GeoAc/GeoAc.Interface.cpp:21-41. */
 int geoac_eq_count(int variant, int calc_amp);
 

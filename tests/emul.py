@@ -17,7 +17,7 @@ ip = C.POINTER(C.c_int32)
 
 def build(force=False):
     csrc = os.path.join(HERE, "..", "geoac_b200", "csrc")
-    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cuh", ".hpp"))]
     if force or not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-mfma", "-ffp-contract=fast", SRC, "-o", SO])
     return SO
@@ -67,4 +67,18 @@ def trace(variant, params, atmo_arrays, theta, phi):
     rec = np.zeros((abi.NFIELDS, nr, n_rec)); status = np.zeros((nr, n_rec), dtype=np.int32); n_steps = np.zeros((nr, n_rec), dtype=np.int32)
     total = L.emul_trace_1d(variant, C.byref(params), n, n_pad, tab.ctypes.data_as(dp), nr, theta.ctypes.data_as(dp), phi.ctypes.data_as(dp),
                             rec.ctypes.data_as(dp), status.ctypes.data_as(ip), n_steps.ctypes.data_as(ip))
+    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total}
+
+
+def trace_grid(variant, params, grid_arrays, theta, phi):
+    """Range-dependent variants: grid_arrays = ax0, ax1, axz, T, u, v, rho as geoac_set_atmosphere_3d takes them."""
+    L = C.CDLL(build())
+    L.emul_trace_3d.restype = C.c_long
+    L.emul_trace_3d.argtypes = [C.c_int, C.POINTER(abi.GeoacParams), C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, C.c_long, dp, dp, dp, ip, ip]
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in grid_arrays]
+    theta = np.ascontiguousarray(theta, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
+    nr = len(theta); n_rec = params.bounces + 1
+    rec = np.zeros((abi.NFIELDS, nr, n_rec)); status = np.zeros((nr, n_rec), dtype=np.int32); n_steps = np.zeros((nr, n_rec), dtype=np.int32)
+    total = L.emul_trace_3d(variant, C.byref(params), len(arrs[0]), len(arrs[1]), len(arrs[2]), *[a.ctypes.data_as(dp) for a in arrs], nr,
+                            theta.ctypes.data_as(dp), phi.ctypes.data_as(dp), rec.ctypes.data_as(dp), status.ctypes.data_as(ip), n_steps.ctypes.data_as(ip))
     return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total}

@@ -12,12 +12,14 @@
 #include "../../geoac_b200/csrc/eq_global.cuh"
 #define HAVE_GLOBAL 1
 #endif
+#include "../../geoac_b200/csrc/eq_rngdep.cuh"
 #include "../../geoac_b200/csrc/trace_kernel.cuh"
+#include "../../geoac_b200/csrc/host_tables.hpp"
 
 using namespace geoac;
 
 template <class EQ>
-static long run(const LaunchConsts& L, const Table1D& T, long n, const double* th, const double* ph, RecOut o) {
+static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const double* th, const double* ph, RecOut o) {
     long steps = 0;
     std::vector<double> prev(EQ::NEQ, 0.0);
     for (long i = 0; i < n; i++) {
@@ -55,4 +57,32 @@ extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, int n_p
 #endif
     }
     return -1;
+}
+
+// range-dependent variants: fields dense [n0][n1][nz] exactly as geoac_set_atmosphere_3d receives them
+extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1, int nz, const double* ax0, const double* ax1, const double* axz,
+                              const double* Tf, const double* uf, const double* vf, const double* rhof, long n_rays,
+                              const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps) {
+    const bool glob = variant == GEOAC_GLOBAL_RNGDEP;
+    std::vector<double> z, tuv, rh;
+    build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, Tf, uf, vf, rhof, z, tuv, rh);
+    Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = ax0; g.ax1 = ax1; g.axz = z.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
+    g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
+    LaunchConsts L; std::memset(&L, 0, sizeof L);
+    L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
+    L.z_grnd = p->z_grnd; L.tweak_abs = p->tweak_abs; L.freq = p->freq;
+    for (int i = 0; i < 2; i++) { L.box_min[i] = p->box_min[i]; L.box_max[i] = p->box_max[i]; }
+    for (int i = 0; i < 3; i++) L.src[i] = p->src[i];
+    if (!glob) L.src[2] = std::max(p->z_grnd, p->src[2]); else L.src[0] = std::max(p->z_grnd, p->src[0]);
+    L.bounces = p->bounces; L.calc_amp = p->calc_amp;
+    L.seg_mode = p->accum_per_segment ? 1 : 0;
+    L.step_limit = (int)(p->ray_limit * (int)(1.0 / (p->ds_min * 10)));
+    L.per_bounce_zmax = 1;
+    fill_launch_consts_3d(L, g, variant);
+    RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
+    std::fill(rec, rec + (size_t)GEOAC_NFIELDS * o.n_slots, 0.0);
+    std::fill(status, status + o.n_slots, 0); std::fill(n_steps, n_steps + o.n_slots, 0);
+    const bool amp = p->calc_amp != 0;
+    if (!glob) return amp ? run<Eq3DRD<true>>(L, g, n_rays, th, ph, o) : run<Eq3DRD<false>>(L, g, n_rays, th, ph, o);
+    return amp ? run<EqGlobalRD<true>>(L, g, n_rays, th, ph, o) : run<EqGlobalRD<false>>(L, g, n_rays, th, ph, o);
 }

@@ -12,10 +12,13 @@ from tests import util
 pytestmark = pytest.mark.gpu
 
 
-def _tracer_for(variant, kv):
-    z, T, u, v, rho = g.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+def _tracer_for(variant, kv, case=None):
     tr = g.Tracer(variant, 0)
-    tr.set_atmosphere_1d(z, T, u, v, rho)
+    if util.is_rngdep(variant):
+        tr.set_atmosphere_3d(*util.load_grid(case))
+    else:
+        z, T, u, v, rho = g.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+        tr.set_atmosphere_1d(z, T, u, v, rho)
     tr.params = util.apply_keys(variant, tr.params, kv)
     return tr
 
@@ -25,11 +28,11 @@ def _tracer_for(variant, kv):
 AMP_RTOL = 1e-6
 
 
-@pytest.mark.parametrize("name", [c for c in util.golden_cases() if not c.startswith(("3drngdep", "globalrngdep"))])
+@pytest.mark.parametrize("name", util.golden_cases())
 def test_cuda_matches_reference_golden(name, capsys):
     d, kv = util.load_case(name)
     variant = int(d["variant"])
-    tr = _tracer_for(variant, kv)
+    tr = _tracer_for(variant, kv, d)
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
     out = tr.trace(th, ph)
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}

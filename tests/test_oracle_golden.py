@@ -47,7 +47,7 @@ def test_golden_has_reference_invariants():
     assert np.allclose(r[:, 2] / r[:, 0], 3.0, rtol=2e-3)
 
 
-@pytest.mark.parametrize("name", ["3d_elevated", "2d_noamp", "3d_noamp"])
+@pytest.mark.parametrize("name", ["3d_elevated", "2d_noamp", "3d_noamp", "global_segmode", "3drngdep_sub", "globalrngdep_sub"])
 def test_device_math_host_emulation(oracle, name):
     """The per-ray device code (geoac_b200/csrc/*.cuh, GEOAC_HD) compiled with g++ -mfma must agree with the reference
     golden vectors to the GPU tolerance.  This is a build-container debugging aid, not a product path; the real gate
@@ -55,11 +55,17 @@ def test_device_math_host_emulation(oracle, name):
     from tests import emul
     d, kv = util.load_case(name)
     variant = int(d["variant"])
-    arrs = oracle.load_met_1d(util.TOY, global_taper=util.is_global(variant))
-    at = oracle.atmo1d(util.is_global(variant), *arrs)
-    p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
-    out = emul.trace(variant, p, arrs, th, ph)
+    if util.is_rngdep(variant):
+        arrs = util.load_grid(d)
+        at = oracle.atmo3d(util.is_global(variant), *arrs)
+        p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
+        out = emul.trace_grid(variant, p, arrs, th, ph)
+    else:
+        arrs = oracle.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+        at = oracle.atmo1d(util.is_global(variant), *arrs)
+        p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
+        out = emul.trace(variant, p, arrs, th, ph)
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
     problems, _ = util.compare_records(out, want, variant, p.calc_amp, util.RTOL, name, amp_rtol=1e-6)
     assert not problems, "\n".join(problems)
