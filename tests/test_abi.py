@@ -56,6 +56,21 @@ def test_host_loader_matches_oracle_loader(built_lib, oracle):
     assert len(a[0]) == 1400
 
 
+def test_grid_loader_matches_oracle_loader_and_fixture(built_lib, oracle, tmp_path):
+    """geoac_load_met_grid (product host code) == oracle loader == the committed grid fixture, bit for bit, for both variants."""
+    from tests.golden import make_grid
+    files = make_grid.write_cartesian(str(tmp_path / "c"), np.arange(-500.0, 501.0, 200.0), np.arange(-450.0, 451.0, 150.0))
+    a, b = api.load_met_grid(*files), oracle.load_met_grid(*files)
+    fix = np.load(os.path.join(util.GOLD, "grid_cart.npz"))
+    for x, y, k in zip(a, b, ("ax0", "ax1", "axz", "T", "u", "v", "rho")):
+        assert np.array_equal(x, y) and np.array_equal(x, fix[k])
+    files = make_grid.write_global(str(tmp_path / "g"), np.arange(20.0, 51.0, 6.0), np.arange(-15.0, 16.0, 5.0))
+    a, b = api.load_met_grid(*files, is_global=True), oracle.load_met_grid(*files, is_global=True)
+    fix = np.load(os.path.join(util.GOLD, "grid_glob.npz"))
+    for x, y, k in zip(a, b, ("ax0", "ax1", "axz", "T", "u", "v", "rho")):
+        assert np.array_equal(x, y) and np.array_equal(x, fix[k])
+
+
 def test_prop_angles_reproduce_the_mains_loops():
     th_deg, ph_deg, th, ph = api.prop_angles(0.5, 45.0, 0.5, -90.0, -90.0, 1.0)       # GeoAc2D defaults: 90 rays
     assert len(th) == 90 and th_deg[0] == 0.5 and ph_deg[0] == -90.0
