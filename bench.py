@@ -242,6 +242,8 @@ def run_ours(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps        # trace kernel (+4 memsets) per launch
     total_steps, _ = tr.last_stats()                                    # RK4 steps of one pass on this rank
+    lane_occ = tr.last_lane_occupancy()
+    launches_per_pass = tr.last_kernel_launches()
     arrivals = int((d_status == abi.ST_ARRIVAL).sum().item())
 
     t = torch.tensor([dev_ms, float(total_steps), float(n)], dtype=torch.float64, device=dev)
@@ -286,13 +288,13 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic launch-angle grid, ToyAtmo.met profile (the reference's shipped fixture)",
             "config": {"workload": workload_desc(args.workload), "rays_per_gpu": n, "rk4_steps_per_pass_per_gpu": total_steps,
-                       "arrival_records_per_pass": arrivals, "l2": "256 MiB buffer written between iterations (L2 flush); "
+                       "arrival_records_per_pass": arrivals, "lane_occupancy": round(lane_occ, 4), "l2": "256 MiB buffer written between iterations (L2 flush); "
                        "the kernel's working set is the 112 KB table in shared memory", "multi_gpu": "replicated grid per rank, azimuth offset by rank"},
             "e2e": {"value": e2e_rays, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "passes": e2e_k},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * launches_per_pass,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
-                         "traffic": None, "kernel": "geoac::trace_kernel<Eq3D<true>,256,true>", "kernel_ms_per_launch": kern_ms,
+                         "traffic": None, "kernel": "geoac::trace_kernel<Eq3D<true>,512,true>", "kernel_ms_per_launch": kern_ms,
                          "algorithmic_flops_per_rk4_step": flops_step,
                          "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
                                         "HBM is not the bound: ~0.03 B/step of record traffic"},

@@ -51,6 +51,8 @@ def lib():
         L.geoac_load_met_grid.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                           C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.geoac_eq_count.argtypes = [C.c_int, C.c_int]
+        L.geoac_last_trace_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.geoac_selftest_math.argtypes = [C.c_void_p, C.c_int, _dp]
         L.geoac_measure_fp64_peak.restype = C.c_double
         L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _LIB = L
@@ -60,7 +62,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_device",
-    "geoac_last_trace_stats", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
+    "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
 ]
 
 
@@ -181,6 +183,19 @@ class Tracer:
         ms = C.c_double(0)
         self._check(lib().geoac_last_trace_stats(self._h, C.byref(s), C.byref(ms)), "geoac_last_trace_stats")
         return s.value, ms.value
+
+    def last_lane_occupancy(self):
+        """Average fraction of a warp's 32 lanes that carried a ray during the last trace."""
+        steps, _ = self.last_stats()
+        t = C.c_int64(0)
+        self._check(lib().geoac_last_trace_warp_trips(self._h, C.byref(t)), "geoac_last_trace_counters")
+        return steps / (32.0 * t.value) if t.value else 0.0
+
+    def selftest_math(self, n_per_thread=2000):
+        """Max relative error of the kernel's rcp / rsqrt / sqrt / exp / exp10 against the CUDA math library."""
+        out = np.zeros(5)
+        self._check(lib().geoac_selftest_math(self._h, n_per_thread, _p(out)), "geoac_selftest_math")
+        return dict(zip(("rcp", "rsqrt", "sqrt", "exp", "exp10"), out.tolist()))
 
     def measure_fp64_peak(self):
         ms = C.c_double(0)

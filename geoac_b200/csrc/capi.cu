@@ -33,7 +33,7 @@ struct geoac_ctx {
     std::string err;
     // 1-D table
     bool have_atmo = false;
-    int n = 0, n_pad = 0;
+    int n = 0;
     double xmin = 0, xmax = 0;
     std::vector<double> h_table;
     double* d_table = nullptr;
@@ -43,6 +43,9 @@ struct geoac_ctx {
     double *d_tuv = nullptr, *d_rho = nullptr, *d_ax = nullptr;
     LaunchConsts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;     // [0] ray counter, [1] total steps
+    double* d_prev = nullptr; size_t cap_prev = 0; // y_{k-1} scratch of the trace kernel
+    uint32_t *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr; int64_t cap_order = 0;   // longest-ray-first scheduling
+    int last_launches = 0;
     // staging for the host-buffer entry point
     double *d_theta = nullptr, *d_phi = nullptr, *d_rec = nullptr;
     int32_t *d_status = nullptr, *d_nsteps = nullptr;
@@ -98,7 +101,7 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
            && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess
            && cudaMalloc(&ctx->d_consts, sizeof(LaunchConsts)) == cudaSuccess
-           && cudaMalloc(&ctx->d_counters, 2 * sizeof(unsigned long long)) == cudaSuccess;
+           && cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); delete ctx; return bail(GEOAC_ERR_CUDA, "context allocation failed: " + m); }
     if (status) *status = GEOAC_OK;
     return ctx;
@@ -107,7 +110,8 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
 extern "C" void geoac_destroy(geoac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters); cudaFree(ctx->d_prev);
+    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist);
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -157,24 +161,25 @@ extern "C" int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, c
     for (int i = 1; i < n; i++) if (!(z[i] > z[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "altitudes must be strictly increasing");
     cudaSetDevice(ctx->device);
     const bool glob = ctx->variant == GEOAC_GLOBAL;
-    const int n_pad = (n + 1) & ~1;                       // keep every array 16-byte aligned for the bulk copy
-    std::vector<double> x(n);
+    std::vector<double> x(n), col(n), slo(n);
     for (int i = 0; i < n; i++) { x[i] = z[i]; if (glob) x[i] += kREarth; }   // r_vals[nr] += r_earth
-    ctx->h_table.assign((size_t)TAB_NARR * n_pad, 0.0);
+    ctx->h_table.assign((size_t)TAB_NARR * n, 0.0);                           // one record per level (core.cuh)
     double* tb = ctx->h_table.data();
     for (int i = 0; i < n; i++) {
-        tb[TAB_X * n_pad + i] = x[i];
-        tb[TAB_INVH * n_pad + i] = (i + 1 < n) ? 1.0 / (x[i + 1] - x[i]) : 0.0;
-        tb[TAB_T * n_pad + i] = T[i]; tb[TAB_U * n_pad + i] = u[i]; tb[TAB_V * n_pad + i] = v[i]; tb[TAB_RHO * n_pad + i] = rho[i];
+        tb[(size_t)i * TAB_NARR + TAB_X] = x[i];
+        tb[(size_t)i * TAB_NARR + TAB_INVH] = (i + 1 < n) ? 1.0 / (x[i + 1] - x[i]) : 0.0;
     }
-    natural_slopes(x, tb + TAB_T * n_pad, tb + TAB_ST * n_pad);
-    natural_slopes(x, tb + TAB_U * n_pad, tb + TAB_SU * n_pad);
-    natural_slopes(x, tb + TAB_V * n_pad, tb + TAB_SV * n_pad);
-    natural_slopes(x, tb + TAB_RHO * n_pad, tb + TAB_SRHO * n_pad);
+    const double* fields[4] = { T, u, v, rho };
+    const int slots[4] = { TAB_T, TAB_U, TAB_V, TAB_RHO };
+    for (int f = 0; f < 4; f++) {
+        for (int i = 0; i < n; i++) col[i] = fields[f][i];
+        natural_slopes(x, col.data(), slo.data());
+        for (int i = 0; i < n; i++) { tb[(size_t)i * TAB_NARR + slots[f]] = col[i]; tb[(size_t)i * TAB_NARR + slots[f] + 1] = slo[i]; }
+    }
     cudaFree(ctx->d_table); ctx->d_table = nullptr;
     CK(cudaMalloc(&ctx->d_table, ctx->h_table.size() * sizeof(double)));
     CK(cudaMemcpy(ctx->d_table, tb, ctx->h_table.size() * sizeof(double), cudaMemcpyHostToDevice));
-    ctx->n = n; ctx->n_pad = n_pad; ctx->xmin = x[0]; ctx->xmax = x[n - 1];
+    ctx->n = n; ctx->xmin = x[0]; ctx->xmax = x[n - 1];
     // GeoAc_SetPropRegion: G2S_Spline1D.cpp:22-28 / G2S_GlobalSpline1D.cpp:22-30
     ctx->prm.vert_limit = ctx->xmax;
     ctx->prm.range_limit = glob ? 1500.0 : 10000.0;
@@ -223,10 +228,10 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
 }
 
 // ---- per-launch invariants, computed on the device with the same spline routines the kernel uses ----
-__global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, const double* table, int n, int n_pad,
+__global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, const double* table, int n,
                                     double xmin, double xmax, int variant) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Table1D T; T.base = table; T.n = n; T.n_pad = n_pad; T.xmin = xmin; T.xmax = xmax;
+    Table1D T; T.base = table; T.n = n; T.xmin = xmin; T.xmax = xmax;
     LaunchConsts L = in;
     fill_launch_consts_1d(L, T, variant);
     *out = L;
@@ -254,7 +259,7 @@ static int refresh_consts(geoac_ctx* ctx) {
     L.step_limit = (int)(p.ray_limit * (int)(1.0 / (p.ds_min * 10)));                                     // Solver.cpp:14
     L.per_bounce_zmax = (ctx->variant == GEOAC_3D_RNGDEP || ctx->variant == GEOAC_GLOBAL_RNGDEP);         // App. A-3
     if (ctx->is_grid) setup_consts_grid_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->grid, ctx->variant);
-    else setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->n_pad, ctx->xmin, ctx->xmax, ctx->variant);
+    else setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->xmin, ctx->xmax, ctx->variant);
     CK(cudaGetLastError());
     ctx->consts_dirty = false;
     return GEOAC_OK;
@@ -262,12 +267,14 @@ static int refresh_consts(geoac_ctx* ctx) {
 
 // ---- kernel launch ----
 template <class EQ, int BLOCK>
-static int launch_trace(geoac_ctx* ctx, const TraceArgs& a, cudaStream_t st) {
+static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
-    const size_t fixed = ((sizeof(LaunchConsts) + 15) / 16) * 16 + 16 + (size_t)EQ::NEQ * BLOCK * sizeof(double);
-    const size_t tab_bytes = kGrid ? 0 : (size_t)TAB_NARR * ctx->n_pad * sizeof(double);
+    const size_t lane_doubles = ((size_t)LaneLayout<EQ>::STRIDE * BLOCK + 1) & ~(size_t)1;
+    const size_t fixed = ((sizeof(LaunchConsts) + 15) / 16) * 16 + 16 + lane_doubles * sizeof(double);
+    const size_t tab_bytes = kGrid ? 0 : (size_t)TAB_NARR * ctx->n * sizeof(double);
     int max_optin = 0;
     CK(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    if (fixed > (size_t)max_optin) return fail(ctx, GEOAC_ERR_CUDA, "lane records do not fit in shared memory");
     const bool in_smem = !kGrid && fixed + tab_bytes <= (size_t)max_optin;
     const size_t smem = in_smem ? fixed + tab_bytes : fixed;
     const void* fn = in_smem ? (const void*)trace_kernel<EQ, BLOCK, true> : (const void*)trace_kernel<EQ, BLOCK, false>;
@@ -279,8 +286,42 @@ static int launch_trace(geoac_ctx* ctx, const TraceArgs& a, cudaStream_t st) {
     const int64_t warps_needed = (a.n_rays + 31) / 32;
     const int64_t ctas_needed = std::max<int64_t>(1, (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32));
     const int grid = (int)std::min<int64_t>((int64_t)ctx->sm_count * per_sm, ctas_needed);
+    if (NeedsPrev<EQ>::value) {
+        const size_t need = (size_t)EQ::NEQ * grid * BLOCK * sizeof(double);
+        if (need > ctx->cap_prev) {
+            cudaFree(ctx->d_prev); ctx->d_prev = nullptr; ctx->cap_prev = 0;
+            CK(cudaMalloc(&ctx->d_prev, need));
+            ctx->cap_prev = need;
+        }
+    }
+    a.prev = ctx->d_prev;
+    a.order = nullptr;
+    ctx->last_launches = 0;
+    // longest-predicted-ray-first claim order, when a lane will process more than one ray (see trace_kernel.cuh)
+    // GEOAC_B200_LPT: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
+    const char* lpt_env = std::getenv("GEOAC_B200_LPT");
+    const int lpt_mode = lpt_env ? std::atoi(lpt_env) : 1;
+    if ((lpt_mode == 2 || (lpt_mode == 1 && a.n_rays > (int64_t)grid * BLOCK)) && a.n_rays < ((int64_t)1 << 32)) {
+        if (a.n_rays > ctx->cap_order) {
+            cudaFree(ctx->d_cost); cudaFree(ctx->d_order); ctx->d_cost = ctx->d_order = nullptr; ctx->cap_order = 0;
+            CK(cudaMalloc(&ctx->d_cost, sizeof(uint32_t) * a.n_rays)); CK(cudaMalloc(&ctx->d_order, sizeof(uint32_t) * a.n_rays));
+            ctx->cap_order = a.n_rays;
+        }
+        if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 1)));
+        CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 1), st));
+        uint32_t* cmax = ctx->d_hist + kCostBuckets;
+        const int sblocks = (int)std::min<int64_t>((a.n_rays + 127) / 128, (int64_t)ctx->sm_count * 16);
+        scout_kernel<typename EQ::Scout><<<sblocks, 128, 0, st>>>(a, ctx->d_cost, cmax);
+        order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, cmax, ctx->d_hist);
+        order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
+        order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, cmax, ctx->d_hist, ctx->d_order);
+        CK(cudaGetLastError());
+        a.order = ctx->d_order;
+        ctx->last_launches += 4;
+    }
     void* args[] = { (void*)&a };
     CK(cudaLaunchKernel(fn, dim3(grid), dim3(BLOCK), args, smem, st));
+    ctx->last_launches += 1;
     return GEOAC_OK;
 }
 
@@ -295,22 +336,30 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     }
     const int n_rec = ctx->prm.bounces + 1;
     const int64_t n_slots = n_rays * n_rec;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(d_rec, 0, sizeof(double) * GEOAC_NFIELDS * n_slots, st));
     CK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_slots, st));
     CK(cudaMemsetAsync(d_n_steps, 0, sizeof(int32_t) * n_slots, st));
     TraceArgs a;
     a.grid = ctx->grid;
-    a.table = ctx->d_table; a.table_n = ctx->n; a.table_npad = ctx->n_pad; a.table_xmin = ctx->xmin; a.table_xmax = ctx->xmax;
+    a.table = ctx->d_table; a.table_n = ctx->n; a.table_xmin = ctx->xmin; a.table_xmax = ctx->xmax;
     a.consts = ctx->d_consts; a.theta = d_theta; a.phi = d_phi; a.n_rays = n_rays; a.n_rec = n_rec;
     a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
-    a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1;
+    a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1; a.warp_trips = ctx->d_counters + 2;
     const bool amp = ctx->prm.calc_amp != 0;
     switch (ctx->variant) {
         case GEOAC_2D:     return amp ? launch_trace<Eq2D<true>, 512>(ctx, a, st)     : launch_trace<Eq2D<false>, 512>(ctx, a, st);
-        case GEOAC_3D:     return amp ? launch_trace<Eq3D<true>, 256>(ctx, a, st)     : launch_trace<Eq3D<false>, 512>(ctx, a, st);
+        case GEOAC_3D: {
+            if (!amp) return launch_trace<Eq3D<false>, 512>(ctx, a, st);
+            // tuning knob for experiments (lanes per SM vs registers per lane); the default is the measured best
+            const char* e = std::getenv("GEOAC_B200_BLOCK");
+            const int blk = e ? std::atoi(e) : 512;
+            if (blk == 256) return launch_trace<Eq3D<true>, 256>(ctx, a, st);
+            if (blk == 384) return launch_trace<Eq3D<true>, 384>(ctx, a, st);
+            return launch_trace<Eq3D<true>, 512>(ctx, a, st);
+        }
 #ifdef GEOAC_HAVE_GLOBAL
-        case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 256>(ctx, a, st) : launch_trace<EqGlobal<false>, 256>(ctx, a, st);
+        case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 384>(ctx, a, st) : launch_trace<EqGlobal<false>, 512>(ctx, a, st);
 #endif
         case GEOAC_3D_RNGDEP:     return amp ? launch_trace<Eq3DRD<true>, 128>(ctx, a, st)     : launch_trace<Eq3DRD<false>, 128>(ctx, a, st);
         case GEOAC_GLOBAL_RNGDEP: return amp ? launch_trace<EqGlobalRD<true>, 128>(ctx, a, st) : launch_trace<EqGlobalRD<false>, 128>(ctx, a, st);
@@ -373,6 +422,16 @@ extern "C" int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, doub
     ctx->last_steps = (int64_t)cnt[1];
     if (total_steps) *total_steps = ctx->last_steps;
     if (kernel_ms) *kernel_ms = ctx->last_ms;
+    return GEOAC_OK;
+}
+
+extern "C" int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kernel_launches) {
+    if (!ctx) return GEOAC_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    unsigned long long t = 0;
+    CK(cudaMemcpy(&t, ctx->d_counters + 2, sizeof t, cudaMemcpyDeviceToHost));
+    if (warp_trips) *warp_trips = (int64_t)t;
+    if (kernel_launches) *kernel_launches = ctx->last_launches;
     return GEOAC_OK;
 }
 
@@ -443,6 +502,39 @@ extern "C" int geoac_load_met_grid(const char* prefix, const char* loc0, const c
     }
     *n0 = c0; *n1 = c1; *nz = cz;
     return cz >= 3 ? GEOAC_OK : GEOAC_ERR_IO;
+}
+
+// ---- accuracy self-test of the branch-free FP64 primitives (core.cuh) against libdevice, on the device ----
+__global__ void selftest_math_kernel(int n, unsigned long long* worst) {        // worst[5]: rcp, rsqrt, sqrt, exp, exp10 (bits of max rel err)
+    unsigned long long s = 0x9E3779B97F4A7C15ull * (blockIdx.x * blockDim.x + threadIdx.x + 1);
+    auto uni = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) * (1.0 / 9007199254740992.0); };
+    double w[5] = { 0, 0, 0, 0, 0 };
+    for (int i = 0; i < n; i++) {
+        const double mant = 1.0 + uni(), ex = floor(uni() * 1800.0) - 900.0;
+        const double x = ldexp(mant, (int)ex);                                  // 2^-900 .. 2^900
+        const double xe = (uni() * 2.0 - 1.0) * 690.0, xt = (uni() * 2.0 - 1.0) * 290.0;
+        const double a[1] = { xe }, b[1] = { xt }; double oa[1], ob[1];
+        g_exp_n<false, 1>(a, oa); g_exp_n<true, 1>(b, ob);
+        double rs; const double sq = g_sqrt_rs(x, rs);
+        const double got[5] = { g_rcp(x), g_rsqrt(x), sq, oa[0], ob[0] };
+        const double ref[5] = { 1.0 / x, rsqrt(x), sqrt(x), exp(xe), exp10(xt) };
+        for (int k = 0; k < 5; k++) w[k] = fmax(w[k], fabs(got[k] - ref[k]) / fabs(ref[k]));
+    }
+    for (int k = 0; k < 5; k++) atomicMax(worst + k, (unsigned long long)__double_as_longlong(w[k]));   // positive doubles order like integers
+}
+
+extern "C" int geoac_selftest_math(geoac_ctx* ctx, int n_per_thread, double* max_rel_err) {
+    if (!ctx || !max_rel_err || n_per_thread <= 0) return GEOAC_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, 5 * sizeof(unsigned long long)));
+    selftest_math_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(n_per_thread, d);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(max_rel_err, d, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return GEOAC_OK;
 }
 
 // ---- FP64 roofline denominator: dependent-chain-free DFMA loop, 8 independent accumulators per thread ----

@@ -11,6 +11,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 #include "../../include/geoac_b200.h"
 
 #ifdef __CUDACC__
@@ -29,74 +30,163 @@ constexpr double kR    = 287.05;
 constexpr double kGamR = 0.00040187;                    // Code/Atmo/G2S_Spline1D.cpp:332
 constexpr double kREarth = 6370.0;                      // Code/Atmo/G2S_GlobalSpline1D.cpp:35
 
-#if defined(__CUDA_ARCH__)
-GEOAC_HD double g_rsqrt(double x) { return rsqrt(x); }
-GEOAC_HD double g_rcbrt(double x) { return rcbrt(x); }
-GEOAC_HD double g_exp10(double x) { return exp10(x); }
-GEOAC_HD double g_rcp(double x)   { return 1.0 / x; }
+// ---------------------------------------------------------------------------------------------------------------
+// Branch-free FP64 primitives for the per-step hot loop.  libdevice's exp / division / sqrt carry a slow-path test
+// (BSSY/BSYNC + branch) per call and materialise every polynomial coefficient with two moves; the hot loop does ~20
+// exponentials, ~10 reciprocals and ~8 square roots per RK4 step on operands that are known to be normal, so these
+// versions drop the special-case handling and read their coefficients as constant-bank operands of the DFMAs.
+// All are accurate to <= 1 ulp-ish (2e-16 relative), far inside the 1e-9 parity budget; the host build (tests/host_emul)
+// uses the same polynomial code with exact 1/x and sqrt in place of the MUFU seeds.
+// Coefficients: scripts/gen_exp_coeffs.py (degree-11 Chebyshev-node interpolants, max rel err 1.6e-16 / 1.9e-16).
+// ---------------------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+#define GEOAC_CONST_TABLE static __constant__
 #else
-GEOAC_HD double g_rsqrt(double x) { return 1.0 / sqrt(x); }
-GEOAC_HD double g_rcbrt(double x) { return 1.0 / cbrt(x); }
-GEOAC_HD double g_exp10(double x) { return pow(10.0, x); }
-GEOAC_HD double g_rcp(double x)   { return 1.0 / x; }
+#define GEOAC_CONST_TABLE static const
 #endif
+GEOAC_CONST_TABLE double kExpE[12] = { 1.0, 1.0, 0.5000000000000019, 0.1666666666666668, 0.0416666666664881, 0.008333333333319601,
+    0.0013888888952314775, 0.00019841269890047113, 2.4801485482328494e-05, 2.755724091857897e-06, 2.763263963904103e-07, 2.5110037605963777e-08 };
+GEOAC_CONST_TABLE double kExp10[12] = { 1.0, 2.302585092994046, 2.6509490552392085, 2.034678592293478, 1.1712551489072474, 0.5393829291946926,
+    0.20699584964214854, 0.06808936524182622, 0.019597614171033596, 0.005013914586462978, 0.0011576552892216332, 0.00024222554338191172 };
+
+#if defined(__CUDA_ARCH__)
+GEOAC_HD double g_scale2(double p, int n) { return __hiloint2double(__double2hiint(p) + (n << 20), __double2loint(p)); }
+GEOAC_HD int    g_lo32(double t) { return __double2loint(t); }
+// 1/x for normal x: MUFU seed (>= 20 bits) + one third-order Newton step
+GEOAC_HD double g_rcp(double x) {
+    double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);                       // y (1 + e + e^2): relative error e^3 <= 2^-60 before rounding
+}
+// 1/sqrt(x) for normal positive x: MUFU seed (~2^-21) + one third-order Newton step
+GEOAC_HD double g_rsqrt(double x) {
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);             // y (1 + e/2 + 3 e^2/8): relative error ~e^3 <= 2^-63 before rounding
+}
+// sqrt(x) and 1/sqrt(x) together (x > 0 normal)
+GEOAC_HD double g_sqrt_rs(double x, double& rs) {
+    rs = g_rsqrt(x);
+    const double s = x * rs;
+    return fma(fma(-s, s, x), 0.5 * rs, s);
+}
+GEOAC_HD double g_rcbrt(double x) { return rcbrt(x); }
+#else
+GEOAC_HD double g_scale2(double p, int n) { return ldexp(p, n); }
+GEOAC_HD int    g_lo32(double t) { int64_t b; memcpy(&b, &t, 8); return (int)(uint32_t)b; }
+GEOAC_HD double g_rcp(double x)   { return 1.0 / x; }
+GEOAC_HD double g_rsqrt(double x) { return 1.0 / sqrt(x); }
+GEOAC_HD double g_sqrt_rs(double x, double& rs) { const double s = sqrt(x); rs = 1.0 / s; return s; }
+GEOAC_HD double g_rcbrt(double x) { return 1.0 / cbrt(x); }
+#endif
+GEOAC_HD double g_sqrt(double x) { double rs; return g_sqrt_rs(x, rs); }
+
+// N exponentials in lock step (explicit ILP): out[j] = exp(x[j]) (BASE10 = false) or 10^x[j] (BASE10 = true),
+// for |result exponent| < 1020: the exponent is patched directly, arguments must stay inside +-700 (e) / +-300 (10).
+template <bool BASE10, int N>
+GEOAC_HD void g_exp_n(const double (&x)[N], double (&out)[N]) {     // caller guarantees |x| < 700 (e) / 300 (10)
+    const double MAGIC = 6755399441055744.0;                                  // 1.5 * 2^52: rint() by addition
+    const double L2B = BASE10 ? 3.321928094887362 : 1.4426950408889634;       // log2(base)
+    const double HI = BASE10 ? 0.3010299956639812 : 0.6931471805599453;       // log_base(2), split
+    const double LO = BASE10 ? -2.8037281277851704e-18 : 2.3190468138462996e-17;
+    const double* C = BASE10 ? kExp10 : kExpE;
+    double r[N], p[N]; int n[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+        const double xc = x[j];
+        const double t = fma(xc, L2B, MAGIC);
+        n[j] = g_lo32(t);
+        const double nf = t - MAGIC;
+        r[j] = fma(nf, -LO, fma(nf, -HI, xc));
+        p[j] = C[11];
+    }
+#pragma unroll
+    for (int k = 10; k >= 0; k--) {
+#pragma unroll
+        for (int j = 0; j < N; j++) p[j] = fma(p[j], r[j], C[k]);
+    }
+#pragma unroll
+    for (int j = 0; j < N; j++) out[j] = g_scale2(p[j], n[j]);
+}
+GEOAC_HD double g_exp(double x) { const double a[1] = { x }; double o[1]; g_exp_n<false, 1>(a, o); return o[0]; }
 
 // ---------------------------------------------------------------------------------------------------------------
-// 1-D table: structure-of-arrays, `n` levels per array, in this order (each array padded to n_pad doubles):
-//   x, invh, T, sT, u, su, v, sv, rho, srho          (invh[k] = 1/(x[k+1]-x[k]), invh[n-1] = 0)
-// SoA keeps neighbouring levels in neighbouring shared-memory banks; lanes at the same level broadcast.
+// 1-D table: one 80-byte record per level,
+//   { x, invh, T, sT, u, su, v, sv, rho, srho }          (invh[k] = 1/(x[k+1]-x[k]), invh[n-1] = 0; s* = knot slopes)
+// so that a sample touches two adjacent records and every (value, slope) pair -- and (x, invh) -- is one aligned 16-byte
+// load: 8 LDS.128 per RK4 stage instead of 15 LDS.64, with one address computation per sample.
 // ---------------------------------------------------------------------------------------------------------------
 enum { TAB_X = 0, TAB_INVH, TAB_T, TAB_ST, TAB_U, TAB_SU, TAB_V, TAB_SV, TAB_RHO, TAB_SRHO, TAB_NARR };
 
 struct Table1D {
-    const double* base;     // shared or global memory
-    int n, n_pad;
+    const double* base;     // shared or global memory, 16-byte aligned on the device
+    int n;
     double xmin, xmax;
-    GEOAC_HD const double* arr(int a) const { return base + (size_t)a * n_pad; }
+    GEOAC_HD const double* lvl(int k) const { return base + (size_t)k * TAB_NARR; }
 };
 
-struct SegPos { int k; double X, h, invh; };
+#if defined(__CUDA_ARCH__)
+struct Pair { double a, b; };
+GEOAC_HD Pair ld_pair(const double* p) { const double2 v = *reinterpret_cast<const double2*>(p); Pair r; r.a = v.x; r.b = v.y; return r; }
+#else
+struct Pair { double a, b; };
+GEOAC_HD Pair ld_pair(const double* p) { Pair r; r.a = p[0]; r.b = p[1]; return r; }
+#endif
 
-// locate the interval containing xc (already clamped into [xmin,xmax]) starting from cursor k.
-// Same tie-breaking as the reference's Find_Segment (G2S_Spline1D.cpp:202-243): a point on a knot stays in the
-// interval the cursor is already in.
-GEOAC_HD SegPos seg_locate(const Table1D& t, double xc, int& k) {
-    const double* x = t.arr(TAB_X);
-    double x0 = x[k], x1 = x[k + 1];
-    while (xc < x0) { --k; x1 = x0; x0 = x[k]; }
-    while (xc > x1) { ++k; x0 = x1; x1 = x[k + 1]; }
-    SegPos s; s.k = k; s.h = x1 - x0; s.invh = t.arr(TAB_INVH)[k]; s.X = (xc - x0) * s.invh;
+struct SegPos { const double* r0; double X, h, invh; };      // r0 = record of the interval's lower level (upper: r0 + TAB_NARR)
+
+// clamp without the NaN plumbing of fmin/fmax (one compare + select per bound)
+GEOAC_HD double clampd(double v, double lo, double hi) { v = (v > hi) ? hi : v; return (v < lo) ? lo : v; }
+
+// locate the interval containing x, clamped into the table range like every reference look-up (G2S_Spline1D.cpp:335),
+// starting from cursor k.  Same tie-breaking as the reference's Find_Segment (G2S_Spline1D.cpp:202-243): a point on a
+// knot stays in the interval the cursor is already in.  Fast path: the query is still inside the cursor's interval
+// (then it needs no clamping either) -- one 16-byte and one 8-byte load, two compares.
+GEOAC_HD SegPos seg_locate(const Table1D& t, double xq, int& k) {
+    const double* r = t.lvl(k);
+    Pair lo = ld_pair(r);                                     // x[k], invh[k]
+    double x1 = r[TAB_NARR];
+    double xc = xq;
+    if (!(xq >= lo.a && xq <= x1)) {
+        xc = clampd(xq, t.xmin, t.xmax);
+        while (xc < lo.a) { --k; r -= TAB_NARR; x1 = lo.a; lo = ld_pair(r); }
+        while (xc > x1)   { ++k; r += TAB_NARR; lo = ld_pair(r); x1 = r[TAB_NARR]; }
+    }
+    SegPos s; s.r0 = r; s.h = x1 - lo.a; s.invh = lo.b; s.X = (xc - lo.a) * lo.b;
     return s;
 }
 
-GEOAC_HD double clampd(double v, double lo, double hi) { return fmax(fmin(v, hi), lo); }
-
+// Hermite "slopes" form of the natural cubic spline on one interval (G2S_Spline1D.cpp:245-281), arranged for FMAs:
+//   A = s0 h - df, B = df - s1 h, C = B - A, P = A + C X
+//   f = f0 + X df + X(1-X) P,   f' h = df + (1-2X) P + X(1-X) C,   f'' h^2 = 2 ((1-2X) C - P)
+struct SplCoef { double f0, df, A, C; };
+GEOAC_HD SplCoef spl_coef(const SegPos& p, int field) {
+    const Pair a = ld_pair(p.r0 + field), b = ld_pair(p.r0 + TAB_NARR + field);       // (f, slope) at both levels
+    SplCoef c; c.f0 = a.a; c.df = b.a - a.a;
+    c.A = fma(a.b, p.h, -c.df);
+    c.C = fma(-b.b, p.h, c.df) - c.A;
+    return c;
+}
 // value only
-GEOAC_HD double spl_f(const double* F, const double* S, const SegPos& p) {
-    const double f0 = F[p.k], f1 = F[p.k + 1];
-    const double df = f1 - f0;
-    const double A = S[p.k] * p.h - df, B = -S[p.k + 1] * p.h + df;
-    const double omX = 1.0 - p.X;
-    return omX * f0 + p.X * f1 + p.X * omX * (A * omX + B * p.X);
+GEOAC_HD double spl_f(const Table1D&, int field, const SegPos& p) {
+    const SplCoef c = spl_coef(p, field);
+    const double XomX = p.X * (1.0 - p.X);
+    return fma(XomX, fma(c.C, p.X, c.A), fma(p.X, c.df, c.f0));
 }
 // value + first derivative
-GEOAC_HD void spl_f1(const double* F, const double* S, const SegPos& p, double& f, double& d1) {
-    const double f0 = F[p.k], f1 = F[p.k + 1];
-    const double df = f1 - f0;
-    const double A = S[p.k] * p.h - df, B = -S[p.k + 1] * p.h + df;
-    const double omX = 1.0 - p.X, P = A * omX + B * p.X, XomX = p.X * omX;
-    f  = omX * f0 + p.X * f1 + XomX * P;
-    d1 = (df + (1.0 - 2.0 * p.X) * P + XomX * (B - A)) * p.invh;
+GEOAC_HD void spl_f1(const Table1D&, int field, const SegPos& p, double& f, double& d1) {
+    const SplCoef c = spl_coef(p, field);
+    const double XomX = p.X * (1.0 - p.X), om2X = fma(-2.0, p.X, 1.0), P = fma(c.C, p.X, c.A);
+    f  = fma(XomX, P, fma(p.X, c.df, c.f0));
+    d1 = fma(XomX, c.C, fma(om2X, P, c.df)) * p.invh;
 }
 // value + first + second derivative
-GEOAC_HD void spl_f2(const double* F, const double* S, const SegPos& p, double& f, double& d1, double& d2) {
-    const double f0 = F[p.k], f1 = F[p.k + 1];
-    const double df = f1 - f0;
-    const double A = S[p.k] * p.h - df, B = -S[p.k + 1] * p.h + df;
-    const double omX = 1.0 - p.X, P = A * omX + B * p.X, XomX = p.X * omX;
-    f  = omX * f0 + p.X * f1 + XomX * P;
-    d1 = (df + (1.0 - 2.0 * p.X) * P + XomX * (B - A)) * p.invh;
-    d2 = 2.0 * (B - 2.0 * A + (A - B) * 3.0 * p.X) * (p.invh * p.invh);
+GEOAC_HD void spl_f2(const Table1D&, int field, const SegPos& p, double& f, double& d1, double& d2) {
+    const SplCoef c = spl_coef(p, field);
+    const double XomX = p.X * (1.0 - p.X), om2X = fma(-2.0, p.X, 1.0), P = fma(c.C, p.X, c.A);
+    f  = fma(XomX, P, fma(p.X, c.df, c.f0));
+    d1 = fma(XomX, c.C, fma(om2X, P, c.df)) * p.invh;
+    d2 = fma(om2X, c.C, -P) * (2.0 * p.invh * p.invh);
 }
 
 // thermodynamic sound speed and its vertical derivatives from T, T', T''
@@ -118,7 +208,7 @@ GEOAC_HD double sound_speed0(double T) { return sqrt(kGamR * T); }
 // ---------------------------------------------------------------------------------------------------------------
 // reference state of the Sutherland-Bass model (T_o, P_o): per launch for the Cartesian variants and the stratified
 // Global one, per step for Global.RngDep (its reference point follows the ray's latitude / longitude, App. A-14)
-struct SBRef { double invTo, cbrtTo, visc_num, invPo; };
+struct SBRef { double invTo, cbrtTo, visc_num, inv_visc_num, invPo; };
 
 struct LaunchConsts {
     // parameters (copy of geoac_params + derived)
@@ -135,100 +225,159 @@ struct LaunchConsts {
     // Sutherland-Bass invariants
     SBRef sb;                                 // 1/T_o, T_o^(1/3), (1 + S/T_o), 1/P_o
     double sb_w;                              // 2*pi*freq
+    // log10 gas-fraction polynomials with an altitude branch, [0] = low / [1] = high (Absorption.cpp:70-99): read with a
+    // lane-dependent branch index, so they sit in shared memory next to the other invariants rather than in constant memory
+    double sbx3[2][6], sbx4[2][4], sbx6[2][6];
 };
 
+// log10 of the gas fractions as polynomials in altitude [km] (Atmo_State.Absorption.cpp:55-99); [0] = low branch, [1] = high branch
+GEOAC_CONST_TABLE double kSBX0[6] = { 49.296, -1.5524, 1.8714E-2, -1.1069E-4, 3.199E-7, -3.6211E-10 };                    // O2, z > 90
+GEOAC_CONST_TABLE double kSBX1[4] = { 1.3972E-1, -5.6269E-3, 3.9407E-5, -1.0737E-7 };                                       // N2, z > 76
+GEOAC_CONST_TABLE double kSBX5[6] = { -53.746, 1.5439, -1.8824E-2, 1.1587E-4, -3.5399E-7, 4.2609E-10 };                   // N
+
 // Sutherland-Bass absorption [dB/km] at altitude z [km] with local sound speed c [km/s] (and 1/c) and density rho.
-// Restructured from Atmo_State.Absorption.cpp:14-143: constants folded, pow(10,.) -> exp10, pow(T,-1/3) -> rcbrt,
-// exp(9.17 Tr) = 1/exp(-9.17 Tr), common factors hoisted.  Branch thresholds are the reference's (strict >).
+// Same model and branch thresholds (strict >) as Atmo_State.Absorption.cpp:14-143, restructured for the FP64 pipe:
+//   * the ten exp(a_i Tr) factors of the vibrational relaxation frequencies share ONE exponential: every a_i is a
+//     multiple of 0.01, so they are integer powers of g = exp(-Tr/100) (binary powers, ~40 multiplies; the relative
+//     error grows to <= 2000 * 2^-53 ~ 2e-13, four orders inside the parity budget);
+//   * the remaining exponentials (gas fractions 10^poly(z), rotational collision numbers, vibrational Boltzmann factors)
+//     are evaluated in lock step by the branch-free g_exp_n; the polynomials in z are Horner forms;
+//   * every quotient is a product with one of five reciprocals (two of them batched inversions).
 GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho) {
     const double mu_o = 18.192E-6, S = 117.0;
-    const double c1000 = c * 1000.0;
-    const double c2 = c1000 * c1000;
+    const double inv_c2 = inv_c * inv_c;
+    const double c2 = (c * c) * 1.0e6;                                      // (1000 c)^2
     const double T_z = c2 * (1.0 / (kR * kGam));
+    const double inv_Tz = inv_c2 * (kR * kGam * 1.0e-6);
     const double P_z = rho * c2 * (1000.0 / kGam);
-    const double inv_Tz = 1.0 / T_z;
-    const double inv_Pz = 1.0 / P_z;
+    const double den1 = 1.0 + S * inv_Tz;
+    const double r1 = g_rcp(rho * den1);
+    const double inv_rho = r1 * den1, inv_den1 = r1 * rho;
+    const double inv_Pz = inv_rho * inv_c2 * (kGam * 1.0e-9);
 
-    const double mu_ratio = sqrt(T_z * R.invTo) * (R.visc_num / (1.0 + S * inv_Tz));     // mu/mu_o
-    const double mu = mu_o * mu_ratio;
-    const double nu = (8.0 * kPi * L.freq * mu) * inv_Pz * (1.0 / 3.0);
+    const double tq = T_z * R.invTo;
+    double rs; const double sq = g_sqrt_rs(tq, rs);
+    const double mu_ratio = sq * (R.visc_num * inv_den1);                    // mu/mu_o
+    const double inv_mu_ratio = rs * (den1 * R.inv_visc_num);
+    const double nu = (8.0 * kPi * L.freq * mu_o * (1.0 / 3.0)) * mu_ratio * inv_Pz;
 
-    const double z2 = z * z, z3 = z2 * z, z4 = z2 * z2, z5 = z4 * z;
-    double X0, X1, X3, X4, X5, X6;
+    // gas fractions X0..X6 = 10^(polynomial in z), Absorption.cpp:55-99.  Coefficient sets live in constant memory and are
+    // picked by the branch predicate, so the warp never diverges on the altitude thresholds; z is clamped to the range in
+    // which every polynomial stays representable (the reference under/overflows to 0 / inf beyond it).
+    const double zc = fmax(fmin(z, 200.0), -20.0);
+    double X0 = 0.20947393930547747;                                       // 10^-0.67887
+    double X1 = 0.780836309209143;                                         // 10^-0.10744
     const double X2 = 0.00040003685104612505;                              // 10^-3.3979
-    if (z > 90.) X0 = g_exp10(49.296 - (1.5524 * z) + (1.8714E-2 * z2) - (1.1069E-4 * z3) + (3.199E-7 * z4) - (3.6211E-10 * z5));
-    else         X0 = 0.20947393930547747;                                 // 10^-0.67887
-    if (z > 76.) X1 = g_exp10((1.3972E-1) - (5.6269E-3 * z) + (3.9407E-5 * z2) - (1.0737E-7 * z3));
-    else         X1 = 0.780836309209143;                                   // 10^-0.10744
-    if (z > 80.) X3 = g_exp10(-4.234 - (3.0975E-2 * z));
-    else         X3 = g_exp10(-19.027 + (1.3093 * z) - (4.6496E-2 * z2) + (7.8543E-4 * z3) - (6.5169E-6 * z4) + (2.1343E-8 * z5));
-    if (z > 95.) X4 = g_exp10(-3.2456 + (4.6642E-2 * z) - (2.6894E-4 * z2) + (5.264E-7 * z3));
-    else         X4 = g_exp10(-11.195 + (1.5408E-1 * z) - (1.4348E-3 * z2) + (1.0166E-5 * z3));
-    X5 = g_exp10(-53.746 + (1.5439 * z) - (1.8824E-2 * z2) + (1.1587E-4 * z3) - (3.5399E-7 * z4) + (4.2609E-10 * z5));
-    if (z > 30.) X6 = g_exp10(-4.2563 + (7.6245E-2 * z) - (2.1824E-3 * z2) - (2.3010E-6 * z3) + (2.4265E-7 * z4) - (1.2500E-09 * z5));
-    else         X6 = g_exp10(-1.7491 + (4.4986E-2 * z) - (6.8549E-2 * z2) + (5.4639E-3 * z3) - (1.5539E-4 * z4) + (1.5063E-06 * z5));
-    const double X_ON = (X0 + X1) * (1.0 / 0.9903);
+    if (z > 76.) {
+        const double q[2] = { kSBX0[0] + zc * (kSBX0[1] + zc * (kSBX0[2] + zc * (kSBX0[3] + zc * (kSBX0[4] + zc * kSBX0[5])))),
+                              kSBX1[0] + zc * (kSBX1[1] + zc * (kSBX1[2] + zc * kSBX1[3])) };
+        double e[2]; g_exp_n<true, 2>(q, e);
+        if (z > 90.) X0 = e[0];
+        X1 = e[1];
+    }
+    double X3, X4, X5, X6;
+    {
+        const double* a = L.sbx3[z > 80. ? 1 : 0];
+        const double* bq = L.sbx4[z > 95. ? 1 : 0];
+        const double* d = L.sbx6[z > 30. ? 1 : 0];
+        const double q[4] = { a[0] + zc * (a[1] + zc * (a[2] + zc * (a[3] + zc * (a[4] + zc * a[5])))),
+                              bq[0] + zc * (bq[1] + zc * (bq[2] + zc * bq[3])),
+                              kSBX5[0] + zc * (kSBX5[1] + zc * (kSBX5[2] + zc * (kSBX5[3] + zc * (kSBX5[4] + zc * kSBX5[5])))),
+                              d[0] + zc * (d[1] + zc * (d[2] + zc * (d[3] + zc * (d[4] + zc * d[5])))) };
+        double e[4]; g_exp_n<true, 4>(q, e);
+        X3 = e[0]; X4 = e[1]; X5 = e[2]; X6 = e[3];
+    }
+    const double X01 = X0 + X1;
+    const double X_ON = X01 * (1.0 / 0.9903);
 
+    // natural exponentials: g = exp(-Tr/100); rotational collision numbers; vibrational Boltzmann factors
     const double cb = g_rcbrt(T_z);                                        // T_z^(-1/3)
-    const double Zr0 = 54.1 * exp(-17.3 * cb), Zr1 = 63.3 * exp(-16.7 * cb);
-    const double Z_rot_ = (Zr0 * Zr1) / (X1 * Zr0 + X0 * Zr1);             // 1/(X1/Zr1 + X0/Zr0)
+    const double Tr = cb * R.cbrtTo - 1.0;                                 // (T_z/T_o)^(-1/3) - 1
+    const double th[4] = { 2239.1, 3352.0, 915.0, 1037.0 };
+    double ex[7];
+    {
+        const double q[7] = { -0.01 * Tr, -17.3 * cb, -16.7 * cb, -th[0] * inv_Tz, -th[1] * inv_Tz, -th[2] * inv_Tz, -th[3] * inv_Tz };
+        g_exp_n<false, 7>(q, ex);
+    }
+    const double Zr0 = 54.1 * ex[1], Zr1 = 63.3 * ex[2];
+    const double Z_rot_ = (Zr0 * Zr1) * g_rcp(X1 * Zr0 + X0 * Zr1);         // 1/(X1/Zr1 + X0/Zr0)
 
     const double sigma = 1.091089451179962;                                // 5/sqrt(21)
     const double nn = 0.5237229365663817 * Z_rot_;                         // (4/5) sqrt(3/7) Z_rot_
     const double chi = 0.75 * nn * nu;
     const double cchi = 2.36 * chi;
-
     const double nu2p1 = 1.0 + nu * nu;
-    const double s1 = sqrt(nu2p1);
+    const double s1 = g_sqrt(nu2p1);
     const double cchi2p1 = 1.0 + cchi * cchi;
     const double sc = sigma * cchi;
     const double w_c = L.sb_w * inv_c;                                     // 2 pi f / c
     // NB: sqrt(1+nu^2) - 1 cancels catastrophically for small nu (it is 0 or a few ulp below ~60 km at 0.1 Hz).
     // That quantisation IS the reference's observable behaviour (Absorption.cpp:108), so it is reproduced literally.
     const double s1m1 = s1 - 1.0;
-    const double a_cl  = w_c * sqrt(0.5 * s1m1 * cchi2p1 / (nu2p1 * (1.0 + sc * sc)));
-    const double a_rot = w_c * X_ON * ((sigma * sigma - 1.0) * chi * (0.5 / sigma)) * sqrt(0.5 * (s1 + 1.0) / (nu2p1 * cchi2p1));
+    const double q1 = nu2p1 * (1.0 + sc * sc), q2 = nu2p1 * cchi2p1;
+    const double rq = g_rcp(q1 * q2);                                      // 1/q1 = rq q2, 1/q2 = rq q1
+    const double a_cl  = w_c * g_sqrt(fmax(0.5 * s1m1 * cchi2p1 * (rq * q2), 1e-290));
+    const double a_rot = w_c * X_ON * ((sigma * sigma - 1.0) * chi * (0.5 / sigma)) * g_sqrt(0.5 * (s1 + 1.0) * (rq * q1));
     const double a_diff = 0.003 * a_cl;
 
-    const double Tr = cb * R.cbrtTo - 1.0;                              // (T_z/T_o)^(-1/3) - 1
-    const double A1 = (X0 + X1) * 24.0 * exp(-9.16 * Tr);
+    // integer powers of g (binary exponentiation): g2 = g^2, g4 = g^4, ... g1024
+    const double g1 = ex[0], g2 = g1 * g1, g4 = g2 * g2, g8 = g4 * g4, g16 = g8 * g8, g32 = g16 * g16, g64 = g32 * g32,
+                 g128 = g64 * g64, g256 = g128 * g128, g512 = g256 * g256, g1024 = g512 * g512;
+    const double g768 = g512 * g256, g896 = g768 * g128;
+    const double g916 = g896 * (g16 * g4);                                 // exp(-9.16 Tr)
+    const double g917 = g916 * g1;                                         // exp(-9.17 Tr)
+    const double g1120 = g1024 * (g64 * g32);                              // exp(-11.2 Tr)
+    const double g1990 = (g1024 * g896) * ((g64 * g4) * g2);               // exp(-19.9 Tr)
+    const double g417 = (g256 * g128) * (g32 * g1);                        // exp(-4.17 Tr)
+    const double g1040 = g1024 * g16;                                      // exp(-10.4 Tr)
+    const double g772 = g768 * g4;                                         // exp(-7.72 Tr)
+    const double g1000 = g896 * ((g64 * g32) * g8);                        // 1/exp(10 Tr)
+    const double g841 = g768 * ((g64 * g8) * g1);                          // 1/exp(8.41 Tr)
+    // batched inversion of g1000, g841, g917
+    const double m12 = g1000 * g841;
+    const double rall = g_rcp(m12 * g917);
+    const double i917 = rall * m12, r12 = rall * g917, i1000 = r12 * g841, i841 = r12 * g1000;
+
+    const double A1 = X01 * 24.0 * g916;
     const double A2 = (X4 + X5) * 2400.0;
-    const double B  = 40400.0 * exp(10.0 * Tr);
-    const double C  = 0.02 * exp(-11.2 * Tr);
-    const double D  = 0.391 * exp(8.41 * Tr);
-    const double E  = 9.0 * exp(-19.9 * Tr);
+    const double B  = 40400.0 * i1000;
+    const double C  = 0.02 * g1120;
+    const double D  = 0.391 * i841;
+    const double E  = 9.0 * g1990;
     const double F  = 60000.0;
-    const double G  = 28000.0 * exp(-4.17 * Tr);
-    const double H  = 22000.0 * exp(-7.68 * Tr);
-    const double I  = 15100.0 * exp(-10.4 * Tr);
-    const double eJ = exp(-9.17 * Tr);
-    const double J  = 11500.0 * eJ;
-    const double K  = (8.48E08) / eJ;
-    const double Lx = exp(-7.72 * Tr);
+    const double G  = 28000.0 * g417;
+    const double H  = 22000.0 * g768;
+    const double I  = 15100.0 * g1040;
+    const double J  = 11500.0 * g917;
+    const double K  = (8.48E08) * i917;
     const double ZZ = H * X2 + I * (X0 + 0.5 * X4) + J * (X1 + 0.5 * X5) + K * (X6 + X3);
     const double hu = 100.0 * (X3 + X6);
-    const double pm = (P_z * R.invPo) / mu_ratio;                       // (P_z/P_o)(mu_o/mu)
+    const double pm = (P_z * R.invPo) * inv_mu_ratio;                       // (P_z/P_o)(mu_o/mu)
     double fv[4];
     fv[0] = pm * (A1 + A2 + B * hu * (C + hu) * (D + hu));
     fv[1] = pm * (E + F * X3 + G * X6);
     fv[2] = pm * ZZ;
-    fv[3] = pm * (1.2E5) * Lx;
+    fv[3] = pm * (1.2E5) * g772;
 
-    const double th[4] = { 2239.1, 3352.0, 915.0, 1037.0 };
+    // vibrational terms: A_max/c * (2 f^2/fv)/(1 + (f/fv)^2) with A_max = X (pi/2) C_R / (Cp (Cv + C_R)), C_R = r^2 e/(1-e)^2
+    //   = X (pi/2) r^2 e * 2 f^2 fv / ( c * Cp (Cv (1-e)^2 + r^2 e) (fv^2 + f^2) ): one quotient per term, inverted together
     const double CpR[4] = { 3.5, 3.5, 4.0, 4.0 }, CvR[4] = { 2.5, 2.5, 3.0, 3.0 };
     const double Xm[4] = { X0, X1, X2, X3 };
     const double f2 = L.freq * L.freq;
-    double a_vib = 0.0;
+    double num[4], den[4];
 #pragma unroll
     for (int m = 0; m < 4; m++) {
         const double r = th[m] * inv_Tz;
-        const double e = exp(-r);
+        const double e = ex[3 + m];
         const double ome = 1.0 - e;
-        const double C_R = (r * r * e) / (ome * ome);
-        const double A_max = (Xm[m] * (kPi / 2) * C_R) / (CpR[m] * (CvR[m] + C_R));
-        // (2 f^2/fv)/(1 + (f/fv)^2) = 2 f^2 fv/(fv^2 + f^2)
-        a_vib += (A_max * inv_c) * (2.0 * f2 * fv[m] / (fv[m] * fv[m] + f2));
+        const double r2e = (r * r) * e;
+        num[m] = (Xm[m] * (kPi / 2) * 2.0) * r2e * (f2 * fv[m]);
+        den[m] = CpR[m] * (CvR[m] * (ome * ome) + r2e) * (fv[m] * fv[m] + f2);
     }
+    const double d01 = den[0] * den[1], d23 = den[2] * den[3];
+    const double rd = g_rcp(d01 * d23);
+    const double r01 = rd * d23, r23 = rd * d01;
+    const double a_vib = inv_c * ((num[0] * (r01 * den[1]) + num[1] * (r01 * den[0])) + (num[2] * (r23 * den[3]) + num[3] * (r23 * den[2])));
     return (a_cl + a_rot + a_diff + a_vib) * L.tweak_abs * 8.685889;
 }
 
@@ -237,12 +386,23 @@ GEOAC_HD void suthbass_ref(SBRef& R, double c_ref, double rho_ref) {
     const double c1000 = c_ref * 1000.0;
     const double T_o = c1000 * c1000 / (kR * kGam);
     const double P_o = rho_ref * (c1000 * c1000) / kGam * 1000.0;
-    R.invTo = 1.0 / T_o; R.cbrtTo = cbrt(T_o); R.visc_num = 1.0 + 117.0 / T_o;
+    R.invTo = 1.0 / T_o; R.cbrtTo = cbrt(T_o); R.visc_num = 1.0 + 117.0 / T_o; R.inv_visc_num = 1.0 / R.visc_num;
     R.invPo = 1.0 / P_o;
+}
+GEOAC_HD void suthbass_tables(LaunchConsts& L) {
+    const double x3[2][6] = { { -19.027, 1.3093, -4.6496E-2, 7.8543E-4, -6.5169E-6, 2.1343E-8 }, { -4.234, -3.0975E-2, 0.0, 0.0, 0.0, 0.0 } };   // O3: z <= 80, z > 80
+    const double x4[2][4] = { { -11.195, 1.5408E-1, -1.4348E-3, 1.0166E-5 }, { -3.2456, 4.6642E-2, -2.6894E-4, 5.264E-7 } };                     // O:  z <= 95, z > 95
+    const double x6[2][6] = { { -1.7491, 4.4986E-2, -6.8549E-2, 5.4639E-3, -1.5539E-4, 1.5063E-06 },                                            // H2O: z <= 30
+                              { -4.2563, 7.6245E-2, -2.1824E-3, -2.3010E-6, 2.4265E-7, -1.2500E-09 } };                                         //      z > 30
+    for (int b = 0; b < 2; b++) {
+        for (int k = 0; k < 6; k++) { L.sbx3[b][k] = x3[b][k]; L.sbx6[b][k] = x6[b][k]; }
+        for (int k = 0; k < 4; k++) L.sbx4[b][k] = x4[b][k];
+    }
+    L.sb_w = 2.0 * kPi * L.freq;
 }
 GEOAC_HD void suthbass_setup(LaunchConsts& L, double c_ref, double rho_ref) {
     suthbass_ref(L.sb, c_ref, rho_ref);
-    L.sb_w = 2.0 * kPi * L.freq;
+    suthbass_tables(L);
 }
 
 }  // namespace geoac

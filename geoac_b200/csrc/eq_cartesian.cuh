@@ -14,6 +14,7 @@ namespace geoac {
 // ======================================================= 3-D stratified =======================================
 template <bool AMP>
 struct Eq3D {
+    using Scout = Eq3D<false>;           // amplitude-free set used by the cost scout (trace_kernel.cuh)
     static constexpr int NEQ = AMP ? 12 : 4;
     using Atmo = Table1D;
     using Cursor = int;
@@ -53,27 +54,27 @@ struct Eq3D {
 
     // GeoAc_Set_ds, 3DStratified.cpp:191-198
     GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {
-        double r = 0.05 - 0.049 * exp(-(y[2] - L.z_grnd) * (1.0 / 0.75));
+        double r = 0.05 - 0.049 * g_exp(-(y[2] - L.z_grnd) * (1.0 / 0.75));
         return fmax(fmin(r, L.ds_max), L.ds_min);
     }
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, 3DStratified.cpp:203-310: all NEQ right-hand sides from ONE atmosphere sample
     GEOAC_HD static void rhs(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* p, double* f, int& cur) {
-        const SegPos sp = seg_locate(T, clampd(p[2], T.xmin, T.xmax), cur);
+        const SegPos sp = seg_locate(T, p[2], cur);
         double Tv, dT, ddT, u, du, ddu, v, dv, ddv;
         if (AMP) {
-            spl_f2(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT, ddT);
-            spl_f2(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du, ddu);
-            spl_f2(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv, ddv);
+            spl_f2(T, TAB_T, sp, Tv, dT, ddT);
+            spl_f2(T, TAB_U, sp, u, du, ddu);
+            spl_f2(T, TAB_V, sp, v, dv, ddv);
         } else {
-            spl_f1(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT); ddT = 0.0;
-            spl_f1(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du);  ddu = 0.0;
-            spl_f1(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv);  ddv = 0.0;
+            spl_f1(T, TAB_T, sp, Tv, dT); ddT = 0.0;
+            spl_f1(T, TAB_U, sp, u, du);  ddu = 0.0;
+            spl_f1(T, TAB_V, sp, v, dv);  ddv = 0.0;
         }
         const SoundSpeed s = sound_speed2(Tv, dT, ddT);
         const double nz = p[3];
         const double nu_mag = (L.c_src - (rc.nx * u + rc.ny * v)) * s.inv_c;     // c0/c (1 - nu.v/c0), w = 0
-        const double inv_nm = 1.0 / nu_mag;
+        const double inv_nm = g_rcp(nu_mag);
         const double cn = s.c * inv_nm;
         const double cp0 = cn * rc.nx + u, cp1 = cn * rc.ny + v, cp2 = cn * nz;
         const double inv_cpm = g_rsqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
@@ -105,7 +106,7 @@ struct Eq3D {
     // BreakCheck / GroundCheck, 3DStratified.cpp:327-343 (strict inequalities on the unclamped state)
     GEOAC_HD static bool left_region(const LaunchConsts& L, const RayC&, const double* y) {
         const double r2 = y[0] * y[0] + y[1] * y[1];
-        return (y[2] > L.vert_limit) || (sqrt(r2) > L.range_limit);
+        return (y[2] > L.vert_limit) || (r2 > L.range_limit * L.range_limit);      // sqrt(r2) > limit
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[2] < L.z_grnd; }
 
@@ -113,18 +114,18 @@ struct Eq3D {
     GEOAC_HD static void segment(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ya, const double* yb,
                                  int& cur, double& dtt, double& datt) {
         const double dx = yb[0] - ya[0], dy = yb[1] - ya[1], dz = yb[2] - ya[2];
-        const double ds = sqrt(dx * dx + dy * dy + dz * dz);
+        const double ds = g_sqrt(fmax(dx * dx + dy * dy + dz * dz, 1e-290));
         const double zm = ya[2] + dz * 0.5;
         const double nz = ya[3] + (yb[3] - ya[3]) * 0.5;
-        const SegPos sp = seg_locate(T, clampd(zm, T.xmin, T.xmax), cur);
-        const double Tv = spl_f(T.arr(TAB_T), T.arr(TAB_ST), sp);
-        const double u = spl_f(T.arr(TAB_U), T.arr(TAB_SU), sp);
-        const double v = spl_f(T.arr(TAB_V), T.arr(TAB_SV), sp);
-        const double rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+        const SegPos sp = seg_locate(T, zm, cur);
+        const double Tv = spl_f(T, TAB_T, sp);
+        const double u = spl_f(T, TAB_U, sp);
+        const double v = spl_f(T, TAB_V, sp);
+        const double rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         const double nu_mag = (L.c_000 - rc.nx * u - rc.ny * v) * inv_c;            // c(0,0,0): App. A-4
-        const double cn = c / nu_mag;
+        const double cn = c * g_rcp(nu_mag);
         const double cp0 = cn * rc.nx + u, cp1 = cn * rc.ny + v, cp2 = cn * nz;
         dtt = ds * g_rsqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
         datt = suthbass_alpha(L, L.sb, zm, c, inv_c, rho) * ds;
@@ -163,10 +164,10 @@ struct Eq3D {
         margin = (yk[2] - L.z_grnd) / fabs(yk[2] - ym1[2]);
         amp = 0.0;
         if (AMP) {
-            const SegPos sp = seg_locate(T, clampd(yk[2], T.xmin, T.xmax), cur);
-            const double c = sound_speed0(spl_f(T.arr(TAB_T), T.arr(TAB_ST), sp));
-            const double u = spl_f(T.arr(TAB_U), T.arr(TAB_SU), sp), v = spl_f(T.arr(TAB_V), T.arr(TAB_SV), sp);
-            const double rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+            const SegPos sp = seg_locate(T, yk[2], cur);
+            const double c = sound_speed0(spl_f(T, TAB_T, sp));
+            const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
+            const double rho = spl_f(T, TAB_RHO, sp);
             const double c0 = L.c_src, u0 = L.u_src, v0 = L.v_src;
             const double nz = yk[3];
             const double nu_mag = (c0 - rc.nx * u - rc.ny * v) / c;
@@ -188,13 +189,14 @@ struct Eq3D {
 // ======================================================= 2-D effective sound speed ============================
 template <bool AMP>
 struct Eq2D {
+    using Scout = Eq2D<false>;           // amplitude-free set used by the cost scout (trace_kernel.cuh)
     static constexpr int NEQ = AMP ? 6 : 3;
     using Atmo = Table1D;
     using Cursor = int;
     static constexpr int VARIANT = GEOAC_2D;
     static constexpr bool QUADRATIC_INTERCEPT = true;
 
-    struct RayC { double cphi, sphi, costh, sinth, ceff0, theta_deg; };
+    struct RayC { double cphi, sphi, costh, sinth, ceff0, inv_ceff0, theta_deg; };
 
     GEOAC_HD static double altitude(const double* y) { return y[1]; }
 
@@ -202,33 +204,34 @@ struct Eq2D {
     GEOAC_HD static void init(const LaunchConsts& L, const Table1D&, double theta, double phi, RayC& rc, double* y, int&) {
         sincos(phi, &rc.sphi, &rc.cphi); sincos(theta, &rc.sinth, &rc.costh);
         rc.ceff0 = L.c_src + L.u_src * rc.cphi + L.v_src * rc.sphi;
+        rc.inv_ceff0 = 1.0 / rc.ceff0;
         rc.theta_deg = theta * 180.0 / kPi;
         y[0] = 0.0; y[1] = L.src[2]; y[2] = rc.sinth;
         if (AMP) { y[3] = 0.0; y[4] = 0.0; y[5] = rc.costh; }
     }
 
     GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {   // 2DStratified.cpp:123-130
-        double r = 0.05 - 0.049 * exp(-(y[1] - L.z_grnd) * (1.0 / 0.75));
+        double r = 0.05 - 0.049 * g_exp(-(y[1] - L.z_grnd) * (1.0 / 0.75));
         return fmax(fmin(r, L.ds_max), L.ds_min);
     }
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, 2DStratified.cpp:135-181
     GEOAC_HD static void rhs(const LaunchConsts&, const Table1D& T, const RayC& rc, const double* p, double* f, int& cur) {
-        const SegPos sp = seg_locate(T, clampd(p[1], T.xmin, T.xmax), cur);
+        const SegPos sp = seg_locate(T, p[1], cur);
         double Tv, dT, ddT, u, du, ddu, v, dv, ddv;
         if (AMP) {
-            spl_f2(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT, ddT);
-            spl_f2(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du, ddu);
-            spl_f2(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv, ddv);
+            spl_f2(T, TAB_T, sp, Tv, dT, ddT);
+            spl_f2(T, TAB_U, sp, u, du, ddu);
+            spl_f2(T, TAB_V, sp, v, dv, ddv);
         } else {
-            spl_f1(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT); ddT = 0.0;
-            spl_f1(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du);  ddu = 0.0;
-            spl_f1(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv);  ddv = 0.0;
+            spl_f1(T, TAB_T, sp, Tv, dT); ddT = 0.0;
+            spl_f1(T, TAB_U, sp, u, du);  ddu = 0.0;
+            spl_f1(T, TAB_V, sp, v, dv);  ddv = 0.0;
         }
         const SoundSpeed s = sound_speed2(Tv, dT, ddT);
         const double c  = s.c  + u  * rc.cphi + v  * rc.sphi;
         const double dc = s.dc + du * rc.cphi + dv * rc.sphi;
-        const double inv_c0 = 1.0 / rc.ceff0, inv_c = 1.0 / c;
+        const double inv_c0 = rc.inv_ceff0, inv_c = g_rcp(c);
         const double cr = c * inv_c0;                              // c/c0
         f[0] = cr * rc.costh;
         f[1] = cr * p[2];
@@ -254,15 +257,15 @@ struct Eq2D {
                                  int& cur, double& dtt, double& datt) {
         const double dr = yb[0] - ya[0], dz = yb[1] - ya[1];
         const double zm = ya[1] + dz * 0.5;
-        const double ds = sqrt(dr * dr + dz * dz);
-        const SegPos sp = seg_locate(T, clampd(zm, T.xmin, T.xmax), cur);
-        const double Tv = spl_f(T.arr(TAB_T), T.arr(TAB_ST), sp);
-        const double u = spl_f(T.arr(TAB_U), T.arr(TAB_SU), sp);
-        const double v = spl_f(T.arr(TAB_V), T.arr(TAB_SV), sp);
-        const double rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+        const double ds = g_sqrt(fmax(dr * dr + dz * dz, 1e-290));
+        const SegPos sp = seg_locate(T, zm, cur);
+        const double Tv = spl_f(T, TAB_T, sp);
+        const double u = spl_f(T, TAB_U, sp);
+        const double v = spl_f(T, TAB_V, sp);
+        const double rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
-        dtt = ds / (c + u * rc.cphi + v * rc.sphi);
+        dtt = ds * g_rcp(c + u * rc.cphi + v * rc.sphi);
         datt = suthbass_alpha(L, L.sb, zm, c, inv_c, rho) * ds;
     }
 
@@ -291,9 +294,9 @@ struct Eq2D {
         margin = (yk[1] - L.z_grnd) / fabs(yk[1] - ym1[1]);
         amp = 0.0;
         if (AMP) {
-            const SegPos sp = seg_locate(T, clampd(yk[1], T.xmin, T.xmax), cur);
-            const double c = sound_speed0(spl_f(T.arr(TAB_T), T.arr(TAB_ST), sp));
-            const double rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+            const SegPos sp = seg_locate(T, yk[1], cur);
+            const double c = sound_speed0(spl_f(T, TAB_T, sp));
+            const double rho = spl_f(T, TAB_RHO, sp);
             const double drds = c / rc.ceff0 * rc.costh, dzds = c / rc.ceff0 * yk[2];
             const double D = yk[0] * (drds * yk[4] - dzds * yk[3]);
             amp = 1.0 / (4.0 * kPi) * sqrt(fabs((rho * c * rc.costh) / (L.rho_gnd * rc.ceff0 * D)));

@@ -15,6 +15,7 @@ namespace geoac {
 
 template <bool AMP>
 struct EqGlobal {
+    using Scout = EqGlobal<false>;           // amplitude-free set used by the cost scout (trace_kernel.cuh)
     static constexpr int NEQ = AMP ? 18 : 6;
     using Atmo = Table1D;
     using Cursor = int;
@@ -55,23 +56,23 @@ struct EqGlobal {
 
     // GeoAc_Set_ds, Global.cpp:210-217
     GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {
-        double r = 0.05 - 0.049 * exp(-(y[0] - L.ground) * (1.0 / 0.75));
+        double r = 0.05 - 0.049 * g_exp(-(y[0] - L.ground) * (1.0 / 0.75));
         return fmax(fmin(r, L.ds_max), L.ds_min);
     }
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, Global.cpp:222-442
     GEOAC_HD static void rhs(const LaunchConsts&, const Table1D& T, const RayC&, const double* p, double* f, int& cur) {
         const double r = p[0];
-        const SegPos sp = seg_locate(T, clampd(r, T.xmin, T.xmax), cur);
+        const SegPos sp = seg_locate(T, r, cur);
         double Tv, dT, ddT, u, du, ddu, v, dv, ddv;
         if (AMP) {
-            spl_f2(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT, ddT);
-            spl_f2(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du, ddu);
-            spl_f2(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv, ddv);
+            spl_f2(T, TAB_T, sp, Tv, dT, ddT);
+            spl_f2(T, TAB_U, sp, u, du, ddu);
+            spl_f2(T, TAB_V, sp, v, dv, ddv);
         } else {
-            spl_f1(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT); ddT = 0.0;
-            spl_f1(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du);  ddu = 0.0;
-            spl_f1(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv);  ddv = 0.0;
+            spl_f1(T, TAB_T, sp, Tv, dT); ddT = 0.0;
+            spl_f1(T, TAB_U, sp, u, du);  ddu = 0.0;
+            spl_f1(T, TAB_V, sp, v, dv);  ddv = 0.0;
         }
         const SoundSpeed s = sound_speed2(Tv, dT, ddT);
         const double nu0 = p[3], nu1 = p[4], nu2 = p[5];
@@ -81,7 +82,7 @@ struct EqGlobal {
         const double g0 = cn * nu0, g1 = cn * nu1 + v, g2 = cn * nu2 + u;          // group velocity (w = 0)
         const double inv_cgm = g_rsqrt(g0 * g0 + g1 * g1 + g2 * g2);
         double st, ct; sincos(p[1], &st, &ct);
-        const double inv_r = 1.0 / r, inv_ct = 1.0 / ct, tant = st * inv_ct;
+        const double inv_r = g_rcp(r), inv_ct = g_rcp(ct), tant = st * inv_ct;
         const double GC1 = inv_r, GC2 = inv_r * inv_ct;
         const double nug = nu1 * g1 + nu2 * g2;
         const double A = nu0 * ct + nu1 * st;
@@ -143,14 +144,14 @@ struct EqGlobal {
         const double rm = ya[0] + dr * 0.5, tm = ya[1] + dt * 0.5;
         double st, ct; sincos(tm, &st, &ct);
         const double a = rm * dt, bc = rm * ct * dp, bs = rm * st * dp;
-        const double ds_tt = sqrt(dr * dr + a * a + bc * bc);
-        const double ds_sb = sqrt(dr * dr + a * a + bs * bs);
+        const double ds_tt = g_sqrt(fmax(dr * dr + a * a + bc * bc, 1e-290));
+        const double ds_sb = g_sqrt(fmax(dr * dr + a * a + bs * bs, 1e-290));
         const double n0 = ya[3] + (yb[3] - ya[3]) * 0.5, n1 = ya[4] + (yb[4] - ya[4]) * 0.5, n2 = ya[5] + (yb[5] - ya[5]) * 0.5;
-        const SegPos sp = seg_locate(T, clampd(rm, T.xmin, T.xmax), cur);
-        const double Tv = spl_f(T.arr(TAB_T), T.arr(TAB_ST), sp);
-        const double u = spl_f(T.arr(TAB_U), T.arr(TAB_SU), sp);
-        const double v = spl_f(T.arr(TAB_V), T.arr(TAB_SV), sp);
-        const double rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+        const SegPos sp = seg_locate(T, rm, cur);
+        const double Tv = spl_f(T, TAB_T, sp);
+        const double u = spl_f(T, TAB_U, sp);
+        const double v = spl_f(T, TAB_V, sp);
+        const double rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         const double cn = c * g_rsqrt(n0 * n0 + n1 * n1 + n2 * n2);
@@ -166,11 +167,11 @@ struct EqGlobal {
         double pv[NEQ];
 #pragma unroll
         for (int i = 0; i < NEQ; i++) pv[i] = ym1[i] + (ym1[i] - yk[i]) * a1;
-        const SegPos sp = seg_locate(T, clampd(pv[0], T.xmin, T.xmax), cur);
+        const SegPos sp = seg_locate(T, pv[0], cur);
         double Tv, dT, u, du, v, dv;
-        spl_f1(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT);
-        spl_f1(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du);
-        spl_f1(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv);
+        spl_f1(T, TAB_T, sp, Tv, dT);
+        spl_f1(T, TAB_U, sp, u, du);
+        spl_f1(T, TAB_V, sp, v, dv);
         const double c = sqrt(kGamR * Tv), dc = kGamR / (2.0 * c) * dT;
         const double dnu_r_ds = -1.0 / c * (L.c_src / c * dc + pv[4] * dv + pv[5] * du + c / pv[0] * (pv[4] * pv[4] + pv[5] * pv[5]));
 #pragma unroll
@@ -188,8 +189,8 @@ struct EqGlobal {
     // GeoAc_Jacobian + GeoAc_Amplitude (Global.cpp:594-629) and the results row of GeoAcGlobal_main.cpp:294-317
     GEOAC_HD static void arrival(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ym1, const double* yk,
                                  double tt, int& cur, double& amp, double& incl, double& backaz, double& aux, double& margin) {
-        const SegPos sp = seg_locate(T, clampd(yk[0], T.xmin, T.xmax), cur);
-        const double c = sound_speed0(spl_f(T.arr(TAB_T), T.arr(TAB_ST), sp));
+        const SegPos sp = seg_locate(T, yk[0], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
         incl = -asin(c / L.c_src * yk[3]) * 180.0 / kPi;
         double b = 90.0 - atan2(-yk[4], -yk[5]) * 180.0 / kPi;
         if (b < -180.0) b += 360.0;
@@ -201,8 +202,8 @@ struct EqGlobal {
         margin = (yk[0] - L.ground) / fabs(yk[0] - ym1[0]);
         amp = 0.0;
         if (AMP) {
-            const double u = spl_f(T.arr(TAB_U), T.arr(TAB_SU), sp), v = spl_f(T.arr(TAB_V), T.arr(TAB_SV), sp);
-            const double rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+            const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
+            const double rho = spl_f(T, TAB_RHO, sp);
             const double r = yk[0], th = yk[1];
             const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
             double sl, cl; sincos(th, &sl, &cl);

@@ -26,6 +26,7 @@ GEOAC_HD RdSound rd_sound(double T) {
 // ======================================================= 3-D Cartesian, range dependent =======================
 template <bool AMP>
 struct Eq3DRD {
+    using Scout = Eq3DRD<false>;           // amplitude-free set used by the cost scout (trace_kernel.cuh)
     static constexpr int NEQ = AMP ? 18 : 6;
     using Atmo = Grid3D;
     using Cursor = Cur3;
@@ -60,7 +61,7 @@ struct Eq3DRD {
     }
 
     GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {       // 3DRngDep.cpp:206-213
-        double r = 0.05 - 0.049 * exp(-(y[2] - L.z_grnd) * (1.0 / 0.75));
+        double r = 0.05 - 0.049 * g_exp(-(y[2] - L.z_grnd) * (1.0 / 0.75));
         return fmax(fmin(r, L.ds_max), L.ds_min);
     }
 
@@ -121,7 +122,7 @@ struct Eq3DRD {
     GEOAC_HD static void segment(const LaunchConsts& L, const Grid3D& G, const RayC&, const double* ya, const double* yb,
                                  Cur3& cur, double& dtt, double& datt) {
         const double dx = yb[0] - ya[0], dy = yb[1] - ya[1], dz = yb[2] - ya[2];
-        const double ds = sqrt(dx * dx + dy * dy + dz * dz);
+        const double ds = g_sqrt(fmax(dx * dx + dy * dy + dz * dz, 1e-290));
         const double xm = ya[0] + dx * 0.5, ym = ya[1] + dy * 0.5, zm = ya[2] + dz * 0.5;
         const double n0 = ya[3] + (yb[3] - ya[3]) * 0.5, n1 = ya[4] + (yb[4] - ya[4]) * 0.5, n2 = ya[5] + (yb[5] - ya[5]) * 0.5;
         double w[4], dzs[3];
@@ -202,6 +203,7 @@ struct Eq3DRD {
 // 7 ab, 8 az, 9 bz) in coordinate order (r, lat, lon): first derivatives {3, 1, 2}; second derivatives below.
 template <bool AMP>
 struct EqGlobalRD {
+    using Scout = EqGlobalRD<false>;           // amplitude-free set used by the cost scout (trace_kernel.cuh)
     static constexpr int NEQ = AMP ? 18 : 6;
     using Atmo = Grid3D;
     using Cursor = Cur3;
@@ -237,7 +239,7 @@ struct EqGlobalRD {
     }
 
     GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {       // GlobalRngDep.cpp:214-221
-        double r = 0.05 - 0.049 * exp(-(y[0] - L.ground) * (1.0 / 0.75));
+        double r = 0.05 - 0.049 * g_exp(-(y[0] - L.ground) * (1.0 / 0.75));
         return fmax(fmin(r, L.ds_max), L.ds_min);
     }
 
@@ -260,7 +262,7 @@ struct EqGlobalRD {
         const double g0 = cn * nu0, g1 = cn * nu1 + v, g2 = cn * nu2 + u;
         const double inv_cgm = g_rsqrt(g0 * g0 + g1 * g1 + g2 * g2);
         double st, ct; sincos(p[1], &st, &ct);
-        const double inv_r = 1.0 / r, inv_ct = 1.0 / ct, tant = st * inv_ct;
+        const double inv_r = g_rcp(r), inv_ct = g_rcp(ct), tant = st * inv_ct;
         const double GC[3] = { 1.0, inv_r, inv_r * inv_ct };
         const double nug = nu1 * g1 + nu2 * g2;
         const double A = nu0 * ct + nu1 * st;
@@ -322,7 +324,7 @@ struct EqGlobalRD {
         const double rm = ya[0] + dr * 0.5, tm = ya[1] + dt * 0.5, pm = ya[2] + dp * 0.5;
         double st, ct; sincos(tm, &st, &ct);
         const double a = rm * dt, bc = rm * ct * dp, bs = rm * st * dp;
-        const double ds_tt = sqrt(dr * dr + a * a + bc * bc), ds_sb = sqrt(dr * dr + a * a + bs * bs);
+        const double ds_tt = g_sqrt(fmax(dr * dr + a * a + bc * bc, 1e-290)), ds_sb = g_sqrt(fmax(dr * dr + a * a + bs * bs, 1e-290));
         const double n0 = ya[3] + (yb[3] - ya[3]) * 0.5, n1 = ya[4] + (yb[4] - ya[4]) * 0.5, n2 = ya[5] + (yb[5] - ya[5]) * 0.5;
         double w[4], wr[4], dzs[3];
         ms_wrappers<true, true, false>(G, tm, pm, rm, cur, w, dzs);
@@ -425,8 +427,8 @@ GEOAC_HD void fill_launch_consts_3d(LaunchConsts& L, const Grid3D& G, int varian
         ms_wrappers<false, true, false>(G, 0.0, 0.0, L.z_grnd, cur, w, dzs);
         suthbass_setup(L, sqrt(kGamR * w[0]), w[3]);
     } else {
-        L.sb.invTo = L.sb.cbrtTo = L.sb.visc_num = L.sb.invPo = 0.0;     // per step (see EqGlobalRD::segment)
-        L.sb_w = 2.0 * kPi * L.freq;
+        L.sb.invTo = L.sb.cbrtTo = L.sb.visc_num = L.sb.inv_visc_num = L.sb.invPo = 0.0;     // per step (see EqGlobalRD::segment)
+        suthbass_tables(L);
     }
 }
 

@@ -11,8 +11,9 @@
 //    far along their rays are.  Bounces / arrivals / breaks are handled in a rare divergent tail of the trip.
 //  * finished lanes are refilled at the top of the trip: a warp ballot counts the idle lanes, one lane claims that
 //    many ray indices from a global counter with a single atomicAdd, the indices are handed out by lane rank.
-//  * only three states are ever needed (k-2, k-1, k): y_k and y_{k+1} live in registers, y_{k-1} is parked in a
-//    per-thread shared-memory column (conflict-free [eq][thread] layout).  The reference stores 500 000 x EqCnt.
+//  * only three states are ever needed (k-2, k-1, k): y_k sits in the lane's shared-memory record, y_{k+1} is built in
+//    registers, y_{k-1} is parked in an L2-resident global scratch (one coalesced store per equation per step; read back
+//    only at a reflection).  The reference stores 500 000 x EqCnt.
 //  * RK4 combination in the reference's association order  y + k1/6 + k2/3 + k3/3 + k4/6  (Solver.cpp:54), built
 //    on the fly so no k_i is kept.
 #pragma once
@@ -24,8 +25,8 @@ namespace geoac {
 
 struct TraceArgs {
     Grid3D grid;                // range-dependent variants: node tables in global memory (L1/L2 resident working set)
-    const double* table;        // global copy of the table (TAB_NARR * n_pad doubles, 16-byte aligned)
-    int table_n, table_npad;
+    const double* table;        // global copy of the table (n records of TAB_NARR doubles, 16-byte aligned)
+    int table_n;
     double table_xmin, table_xmax;
     const LaunchConsts* consts; // device
     const double* theta;        // [n_rays]
@@ -37,6 +38,9 @@ struct TraceArgs {
     int32_t* n_steps;
     unsigned long long* counter;      // next unclaimed ray
     unsigned long long* total_steps;  // RK4 steps taken (all rays)
+    unsigned long long* warp_trips;   // trips round the step loop, summed over warps (lane occupancy = steps / (32 trips))
+    const uint32_t* order;            // claim order (longest-predicted ray first) or nullptr = natural order
+    double* prev;                     // y_{k-1} scratch: [NEQ][grid * block] doubles (variants with a quadratic intercept)
 };
 
 // Per-launch invariants of the stratified variants (source / ground / reference-level atmosphere samples and the
@@ -46,12 +50,12 @@ GEOAC_HD void fill_launch_consts_1d(LaunchConsts& L, const Table1D& T, int varia
     int cur = 0;
     double c, u, v, rho, dc, du, dv;
     auto sample = [&](double x) {
-        const SegPos sp = seg_locate(T, clampd(x, T.xmin, T.xmax), cur);
+        const SegPos sp = seg_locate(T, x, cur);
         double Tv, dT, ddT, d2;
-        spl_f2(T.arr(TAB_T), T.arr(TAB_ST), sp, Tv, dT, ddT);
-        spl_f2(T.arr(TAB_U), T.arr(TAB_SU), sp, u, du, d2);
-        spl_f2(T.arr(TAB_V), T.arr(TAB_SV), sp, v, dv, d2);
-        rho = spl_f(T.arr(TAB_RHO), T.arr(TAB_SRHO), sp);
+        spl_f2(T, TAB_T, sp, Tv, dT, ddT);
+        spl_f2(T, TAB_U, sp, u, du, d2);
+        spl_f2(T, TAB_V, sp, v, dv, d2);
+        rho = spl_f(T, TAB_RHO, sp);
         c = sqrt(kGamR * Tv);
         dc = kGamR / (2.0 * c) * dT;
     };
@@ -71,93 +75,108 @@ GEOAC_HD void fill_launch_consts_1d(LaunchConsts& L, const Table1D& T, int varia
 struct RecOut { double* rec; int32_t* status; int32_t* n_steps; int64_t n_slots; int n_rec; };
 
 // ---------------------------------------------------------------------------------------------------------------
-// One lane = one ray in flight.  advance() performs exactly one RK4 step, the travel-time/absorption bookkeeping of
-// that step's segment, and -- rarely -- the end-of-bounce tail (arrival record, reflection, break).  It is the whole
-// per-ray state machine of SURVEY 3.4; the kernel below only adds lane refill around it.
+// One lane = one ray in flight.  The FP64 part of its state (LaneD: y_k, the per-ray constants, the running sums) lives
+// in SHARED memory on the device -- one contiguous record per thread with an odd stride in doubles, so the 64-bit
+// accesses of a half-warp fall into 16 distinct bank pairs -- which is what lets 512 threads (16 warps) per SM fit
+// the register file next to the 112 KB spline table.  The integer part (LaneI) stays in registers.
+// lane_advance() performs exactly one RK4 step, the travel-time/absorption bookkeeping of that step's segment, and --
+// rarely -- the end-of-bounce tail (arrival record, reflection, break).  It is the whole per-ray state machine of
+// SURVEY 3.4; the kernel below only adds lane refill around it.
 // ---------------------------------------------------------------------------------------------------------------
 template <class EQ>
-struct Lane {
-    static constexpr int NEQ = EQ::NEQ;
-    double y[NEQ];
+struct LaneD {
+    double y[EQ::NEQ];
     typename EQ::RayC rc;
+    double tt_total, att_total, tt_b, att_b, zmax;
+};
+template <class EQ>
+struct LaneI {
     typename EQ::Cursor cur;
     int bounce, ksteps;
     int64_t ray;
-    double tt_total, att_total, tt_b, att_b, zmax;
+};
 
-    GEOAC_HD void start(const LaunchConsts& L, const typename EQ::Atmo& T, int64_t idx, double theta, double phi) {
-        ray = idx; bounce = 0; ksteps = 0; cur = typename EQ::Cursor{};
-        tt_total = att_total = tt_b = att_b = zmax = 0.0;
-        EQ::init(L, T, theta, phi, rc, y, cur);
-    }
+// does the reflection need y_{k-2}?  (quadratic intercept: 2D, 3D, 3D.RngDep; the Global variants fit a line, App. A-7)
+template <class EQ> struct NeedsPrev { static constexpr bool value = !(EQ::VARIANT == GEOAC_GLOBAL || EQ::VARIANT == GEOAC_GLOBAL_RNGDEP); };
 
-    // prev[i * pstride] holds y_{k-1}[i]; returns false when the ray has ended
-    GEOAC_HD bool advance(const LaunchConsts& L, const typename EQ::Atmo& T, double* prev, int pstride, const RecOut& o) {
-        zmax = fmax(zmax, EQ::altitude(y));                    // running turning height over m < k (App. A-3)
-        const double ds = EQ::step_size(L, y);
-        double acc[NEQ], p[NEQ], f[NEQ];
+template <class EQ>
+GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, int64_t idx, double theta, double phi) {
+    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.cur = typename EQ::Cursor{};
+    d.tt_total = d.att_total = d.tt_b = d.att_b = d.zmax = 0.0;
+    EQ::init(L, T, theta, phi, d.rc, d.y, n.cur);
+}
+
+// prev[i * pstride] holds y_{k-1}[i] (only maintained when NeedsPrev); returns false when the ray has ended
+template <class EQ>
+GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, double* prev, int64_t pstride, const RecOut& o) {
+    constexpr int NEQ = EQ::NEQ;
+    double* const y = d.y;
+    d.zmax = fmax(d.zmax, EQ::altitude(y));                     // running turning height over m < k (App. A-3)
+    const double ds = EQ::step_size(L, y);
+    double acc[NEQ], p[NEQ], f[NEQ];
 #pragma unroll
-        for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = y[i]; }
+    for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = acc[i]; }
 #pragma unroll 1
-        for (int s = 0; s < 4; s++) {
-            EQ::rhs(L, T, rc, p, f, cur);
-            const double wa = (s == 2) ? 1.0 : 0.5;
-            const double wb = (s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0);
+    for (int s = 0; s < 4; s++) {
+        EQ::rhs(L, T, d.rc, p, f, n.cur);
+        const double dsa = ds * ((s == 2) ? 1.0 : 0.5);
+        const double dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
 #pragma unroll
-            for (int i = 0; i < NEQ; i++) {
-                const double k = ds * f[i];
-                acc[i] += k * wb;                              // y + k1/6 + k2/3 + k3/3 + k4/6, left to right
-                p[i] = y[i] + k * wa;
-            }
+        for (int i = 0; i < NEQ; i++) {
+            acc[i] = fma(f[i], dsb, acc[i]);                   // y + k1/6 + k2/3 + k3/3 + k4/6, left to right (k_i = ds f_i)
+            p[i] = fma(f[i], dsa, y[i]);                       // y + k_i/2 (stage 4: y + k_3)
         }
-        ksteps++;
-        double dtt, datt;
-        EQ::segment(L, T, rc, y, acc, cur, dtt, datt);
-        const bool brk = EQ::left_region(L, rc, acc);            // BreakCheck first (Solver.cpp:57-64)
-        const bool gnd = !brk && EQ::below_ground(L, acc);
-        const bool lim = !brk && !gnd && (ksteps >= L.step_limit - 1);
-        if (L.seg_mode) { if (!(brk || gnd || lim)) { tt_total += dtt; att_total += datt; } }
-        else            { tt_b += dtt; att_b += datt; }
+    }
+    n.ksteps++;
+    double dtt, datt;
+    EQ::segment(L, T, d.rc, y, acc, n.cur, dtt, datt);
+    const bool brk = EQ::left_region(L, d.rc, acc);              // BreakCheck first (Solver.cpp:57-64)
+    const bool gnd = !brk && EQ::below_ground(L, acc);
+    const bool lim = !brk && !gnd && (n.ksteps >= L.step_limit - 1);
+    if (L.seg_mode) { if (!(brk || gnd || lim)) { d.tt_total += dtt; d.att_total += datt; } }
+    else            { d.tt_b += dtt; d.att_b += datt; }
 
-        if (!(brk || gnd || lim)) {
+    if (!(brk || gnd || lim)) {
 #pragma unroll
-            for (int i = 0; i < NEQ; i++) { prev[i * pstride] = y[i]; y[i] = acc[i]; }
-            return true;
+        for (int i = 0; i < NEQ; i++) {
+            if (NeedsPrev<EQ>::value) prev[i * pstride] = y[i];
+            y[i] = acc[i];
         }
-        // ---------------- rare tail: end of a bounce segment ----------------
-        const int64_t slot = ray * o.n_rec + bounce;
-        if (!gnd) {
-            o.status[slot] = brk ? GEOAC_ST_BREAK : GEOAC_ST_LIMIT;
-            o.n_steps[slot] = brk ? ksteps : L.step_limit;
-            return false;
-        }
-        if (!L.seg_mode) { tt_total += tt_b; att_total += att_b; tt_b = 0.0; att_b = 0.0; }
-        double amp, incl, baz, aux, margin;
-        EQ::arrival(L, T, rc, y, acc, tt_total, cur, amp, incl, baz, aux, margin);
-#pragma unroll
-        for (int i = 0; i < NEQ; i++) o.rec[(int64_t)i * o.n_slots + slot] = acc[i];
-        o.rec[(int64_t)GEOAC_F_TRAVELTIME * o.n_slots + slot] = tt_total;
-        o.rec[(int64_t)GEOAC_F_ATTEN * o.n_slots + slot] = att_total;
-        o.rec[(int64_t)GEOAC_F_TURNHEIGHT * o.n_slots + slot] = zmax;
-        o.rec[(int64_t)GEOAC_F_AMPLITUDE * o.n_slots + slot] = amp;
-        o.rec[(int64_t)GEOAC_F_INCLINATION * o.n_slots + slot] = incl;
-        o.rec[(int64_t)GEOAC_F_BACKAZ * o.n_slots + slot] = baz;
-        o.rec[(int64_t)GEOAC_F_AUX * o.n_slots + slot] = aux;
-        o.rec[(int64_t)GEOAC_F_MARGIN * o.n_slots + slot] = margin;
-        o.status[slot] = GEOAC_ST_ARRIVAL;
-        o.n_steps[slot] = ksteps;
-        if (bounce >= L.bounces) return false;
-        double ym2[NEQ], y0[NEQ];
-#pragma unroll
-        for (int i = 0; i < NEQ; i++) ym2[i] = prev[i * pstride];
-        EQ::reflect(L, T, rc, ym2, y, acc, y0, cur);
-#pragma unroll
-        for (int i = 0; i < NEQ; i++) y[i] = y0[i];
-        bounce++; ksteps = 0;
-        if (L.per_bounce_zmax) zmax = 0.0;
         return true;
     }
-};
+    // ---------------- rare tail: end of a bounce segment ----------------
+    const int64_t slot = n.ray * o.n_rec + n.bounce;
+    if (!gnd) {
+        o.status[slot] = brk ? GEOAC_ST_BREAK : GEOAC_ST_LIMIT;
+        o.n_steps[slot] = brk ? n.ksteps : L.step_limit;
+        return false;
+    }
+    if (!L.seg_mode) { d.tt_total += d.tt_b; d.att_total += d.att_b; d.tt_b = 0.0; d.att_b = 0.0; }
+    double amp, incl, baz, aux, margin;
+    EQ::arrival(L, T, d.rc, y, acc, d.tt_total, n.cur, amp, incl, baz, aux, margin);
+#pragma unroll
+    for (int i = 0; i < NEQ; i++) o.rec[(int64_t)i * o.n_slots + slot] = acc[i];
+    o.rec[(int64_t)GEOAC_F_TRAVELTIME * o.n_slots + slot] = d.tt_total;
+    o.rec[(int64_t)GEOAC_F_ATTEN * o.n_slots + slot] = d.att_total;
+    o.rec[(int64_t)GEOAC_F_TURNHEIGHT * o.n_slots + slot] = d.zmax;
+    o.rec[(int64_t)GEOAC_F_AMPLITUDE * o.n_slots + slot] = amp;
+    o.rec[(int64_t)GEOAC_F_INCLINATION * o.n_slots + slot] = incl;
+    o.rec[(int64_t)GEOAC_F_BACKAZ * o.n_slots + slot] = baz;
+    o.rec[(int64_t)GEOAC_F_AUX * o.n_slots + slot] = aux;
+    o.rec[(int64_t)GEOAC_F_MARGIN * o.n_slots + slot] = margin;
+    o.status[slot] = GEOAC_ST_ARRIVAL;
+    o.n_steps[slot] = n.ksteps;
+    if (n.bounce >= L.bounces) return false;
+    double ym2[NEQ], y0[NEQ];
+#pragma unroll
+    for (int i = 0; i < NEQ; i++) ym2[i] = NeedsPrev<EQ>::value ? prev[i * pstride] : 0.0;
+    EQ::reflect(L, T, d.rc, ym2, y, acc, y0, n.cur);
+#pragma unroll
+    for (int i = 0; i < NEQ; i++) y[i] = y0[i];
+    n.bounce++; n.ksteps = 0;
+    if (L.per_bounce_zmax) d.zmax = 0.0;
+    return true;
+}
 
 #ifdef __CUDACC__
 
@@ -189,15 +208,18 @@ __device__ __forceinline__ void tma_stage_table(double* dst, const double* src, 
     }
 }
 
+// odd number of doubles per lane record: conflict-free 64-bit shared-memory accesses with one record per thread
+template <class EQ> struct LaneLayout { static constexpr int STRIDE = (int)((sizeof(LaneD<EQ>) / sizeof(double)) | 1); };
+
 template <class EQ, int BLOCK, bool TABLE_IN_SMEM>
 __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__ TraceArgs a) {
     constexpr int NEQ = EQ::NEQ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    // layout: [LaunchConsts][mbarrier][prev: NEQ*BLOCK doubles][table]
+    // layout: [LaunchConsts][mbarrier][lane records: BLOCK x STRIDE doubles][table]
     LaunchConsts* Ls = reinterpret_cast<LaunchConsts*>(smem_raw);
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(LaunchConsts) + 15) / 16) * 16);
-    double* prev = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bar) + 16);
-    double* tab_s = prev + NEQ * BLOCK;
+    double* lanes = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(bar) + 16);
+    double* tab_s = lanes + ((LaneLayout<EQ>::STRIDE * BLOCK + 1) & ~1);          // keep the table 16-byte aligned
 
     for (int i = threadIdx.x; i < (int)(sizeof(LaunchConsts) / 8); i += BLOCK)
         reinterpret_cast<double*>(Ls)[i] = reinterpret_cast<const double*>(a.consts)[i];
@@ -205,9 +227,9 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
     if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) {
         T = a.grid;
     } else {
-        T.n = a.table_n; T.n_pad = a.table_npad; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
+        T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
         if (TABLE_IN_SMEM) {
-            tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_npad * sizeof(double)), bar);
+            tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_n * sizeof(double)), bar);
             T.base = tab_s;
         } else {
             T.base = a.table;
@@ -218,9 +240,14 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
 
     const unsigned lane = threadIdx.x & 31;
     RecOut o; o.rec = a.rec; o.status = a.status; o.n_steps = a.n_steps; o.n_rec = a.n_rec; o.n_slots = a.n_rays * a.n_rec;
-    Lane<EQ> ln;
+    LaneD<EQ>& ld = *reinterpret_cast<LaneD<EQ>*>(lanes + (size_t)threadIdx.x * LaneLayout<EQ>::STRIDE);
+    LaneI<EQ> li;
+    // y_{k-1} history (quadratic intercept only): [eq][global thread] in an L2-resident global scratch, written once per step
+    const int64_t pstride = (int64_t)gridDim.x * BLOCK;
+    double* prev = a.prev + ((int64_t)blockIdx.x * BLOCK + threadIdx.x);
     bool have_ray = false, exhausted = false;
     unsigned long long my_steps = 0;
+    unsigned my_trips = 0;
 
     while (true) {
         // ---------------- refill idle lanes (warp-aggregated claim) ----------------
@@ -233,18 +260,114 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             base = __shfl_sync(0xffffffffu, base, leader);
             if (want) {
                 const int64_t idx = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
-                if (idx < a.n_rays) { ln.start(L, T, idx, a.theta[idx], a.phi[idx]); have_ray = true; }
+                if (idx < a.n_rays) {
+                    const int64_t r = a.order ? (int64_t)a.order[idx] : idx;
+                    lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]); have_ray = true;
+                }
                 else exhausted = true;
             }
         }
         if (!__any_sync(0xffffffffu, have_ray)) break;
+        my_trips++;
         if (have_ray) {
-            have_ray = ln.advance(L, T, prev + threadIdx.x, BLOCK, o);
+            have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o);
             my_steps++;
         }
     }
     for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
-    if (lane == 0 && my_steps) atomicAdd(a.total_steps, my_steps);      // one atomic per warp
+    if (lane == 0 && my_steps) { atomicAdd(a.total_steps, my_steps); atomicAdd(a.warp_trips, (unsigned long long)my_trips); }   // per warp
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Longest-ray-first scheduling.  Ray lifetimes differ by an order of magnitude and a lane processes only a few rays,
+// so with the natural claim order ~30 % of the lane-steps of a 2e5-ray batch idle in the tail while the last long
+// rays finish.  A SCOUT pass predicts each ray's RK4 step count by tracing it with the amplitude-free equation set
+// (EQ<false>) at COARSE times the step size -- ~1/COARSE of the steps at ~1/4 of the cost per step, i.e. a few per cent
+// of the real trace -- then a counting sort over 256 cost buckets yields the claim order, longest first.  The order
+// only affects scheduling: every ray's arithmetic is independent of which lane runs it and when.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kScoutCoarse = 16;
+constexpr int kCostBuckets = 256;
+
+template <class EQ>
+__global__ void __launch_bounds__(128) scout_kernel(const __grid_constant__ TraceArgs a, uint32_t* cost, uint32_t* cost_max) {
+    constexpr int NEQ = EQ::NEQ;
+    const LaunchConsts& L = *a.consts;
+    typename EQ::Atmo T;
+    if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) { T = a.grid; }
+    else { T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.base = a.table; }
+    uint32_t worst = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_rays; r += (int64_t)gridDim.x * blockDim.x) {
+        double y[NEQ], ym1[NEQ], acc[NEQ], p[NEQ], f[NEQ];
+        typename EQ::RayC rc; typename EQ::Cursor cur = typename EQ::Cursor{};
+        EQ::init(L, T, a.theta[r], a.phi[r], rc, y, cur);
+#pragma unroll
+        for (int i = 0; i < NEQ; i++) ym1[i] = y[i];
+        uint32_t est = 0, seg = 0; int bounce = 0;
+        const uint32_t cap = (uint32_t)L.step_limit;
+        while (true) {
+            const double ds = (double)kScoutCoarse * EQ::step_size(L, y);
+#pragma unroll
+            for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = y[i]; }
+#pragma unroll 1
+            for (int s = 0; s < 4; s++) {
+                EQ::rhs(L, T, rc, p, f, cur);
+                const double dsa = ds * ((s == 2) ? 1.0 : 0.5), dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+#pragma unroll
+                for (int i = 0; i < NEQ; i++) { acc[i] = fma(f[i], dsb, acc[i]); p[i] = fma(f[i], dsa, y[i]); }
+            }
+            est += kScoutCoarse; seg += kScoutCoarse;
+            if (EQ::left_region(L, rc, acc) || seg >= cap) break;
+            if (EQ::below_ground(L, acc)) {
+                if (bounce >= L.bounces) break;
+                double y0[NEQ];
+                EQ::reflect(L, T, rc, ym1, y, acc, y0, cur);
+#pragma unroll
+                for (int i = 0; i < NEQ; i++) { y[i] = y0[i]; ym1[i] = y0[i]; }
+                bounce++; seg = 0;
+                continue;
+            }
+#pragma unroll
+            for (int i = 0; i < NEQ; i++) { ym1[i] = y[i]; y[i] = acc[i]; }
+        }
+        cost[r] = est;
+        worst = max(worst, est);
+    }
+    worst = __reduce_max_sync(0xffffffffu, worst);
+    if ((threadIdx.x & 31) == 0 && worst) atomicMax(cost_max, worst);
+}
+
+// counting sort by predicted cost, descending: hist[b] of bucket(cost) -> start offsets -> scatter
+__device__ __forceinline__ int cost_bucket(uint32_t c, uint32_t cmax) {
+    return (kCostBuckets - 1) - (int)(((uint64_t)c * (kCostBuckets - 1)) / (cmax ? cmax : 1u));      // longest -> bucket 0
+}
+__global__ void order_hist_kernel(const uint32_t* cost, int64_t n, const uint32_t* cost_max, uint32_t* hist) {
+    __shared__ uint32_t h[kCostBuckets];
+    for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const uint32_t cmax = *cost_max;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[cost_bucket(cost[r], cmax)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
+}
+__global__ void order_scan_kernel(uint32_t* hist) {          // one block of kCostBuckets threads: exclusive prefix in place
+    __shared__ uint32_t h[kCostBuckets];
+    const int t = threadIdx.x;
+    h[t] = hist[t];
+    __syncthreads();
+    for (int off = 1; off < kCostBuckets; off <<= 1) {
+        const uint32_t v = (t >= off) ? h[t - off] : 0u;
+        __syncthreads();
+        h[t] += v;
+        __syncthreads();
+    }
+    hist[t] = h[t] - hist[t];
+}
+__global__ void order_scatter_kernel(const uint32_t* cost, int64_t n, const uint32_t* cost_max, uint32_t* offs, uint32_t* order) {
+    const uint32_t cmax = *cost_max;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
+        order[atomicAdd(&offs[cost_bucket(cost[r], cmax)], 1u)] = (uint32_t)r;
 }
 
 #endif  // __CUDACC__

@@ -153,6 +153,16 @@ int geoac_load_met_grid(const char* prefix, const char* loc0, const char* loc1, 
 /* Number of state equations for (variant, calc_amp): GeoAc_SetEqCnt, Code/GeoAc/GeoAc.Interface.cpp:21-41. */
 int geoac_eq_count(int variant, int calc_amp);
 
+/* Scheduling counters of the last trace.  warp_trips: trips round the kernel's step loop summed over warps -- lane
+ * occupancy = total_steps / (32 * warp_trips), i.e. how full the warps were on average (ray lifetimes differ; finished
+ * lanes are refilled until the batch is exhausted).  kernel_launches: kernels the call enqueued (1 trace kernel, plus 4
+ * when the longest-ray-first claim order was built: cost scout, histogram, scan, scatter).  Either pointer may be NULL. */
+int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kernel_launches);
+
+/* Device self-test of the kernel's branch-free FP64 primitives (reciprocal, reciprocal square root, square root, exp, 10^x)
+ * against the CUDA math library on n_per_thread random operands per thread: max_rel_err[5] in that order. */
+int geoac_selftest_math(geoac_ctx* ctx, int n_per_thread, double* max_rel_err);
+
 /* FP64 DFMA micro-benchmark on ctx's device: returns measured TFLOP/s (2 flops per DFMA) -- the roofline denominator. */
 double geoac_measure_fp64_peak(geoac_ctx* ctx, double* out_ms);
 

@@ -47,25 +47,25 @@ def natural_slopes(x, f):
 
 def make_table(is_global, z, T, u, v, rho):
     x = np.array(z, dtype=np.float64) + (6370.0 if is_global else 0.0)
-    n = len(x); n_pad = (n + 1) & ~1
-    tab = np.zeros((10, n_pad))
-    tab[0, :n] = x
-    tab[1, : n - 1] = 1.0 / (x[1:] - x[:-1])
-    for row, f in ((2, T), (4, u), (6, v), (8, rho)):
-        tab[row, :n] = f
-        tab[row + 1, :n] = natural_slopes(x, np.asarray(f, dtype=np.float64))
-    return tab, n, n_pad
+    n = len(x)
+    tab = np.zeros((n, 10))                      # one record per level: x, invh, T, sT, u, su, v, sv, rho, srho (core.cuh)
+    tab[:, 0] = x
+    tab[: n - 1, 1] = 1.0 / (x[1:] - x[:-1])
+    for col, f in ((2, T), (4, u), (6, v), (8, rho)):
+        tab[:, col] = f
+        tab[:, col + 1] = natural_slopes(x, np.asarray(f, dtype=np.float64))
+    return tab, n
 
 
 def trace(variant, params, atmo_arrays, theta, phi):
     L = C.CDLL(build())
     L.emul_trace_1d.restype = C.c_long
-    L.emul_trace_1d.argtypes = [C.c_int, C.POINTER(abi.GeoacParams), C.c_int, C.c_int, dp, C.c_long, dp, dp, dp, ip, ip]
-    tab, n, n_pad = make_table(variant == abi.GEOAC_GLOBAL, *atmo_arrays)
+    L.emul_trace_1d.argtypes = [C.c_int, C.POINTER(abi.GeoacParams), C.c_int, dp, C.c_long, dp, dp, dp, ip, ip]
+    tab, n = make_table(variant == abi.GEOAC_GLOBAL, *atmo_arrays)
     theta = np.ascontiguousarray(theta, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
     nr = len(theta); n_rec = params.bounces + 1
     rec = np.zeros((abi.NFIELDS, nr, n_rec)); status = np.zeros((nr, n_rec), dtype=np.int32); n_steps = np.zeros((nr, n_rec), dtype=np.int32)
-    total = L.emul_trace_1d(variant, C.byref(params), n, n_pad, tab.ctypes.data_as(dp), nr, theta.ctypes.data_as(dp), phi.ctypes.data_as(dp),
+    total = L.emul_trace_1d(variant, C.byref(params), n, tab.ctypes.data_as(dp), nr, theta.ctypes.data_as(dp), phi.ctypes.data_as(dp),
                             rec.ctypes.data_as(dp), status.ctypes.data_as(ip), n_steps.ctypes.data_as(ip))
     return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total}
 

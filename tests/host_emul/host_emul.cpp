@@ -1,5 +1,5 @@
 // tests/host_emul/host_emul.cpp -- TEST-ONLY debugging aid (never part of libgeoac_b200.so, never a fallback).
-// Compiles the per-ray state machine of geoac_b200/csrc (Lane<EQ>::advance and the equation sets, all GEOAC_HD) with
+// Compiles the per-ray state machine of geoac_b200/csrc (lane_advance<EQ> and the equation sets, all GEOAC_HD) with
 // g++ so that the de-duplicated device math can be checked against the oracle in the build container, where there
 // is no GPU.  The real parity gate is tests/test_gpu_parity.py on a B200.
 #include <cmath>
@@ -23,17 +23,17 @@ static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const
     long steps = 0;
     std::vector<double> prev(EQ::NEQ, 0.0);
     for (long i = 0; i < n; i++) {
-        Lane<EQ> ln;
-        ln.start(L, T, i, th[i], ph[i]);
-        while (ln.advance(L, T, prev.data(), 1, o)) steps++;
+        LaneD<EQ> ld; LaneI<EQ> li;
+        lane_start<EQ>(ld, li, L, T, i, th[i], ph[i]);
+        while (lane_advance<EQ>(ld, li, L, T, prev.data(), 1, o)) steps++;
         steps++;
     }
     return steps;
 }
 
-extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, int n_pad, const double* table, long n_rays,
+extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const double* table, long n_rays,
                               const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps) {
-    Table1D T; T.base = table; T.n = n; T.n_pad = n_pad; T.xmin = table[TAB_X * n_pad]; T.xmax = table[TAB_X * n_pad + n - 1];
+    Table1D T; T.base = table; T.n = n; T.xmin = table[TAB_X]; T.xmax = table[(size_t)(n - 1) * TAB_NARR + TAB_X];
     LaunchConsts L; std::memset(&L, 0, sizeof L);
     L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
     L.z_grnd = p->z_grnd; L.tweak_abs = p->tweak_abs; L.freq = p->freq;
