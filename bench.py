@@ -1,15 +1,21 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the batched ray-tracing hot path on BASELINE.json's config 2
+"""bench.py -- throughput of the batched ray-tracing hot path.  Default workload: BASELINE.json's config 2
 (GeoAc3D, ToyAtmo.met, theta 1-60 deg step 1 x azimuth 0-359.9 deg step 0.1 = 216 000 rays, 2 bounces, CalcAmp on,
-WriteRays=False), one pass over the whole launch-angle grid = one "step".
+WriteRays=False); one pass over the whole launch-angle grid = one "step".
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2|config1|smallgrid]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-N > 1 is launched by torchrun, one rank per GPU; the launch-angle grid is replicated per rank with a rank-specific
-azimuth offset (weak scaling, no data-path collective: rays are independent).  Rank 0 prints ONE JSON line.
+Workloads: config1 ... config5 are BASELINE.json's five configurations; config4s / config5s are the
+same range-dependent runs on a coarser node grid with fewer rays (quick checks); smallgrid / midgrid are reduced config-2
+launch grids.  N > 1 is launched by torchrun, one rank per GPU, no data-path collective (rays are independent):
+  * config 5 (the "1e6 rays sharded across 1/2/4/8 B200" configuration) splits its ray list across ranks in interleaved
+    4096-ray blocks -> "scaling": "strong";
+  * every other workload replicates the launch grid per rank with a rank-specific azimuth rotation -> "scaling": "weak".
+Rank 0 prints ONE JSON line.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -23,27 +29,82 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 TOY = os.path.join(ROOT, "tests", "golden", "ToyAtmo.met")
-# ALGORITHMIC FP64 operations per RK4 step (de-duplicated, CalcAmp on, incl. travel-time + absorption bookkeeping);
-# convention and derivation in DESIGN.md section "flop counting" (add/sub/mul/div/sqrt/transcendental = 1, fma = 2)
-ALGO_FLOPS_PER_STEP = {"config2": 2200.0, "config1": 1400.0, "smallgrid": 2200.0, "midgrid": 2200.0}
+PI = 3.141592653589793238462643
+
+V2D, V3D, VGLOBAL, V3DRD, VGLOBALRD = 0, 1, 2, 3, 4
+KERNEL_NAMES = {V2D: "geoac::trace_kernel<Eq2D<true>,512,true>", V3D: "geoac::trace_kernel<Eq3D<true>,384,true>",
+                VGLOBAL: "geoac::trace_kernel<EqGlobal<true>,384,true>", V3DRD: "geoac::trace_kernel<Eq3DRD<true>,128,false>",
+                VGLOBALRD: "geoac::trace_kernel<EqGlobalRD<true>,128,false>"}
+# ALGORITHMIC FP64 operations per RK4 step of each variant (de-duplicated, CalcAmp on, incl. travel-time + absorption
+# bookkeeping); convention and derivation in DESIGN.md "flop counting" (add/sub/mul/div/sqrt/transcendental = 1, fma = 2)
+ALGO_FLOPS_PER_STEP = {V2D: 1400.0, V3D: 2200.0, VGLOBAL: 2800.0, V3DRD: 39000.0, VGLOBALRD: 40000.0}
+
+#               variant    theta_min, theta_max, theta_step, phi_min, phi_max, phi_step   bounces  atmosphere
+WORKLOADS = {
+    "config1":   (V2D,       (0.5, 45.0, 0.5, -90.0, -90.0, 1.0),       2, "toy"),
+    "config2":   (V3D,       (1.0, 60.5, 1.0, 0.0, 359.95, 0.1),        2, "toy"),
+    "smallgrid": (V3D,       (1.0, 60.5, 1.0, 0.0, 359.5, 5.0),         2, "toy"),
+    "midgrid":   (V3D,       (1.0, 60.5, 1.0, 0.0, 359.75, 0.5),        2, "toy"),
+    "config3":   (VGLOBAL,   (0.5, 50.45, 0.1, 0.0, 359.8, 0.36),       5, "c3"),
+    "config4":   (V3DRD,     (1.0, 50.975, 0.05, 0.0, 358.0, 3.6),      2, "c4"),
+    "config4s":  (V3DRD,     (1.0, 50.75, 0.5, 0.0, 358.0, 3.6),        2, "c4s"),
+    "config5":   (VGLOBALRD, (1.0, 50.975, 0.05, 0.0, 359.8, 0.36),     2, "c5"),
+    "config5s":  (VGLOBALRD, (1.0, 50.75, 0.5, 0.0, 358.0, 3.6),        2, "c5s"),
+}
+DESCRIPTIONS = {
+    "config1": "BASELINE config 1: GeoAc2D, ToyAtmo.met, theta 0.5..45 step 0.5, azimuth -90 (90 rays), bounces=2",
+    "config2": "BASELINE config 2: GeoAc3D stratified, ToyAtmo.met, theta 1..60 step 1 x azimuth 0..359.9 step 0.1 (216000 rays), bounces=2, CalcAmp on, WriteRays=False",
+    "smallgrid": "reduced grid for debugging: GeoAc3D, theta 1..60 x azimuth 0..355 step 5 (4320 rays)",
+    "midgrid": "reduced grid for ncu captures: GeoAc3D, theta 1..60 x azimuth 0..359.5 step 0.5 (43200 rays)",
+    "config3": "BASELINE config 3: GeoAcGlobal, synthetic stratified profile to 150 km (SURVEY 8d), source lat 30 lon 0, theta 0.5..50.4 step 0.1 x azimuth 0..359.64 step 0.36 (500000 rays), bounces=5, rng_max=3000",
+    "config4": "BASELINE config 4: GeoAc3D.RngDep, synthetic 200x200x300 node grid (SURVEY 8d), theta 1..50.95 step 0.05 x azimuth 0..356.4 step 3.6 (100000 rays), bounces=2, CalcAmp on",
+    "config4s": "config 4 on a 50x50x300 node grid with 10000 rays (quick check)",
+    "config5": "BASELINE config 5: GeoAcGlobal.RngDep, synthetic 181x361x300 global grid (SURVEY 8d), source lat 35 lon 0, theta 1..50.95 step 0.05 x azimuth 0..359.64 step 0.36 (1000000 rays), bounces=2",
+    "config5s": "config 5 on a 46x91x300 node grid with 10000 rays (quick check)",
+}
+SHARDED = {"config5"}            # strong scaling: one ray list split across ranks (geoac_b200/sharding.py)
 
 
 def workload_angles(name, rank=0):
     from geoac_b200 import api
-    if name == "config2":
-        grid = (1.0, 60.5, 1.0, 0.0, 359.95, 0.1)
-    elif name == "smallgrid":
-        grid = (1.0, 60.5, 1.0, 0.0, 359.5, 5.0)
-    elif name == "midgrid":
-        grid = (1.0, 60.5, 1.0, 0.0, 359.75, 0.5)
-    elif name == "config1":
-        grid = (0.5, 45.0, 0.5, -90.0, -90.0, 1.0)
-    else:
-        raise SystemExit(f"unknown workload {name}")
+    variant, grid, _, _ = WORKLOADS[name]
     th_deg, ph_deg, _, _ = api.prop_angles(*grid)
-    ph_deg = ph_deg + 0.05 * rank / 8.0 * (name != "config1")       # weak scaling: same grid, rank-specific rotation
-    Pi = 3.141592653589793238462643
-    return grid, th_deg, ph_deg, th_deg * Pi / 180.0, Pi / 2.0 - ph_deg * Pi / 180.0
+    if name not in SHARDED and variant != V2D:
+        ph_deg = ph_deg + 0.05 * rank / 8.0                          # weak scaling: same grid, rank-specific rotation
+    return grid, th_deg, ph_deg, th_deg * PI / 180.0, PI / 2.0 - ph_deg * PI / 180.0
+
+
+def shard_indices(n, rank, world):
+    from geoac_b200 import sharding
+    return sharding.shard_indices(n, rank, world)
+
+
+def setup_tracer(name, device):
+    """Create the context of a workload on `device` with its atmosphere and parameters; returns (tracer, params)."""
+    import geoac_b200 as g
+    from geoac_b200 import synth
+    variant, _, bounces, atmo = WORKLOADS[name]
+    tr = g.Tracer(variant, device)
+    if atmo == "toy":
+        tr.set_atmosphere_1d(*g.load_met_1d(TOY))
+    elif atmo == "c3":
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "c3.met")
+            synth.write_met(path, synth.config3_profile())
+            tr.set_atmosphere_1d(*g.load_met_1d(path, global_taper=True))
+    elif atmo in ("c4", "c4s"):
+        tr.set_atmosphere_3d(*(synth.config4_grid() if atmo == "c4" else synth.config4_grid(50, 50, 300)))
+    elif atmo in ("c5", "c5s"):
+        tr.set_atmosphere_3d(*(synth.config5_grid() if atmo == "c5" else synth.config5_grid(46, 91, 300)))
+    p = tr.params
+    p.bounces, p.calc_amp, p.accum_per_segment = bounces, 1, (1 if variant == V2D else 0)
+    if name == "config3":
+        p.range_limit = 3000.0
+        p.src[0], p.src[1], p.src[2] = 0.0, 30.0 * PI / 180.0, 0.0
+    if variant == VGLOBALRD:
+        p.src[0], p.src[1], p.src[2] = 0.0, 35.0 * PI / 180.0, 0.0
+    tr.params = p
+    return tr, p
 
 
 class ClockSampler(threading.Thread):
@@ -84,62 +145,90 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def cpu_reference_run(workload, target_rays, n_proc):
-    """Time the reference's own CPU implementation (oracle/_ref/ref_3d: the unmodified reference sources + a driver
-    main) or, when it is not built, the C restatement, on every `stride`-th ray of the workload, split over n_proc
-    processes with disjoint ray sets.  Returns dict(rays, steps, seconds, kind, cores, sample)."""
-    from geoac_b200 import abi
-    variant = abi.GEOAC_2D if workload == "config1" else abi.GEOAC_3D
-    grid, th_deg, _, _, _ = workload_angles(workload)
-    total = len(th_deg)
-    import math
+def _sample_stride(total, target_rays, n_proc, fast_axis):
     stride = max(1, total // max(1, target_rays // n_proc))
     stride = max(stride, n_proc) if total > n_proc else 1
-    while stride > 1 and math.gcd(stride, 60) != 1:      # theta is the fast axis (60 values): keep the sample unbiased
+    while stride > 1 and math.gcd(stride, fast_axis) != 1:   # theta is the fast axis: keep the sample unbiased in theta
         stride += 1
+    return stride
+
+
+def cpu_reference_run(workload, target_rays, n_proc):
+    """Time the reference's own CPU implementation on every `stride`-th ray of the workload, split over n_proc processes
+    with disjoint ray sets.  Stratified workloads run oracle/_ref/ref_<variant> (the unmodified reference sources + a
+    driver main; kind "reference"); when it is not built, and for the range-dependent workloads (whose reference input
+    is 40 000+ node files), the C restatement in oracle/ is timed instead (kind "port").
+    Returns dict(rays, steps, seconds, kind, cores, sample)."""
+    from geoac_b200 import abi, synth
+    variant, grid, bounces, atmo = WORKLOADS[workload]
+    _, th_deg, _, _, _ = workload_angles(workload)
+    total = len(th_deg)
+    n_theta = int(round((grid[1] - grid[0]) / grid[2])) + 1
+    stride = _sample_stride(total, target_rays, n_proc, n_theta)
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_" + abi.VARIANT_NAMES[variant])
-    keys = dict(theta_min=grid[0], theta_max=grid[1], theta_step=grid[2], bounces=2)
-    if variant == abi.GEOAC_3D:
+    keys = dict(theta_min=grid[0], theta_max=grid[1], theta_step=grid[2], bounces=bounces)
+    if variant != V2D:
         keys.update(phi_min=grid[3], phi_max=grid[4], phi_step=grid[5], accum_mode=0)
-    if os.path.exists(ref_bin):
+    if workload == "config3":
+        keys.update(lat_src=30, lon_src=0, rng_max=3000)
+    if os.path.exists(ref_bin) and atmo in ("toy", "c3"):
         kind = "reference"
         with tempfile.TemporaryDirectory() as td:
+            prof = TOY
+            if atmo == "c3":
+                prof = os.path.join(td, "c3.met")
+                synth.write_met(prof, synth.config3_profile())
             procs = []
-            t0 = time.perf_counter()
             for i in range(n_proc):
-                # process i takes rays with index % (stride) == i * (stride // n_proc): disjoint, evenly spread
+                # process i takes rays with index % stride == i * (stride // n_proc): disjoint, evenly spread
                 off = (i * (stride // n_proc)) % stride
-                cmd = [ref_bin, os.path.join(td, f"o{i}.bin"), TOY] + [f"{k}={v}" for k, v in keys.items()] + [f"stride={stride}", f"offset={off}"]
+                cmd = [ref_bin, os.path.join(td, f"o{i}.bin"), prof] + [f"{k}={v}" for k, v in keys.items()] + [f"stride={stride}", f"offset={off}"]
                 procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True))
             outs = [p.communicate()[0] for p in procs]
-            secs = time.perf_counter() - t0
         infos = [json.loads(o.strip().splitlines()[-1]) for o in outs]
         rays = sum(i["rays"] for i in infos)
         steps = sum(i["steps"] for i in infos)
-        trace_secs = max(i["t_trace_s"] for i in infos)          # slowest process, excluding profile load
-        secs = trace_secs
+        secs = max(i["t_trace_s"] for i in infos)                # slowest process, excluding profile load
     else:
         kind = "port"
         from multiprocessing import Pool
         idx = np.arange(total)
         shards = [idx[(idx % stride) == ((i * (stride // n_proc)) % stride)] for i in range(n_proc)]
-        t0 = time.perf_counter()
         with Pool(n_proc) as pool:
-            res = pool.starmap(_port_worker, [(workload, variant, s) for s in shards])
-        secs = time.perf_counter() - t0
+            res = pool.starmap(_port_worker, [(workload, s) for s in shards])
+        secs = max(r[2] for r in res)                            # slowest process, excluding atmosphere set-up
         rays = sum(r[0] for r in res)
         steps = sum(r[1] for r in res)
     return {"rays": rays, "steps": steps, "seconds": secs, "kind": kind, "cores": n_proc,
             "sample": f"every {stride}th ray of {workload} ({rays} of {total} rays, {steps} RK4 steps), {n_proc} process(es)"}
 
 
-def _port_worker(workload, variant, idx):
+def _port_worker(workload, idx):
+    from geoac_b200 import synth
     from oracle import pyoracle as po
+    variant, _, bounces, atmo = WORKLOADS[workload]
     _, _, _, th, ph = workload_angles(workload)
-    at = po.atmo1d(False, *po.load_met_1d(TOY))
+    if atmo == "toy":
+        at = po.atmo1d(False, *po.load_met_1d(TOY))
+    elif atmo == "c3":
+        with tempfile.TemporaryDirectory() as td:
+            path = os.path.join(td, "c3.met")
+            synth.write_met(path, synth.config3_profile())
+            at = po.atmo1d(True, *po.load_met_1d(path, global_taper=True))
+    elif atmo in ("c4", "c4s"):
+        at = po.atmo3d(False, *(synth.config4_grid() if atmo == "c4" else synth.config4_grid(50, 50, 300)))
+    else:
+        at = po.atmo3d(True, *(synth.config5_grid() if atmo == "c5" else synth.config5_grid(46, 91, 300)))
     p = po.default_params(variant, at)
+    p.bounces, p.calc_amp, p.accum_per_segment = bounces, 1, (1 if variant == V2D else 0)
+    if workload == "config3":
+        p.range_limit = 3000.0
+        p.src[0], p.src[1], p.src[2] = 0.0, 30.0 * PI / 180.0, 0.0
+    if variant == VGLOBALRD:
+        p.src[0], p.src[1], p.src[2] = 0.0, 35.0 * PI / 180.0, 0.0
+    t0 = time.perf_counter()
     out = po.trace(variant, at, p, th[idx], ph[idx])
-    return len(idx), out["total_steps"]
+    return len(idx), out["total_steps"], time.perf_counter() - t0
 
 
 def run_reference_arm(args):
@@ -147,10 +236,13 @@ def run_reference_arm(args):
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
+    if WORKLOADS[args.workload][3] in ("c4", "c5"):
+        cores = min(cores, 8)                                    # every process holds its own copy of the node tables
     per_step = []
     res = None
+    rays_per_core = 24 if WORKLOADS[args.workload][0] in (V2D, V3D, VGLOBAL) else 1
     for i in range(args.warmup + args.steps):
-        res = cpu_reference_run(args.workload, target_rays=cores * 24, n_proc=cores)
+        res = cpu_reference_run(args.workload, target_rays=cores * rays_per_core, n_proc=cores)
         if i >= args.warmup:
             per_step.append(res)
     secs = sum(r["seconds"] for r in per_step)
@@ -159,26 +251,19 @@ def run_reference_arm(args):
     val = rays / secs
     line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "rk4_steps_per_sec": steps / secs,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic launch-angle grid, ToyAtmo.met profile",
-            "config": {"workload": workload_desc(args.workload), "sample": res["sample"]},
+            "higher_is_better": True, "scaling": "strong" if args.workload in SHARDED else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic launch-angle grid; " + ("ToyAtmo.met profile" if WORKLOADS[args.workload][3] == "toy" else "synthetic G2S atmosphere (SURVEY 8d)"),
+            "config": {"workload": DESCRIPTIONS[args.workload], "sample": res["sample"]},
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
                              "rk4_steps_per_sec": steps / secs},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def workload_desc(name):
-    return {"config2": "BASELINE config 2: GeoAc3D stratified, ToyAtmo.met, theta 1..60 step 1 x azimuth 0..359.9 step 0.1 (216000 rays), bounces=2, CalcAmp on, WriteRays=False",
-            "config1": "BASELINE config 1: GeoAc2D, ToyAtmo.met, theta 0.5..45 step 0.5, azimuth -90 (90 rays), bounces=2",
-            "smallgrid": "reduced grid for debugging: GeoAc3D, theta 1..60 x azimuth 0..355 step 5 (4320 rays)",
-            "midgrid": "reduced grid for ncu captures: GeoAc3D, theta 1..60 x azimuth 0..359.5 step 0.5 (43200 rays)"}[name]
-
-
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    import geoac_b200 as g
     from geoac_b200 import abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -191,14 +276,14 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    variant = abi.GEOAC_2D if args.workload == "config1" else abi.GEOAC_3D
-    grid, th_deg, ph_deg, th, ph = workload_angles(args.workload, rank)
+    variant = WORKLOADS[args.workload][0]
+    _, th_deg, ph_deg, th, ph = workload_angles(args.workload, rank)
+    sharded = args.workload in SHARDED
+    if sharded and world > 1:
+        mine = shard_indices(len(th), rank, world)
+        th, ph = np.ascontiguousarray(th[mine]), np.ascontiguousarray(ph[mine])
     n = len(th)
-    tr = g.Tracer(variant, local)
-    tr.set_atmosphere_1d(*g.load_met_1d(TOY))
-    p = tr.params
-    p.bounces, p.calc_amp, p.accum_per_segment = 2, 1, (1 if variant == abi.GEOAC_2D else 0)
-    tr.params = p
+    tr, p = setup_tracer(args.workload, local)
     n_rec = p.bounces + 1
     n_slots = n * n_rec
 
@@ -240,19 +325,19 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join()
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps        # trace kernel (+4 memsets) per launch
+    kern_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps        # scheduling pass + trace kernel (+4 memsets) per pass
     total_steps, _ = tr.last_stats()                                    # RK4 steps of one pass on this rank
     lane_occ = tr.last_lane_occupancy()
     launches_per_pass = tr.last_kernel_launches()
     arrivals = int((d_status == abi.ST_ARRIVAL).sum().item())
 
-    t = torch.tensor([dev_ms, float(total_steps), float(n)], dtype=torch.float64, device=dev)
+    t = torch.tensor([dev_ms, float(total_steps), float(n), float(arrivals)], dtype=torch.float64, device=dev)
     if world > 1:
         tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms_max, steps_all, rays_all = tmax[0].item(), tsum[1].item(), tsum[2].item()
+        dev_ms_max, steps_all, rays_all, arrivals_all = tmax[0].item(), tsum[1].item(), tsum[2].item(), tsum[3].item()
     else:
-        dev_ms_max, steps_all, rays_all = dev_ms, float(total_steps), float(n)
+        dev_ms_max, steps_all, rays_all, arrivals_all = dev_ms, float(total_steps), float(n), float(arrivals)
     secs = dev_ms_max * 1e-3
     rays_per_s = rays_all * args.steps / secs
     steps_per_s = steps_all * args.steps / secs
@@ -263,10 +348,13 @@ def run_ours(args):
     h_status = torch.empty((n, n_rec), dtype=torch.int32).pin_memory()
     h_nsteps = torch.empty((n, n_rec), dtype=torch.int32).pin_memory()
     out = {"rec": h_rec.numpy(), "status": h_status.numpy(), "n_steps": h_nsteps.numpy()}
-    tr.trace(h_th.numpy(), h_ph.numpy(), out)                           # warm-up (allocates staging)
+    long_run = args.workload in ("config3", "config4", "config5") and not args.e2e_full
+    e2e_k = 1 if long_run else max(1, min(args.steps, 3))
+    tr.reserve(n)                                                       # device staging allocated outside the timed region
+    if not long_run:
+        tr.trace(h_th.numpy(), h_ph.numpy(), out)                       # warm-up pass
     barrier()
     e0 = time.perf_counter()
-    e2e_k = max(1, min(args.steps, 3))
     for _ in range(e2e_k):
         tr.trace(h_th.numpy(), h_ph.numpy(), out)                       # synchronous: returns with results on the host
     barrier()
@@ -280,28 +368,32 @@ def run_ours(args):
 
     if rank == 0:
         peak_tf, peak_ms = tr.measure_fp64_peak()
-        flops_step = ALGO_FLOPS_PER_STEP[args.workload]
+        flops_step = ALGO_FLOPS_PER_STEP[variant]
         achieved_tf = flops_step * total_steps / (kern_ms * 1e-3) / 1e12
+        atmo = WORKLOADS[args.workload][3]
         line = {
             "metric": "rays/sec", "value": rays_per_s, "unit": "rays/s", "rk4_steps_per_sec": steps_per_s,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic launch-angle grid, ToyAtmo.met profile (the reference's shipped fixture)",
-            "config": {"workload": workload_desc(args.workload), "rays_per_gpu": n, "rk4_steps_per_pass_per_gpu": total_steps,
-                       "arrival_records_per_pass": arrivals, "lane_occupancy": round(lane_occ, 4), "l2": "256 MiB buffer written between iterations (L2 flush); "
-                       "the kernel's working set is the 112 KB table in shared memory", "multi_gpu": "replicated grid per rank, azimuth offset by rank"},
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic launch-angle grid; " + ("ToyAtmo.met profile (the reference's shipped fixture)" if atmo == "toy"
+                                                        else "synthetic G2S atmosphere generated as SURVEY 8d specifies"),
+            "config": {"workload": DESCRIPTIONS[args.workload], "rays_per_gpu": n, "rk4_steps_per_pass_per_gpu": total_steps,
+                       "arrival_records_per_pass": int(arrivals_all), "lane_occupancy": round(lane_occ, 4),
+                       "l2": "256 MiB buffer written between iterations (L2 flush)",
+                       "multi_gpu": "one ray list split across ranks in interleaved 4096-ray blocks" if sharded else "replicated grid per rank, azimuth offset by rank"},
             "e2e": {"value": e2e_rays, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "passes": e2e_k},
             "gpu_launches": args.steps * launches_per_pass,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
-                         "traffic": None, "kernel": "geoac::trace_kernel<Eq3D<true>,512,true>", "kernel_ms_per_launch": kern_ms,
+                         "traffic": None, "kernel": KERNEL_NAMES[variant], "kernel_ms_per_launch": kern_ms,
                          "algorithmic_flops_per_rk4_step": flops_step,
                          "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "
                                         "HBM is not the bound: ~0.03 B/step of record traffic"},
             "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_reference_run(args.workload, target_rays=120, n_proc=1)
+            rngdep = variant in (V3DRD, VGLOBALRD)
+            cb = cpu_reference_run(args.workload, target_rays=(8 if rngdep else 120), n_proc=1)
             line["cpu_baseline"] = {"value": cb["rays"] / cb["seconds"], "unit": "rays/s", "cores": 1, "kind": cb["kind"],
                                     "sample": cb["sample"], "rk4_steps_per_sec": cb["steps"] / cb["seconds"]}
         print(json.dumps(line), flush=True)
@@ -316,8 +408,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="config2", choices=["config2", "config1", "smallgrid", "midgrid"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-full", action="store_true", help="warm the end-to-end leg up even on the long workloads")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

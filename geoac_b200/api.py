@@ -46,6 +46,7 @@ def lib():
         L.geoac_set_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
         L.geoac_trace.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip]
         L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.geoac_reserve.argtypes = [C.c_void_p, C.c_int64]
         L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.geoac_load_met_1d.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp]
         L.geoac_load_met_grid.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -62,7 +63,7 @@ def lib():
 EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_device",
-    "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
+    "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
 ]
 
 
@@ -174,6 +175,10 @@ class Tracer:
                                       out["n_steps"].ctypes.data_as(_ip)), "geoac_trace")
         return out
 
+    def reserve(self, n_rays):
+        """Pre-allocate the device staging of trace() for batches of up to n_rays rays."""
+        self._check(lib().geoac_reserve(self._h, n_rays), "geoac_reserve")
+
     def trace_device(self, n, d_theta, d_phi, d_rec, d_status, d_n_steps, stream=0):
         """Device pointers (ints) in/out, enqueued on `stream` (cudaStream_t as int); no synchronisation."""
         self._check(lib().geoac_trace_device(self._h, n, d_theta, d_phi, d_rec, d_status, d_n_steps, stream), "geoac_trace_device")
@@ -188,8 +193,14 @@ class Tracer:
         """Average fraction of a warp's 32 lanes that carried a ray during the last trace."""
         steps, _ = self.last_stats()
         t = C.c_int64(0)
-        self._check(lib().geoac_last_trace_warp_trips(self._h, C.byref(t)), "geoac_last_trace_counters")
+        self._check(lib().geoac_last_trace_counters(self._h, C.byref(t), None), "geoac_last_trace_counters")
         return steps / (32.0 * t.value) if t.value else 0.0
+
+    def last_kernel_launches(self):
+        """Kernels the last trace enqueued (1, or 5 with the longest-ray-first scheduling pass)."""
+        k = C.c_int64(0)
+        self._check(lib().geoac_last_trace_counters(self._h, None, C.byref(k)), "geoac_last_trace_counters")
+        return k.value
 
     def selftest_math(self, n_per_thread=2000):
         """Max relative error of the kernel's rcp / rsqrt / sqrt / exp / exp10 against the CUDA math library."""

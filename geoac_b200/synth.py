@@ -1,0 +1,85 @@
+"""Synthetic G2S atmospheres of BASELINE.json's configs 3-5, exactly as SURVEY.md section 8(d) specifies them (no RNG).
+
+Host-side input generators for bench.py and the scale tests; they produce what the reference's loaders would hand to
+the spline builders (Code/Atmo/G2S_GlobalSpline1D.cpp:113-152, G2S_MultiDimSpline3D.cpp:139-189,
+G2S_GlobalMultiDimSpline3D.cpp:142-199): winds in km/s with the ground taper applied, density in g/cm^3.
+"""
+import numpy as np
+
+R_GAS, G0, P0 = 287.05, 9.8, 101325.0
+
+
+def temperature(z):
+    """Piecewise-linear US-Std-1976 to 91 km, then an exponential thermosphere (574 K at 150 km)."""
+    z = np.asarray(z, dtype=np.float64)
+    zb = [0.0, 11.0, 20.0, 32.0, 47.0, 51.0, 71.0, 84.852, 91.0]
+    lapse = [-6.5, 0.0, 1.0, 2.8, 0.0, -2.8, -2.0, 0.0]
+    T = np.empty_like(z)
+    Tb = 288.15
+    for i in range(len(lapse)):
+        m = (z >= zb[i]) & (z <= zb[i + 1]) if i == 0 else (z > zb[i]) & (z <= zb[i + 1])
+        T[m] = Tb + lapse[i] * (z[m] - zb[i])
+        Tb = Tb + lapse[i] * (zb[i + 1] - zb[i])
+    m = z > 91.0
+    T[m] = Tb + 450.0 * (1.0 - np.exp(-(((z[m] - 91.0) / 42.0) ** 2)))
+    return T
+
+
+def base_profile(z):
+    """z [km] -> T [K], u, v [m/s], rho [g/cm^3], p [mbar] (file units of a `zTuvdp` .met profile)."""
+    z = np.asarray(z, dtype=np.float64)
+    T = temperature(z)
+    u = -60.0 * np.exp(-(((z - 55.0) / 12.0) ** 2)) + 30.0 * np.exp(-(((z - 110.0) / 15.0) ** 2))
+    v = 10.0 * np.exp(-(((z - 15.0) / 5.0) ** 2))
+    p = np.empty_like(z)
+    p[0] = P0
+    for i in range(len(z) - 1):                                    # hydrostatic integration between levels
+        Tbar = 0.5 * (T[i] + T[i + 1])
+        p[i + 1] = p[i] * np.exp(-G0 * (z[i + 1] - z[i]) * 1000.0 / (R_GAS * Tbar))
+    rho = p / (R_GAS * T)
+    return T, u, v, rho / 1000.0, p / 100.0
+
+
+def config3_profile():
+    """Stratified profile of config 3: z = 0 ... 150 km step 0.1 (1501 rows).  Returns the six .met columns."""
+    z = np.round(np.arange(1501) * 0.1, 1)
+    return (z,) + base_profile(z)
+
+
+def write_met(path, cols):
+    np.savetxt(path, np.column_stack(cols), fmt="%.1f %.6f %.6f %.6f %.6e %.6e")
+
+
+def _taper(z, width):
+    return (2.0 / (1.0 + np.exp(-(z - 0.0) / width)) - 1.0) / 1000.0     # m/s -> km/s and ground taper (z_grnd = 0 at load)
+
+
+def config4_grid(nx=200, ny=200, nz=300):
+    """Cartesian range-dependent grid of config 4: x, y = -500 ... 500 km, z = 0 ... (nz-1)/2 km; fields [nx][ny][nz]."""
+    x = np.linspace(-500.0, 500.0, nx)
+    y = np.linspace(-500.0, 500.0, ny)
+    z = np.arange(nz) * 0.5
+    T0, u0, v0, rho0, _ = base_profile(z)
+    X, Y = x[:, None, None], y[None, :, None]
+    tap = _taper(z, 0.05)[None, None, :]
+    T = T0[None, None, :] * (1.0 + 0.02 * np.sin(2 * np.pi * X / 700.0) * np.cos(2 * np.pi * Y / 900.0))
+    u = u0[None, None, :] * (1.0 + 0.2 * np.cos(2 * np.pi * X / 600.0)) * tap * np.ones_like(Y)
+    v = (v0[None, None, :] + 8.0 * np.sin(2 * np.pi * Y / 800.0) * np.exp(-(((z - 50.0) / 20.0) ** 2))[None, None, :]) * tap * np.ones_like(X)
+    rho = np.broadcast_to(rho0[None, None, :], T.shape)
+    return x, y, z, np.ascontiguousarray(T), np.ascontiguousarray(u), np.ascontiguousarray(v), np.ascontiguousarray(rho)
+
+
+def config5_grid(nlat=181, nlon=361, nr=300):
+    """Global range-dependent grid of config 5: lat -90 ... 90, lon -180 ... 180 (radians, as the loader converts them),
+    altitude 0 ... (nr-1)/2 km; fields [nlat][nlon][nr]."""
+    lat = np.radians(np.linspace(-90.0, 90.0, nlat))
+    lon = np.radians(np.linspace(-180.0, 180.0, nlon))
+    z = np.arange(nr) * 0.5
+    T0, u0, v0, rho0, _ = base_profile(z)
+    LA, LO = lat[:, None, None], lon[None, :, None]
+    tap = _taper(z, 0.2)[None, None, :]
+    T = T0[None, None, :] * (1.0 + 0.02 * np.sin(3.0 * LA) * np.cos(2.0 * LO))
+    u = u0[None, None, :] * np.cos(LA) ** 2 * (1.0 + 0.2 * np.cos(4.0 * LO)) * tap
+    v = (v0[None, None, :] + 8.0 * np.sin(5.0 * LO) * np.exp(-(((z - 50.0) / 20.0) ** 2))[None, None, :]) * tap * np.ones_like(LA)
+    rho = np.broadcast_to(rho0[None, None, :], T.shape)
+    return lat, lon, z, np.ascontiguousarray(T), np.ascontiguousarray(u), np.ascontiguousarray(v), np.ascontiguousarray(rho)

@@ -131,6 +131,10 @@ int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const doubl
 int geoac_trace_device(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
                        double* d_rec, int32_t* d_status, int32_t* d_n_steps, void* cuda_stream);
 
+/* Optional: allocate the device staging geoac_trace() needs for batches of up to n_rays rays (with the current
+ * `bounces`) ahead of time, so that the first trace call does not pay for it.  geoac_trace() grows it on demand anyway. */
+int geoac_reserve(geoac_ctx* ctx, int64_t n_rays);
+
 /* Total RK4 steps of the last trace on this ctx (sum of n_steps), and milliseconds the kernel(s) took (CUDA events). */
 int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_ms);
 

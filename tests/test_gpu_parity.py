@@ -105,6 +105,18 @@ def test_longest_ray_first_schedule_is_result_neutral(monkeypatch):
         assert np.array_equal(outs[0]["rec"], outs[1]["rec"])
 
 
+def test_multi_context_sharding_is_bitwise_identical():
+    """the batch split over several contexts (here two contexts on the one GPU of the test box, driven from
+    host threads like a multi-GPU front end) gives bitwise the records of a single-context trace."""
+    from geoac_b200 import sharding
+    kv = {"bounces": 1}
+    _, _, th, ph = g.prop_angles(1, 60.5, 1, 0, 359, 24)
+    one = _tracer_for(abi.GEOAC_3D, kv).trace(th, ph)
+    two = sharding.trace_multi([_tracer_for(abi.GEOAC_3D, kv), _tracer_for(abi.GEOAC_3D, kv)], th, ph, block=64)
+    assert np.array_equal(one["status"], two["status"]) and np.array_equal(one["n_steps"], two["n_steps"])
+    assert np.array_equal(one["rec"], two["rec"])
+
+
 def test_reciprocity_at_scale():
     """Size-independent property at a config-2-like scale slice: in a stratified medium the n-th bounce range of
     the 2-D solver is (n+1) times the first -- checked on 4k rays without any oracle."""
