@@ -215,7 +215,7 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     CK(cudaMemcpy(ctx->d_ax + n0 + n1, z.data(), nz * sizeof(double), cudaMemcpyHostToDevice));
     Grid3D& g = ctx->grid;
     g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + n0; g.axz = ctx->d_ax + n0 + n1;
-    g.n0 = n0; g.n1 = n1; g.nz = nz;
+    g.n0 = n0; g.n1 = n1; g.nz = nz; g.scratch = nullptr;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
     // GeoAc_SetPropRegion: G2S_MultiDimSpline3D.cpp:22-33 / G2S_GlobalMultiDimSpline3D.cpp:22-33
     ctx->prm.vert_limit = g.zmax;
@@ -295,27 +295,30 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         }
     }
     a.prev = ctx->d_prev;
-    a.order = nullptr;
+    a.order = nullptr; a.n_claims = a.n_rays;
     ctx->last_launches = 0;
     // longest-predicted-ray-first claim order, when a lane will process more than one ray (see trace_kernel.cuh)
     // GEOAC_B200_LPT: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
     const char* lpt_env = std::getenv("GEOAC_B200_LPT");
     const int lpt_mode = lpt_env ? std::atoi(lpt_env) : 1;
     if ((lpt_mode == 2 || (lpt_mode == 1 && a.n_rays > (int64_t)grid * BLOCK)) && a.n_rays < ((int64_t)1 << 32)) {
-        if (a.n_rays > ctx->cap_order) {
+        constexpr int group = PacketMode<EQ>::value ? 32 : 1;
+        const int64_t n_entries = ((a.n_rays + group - 1) / group) * group;
+        if (n_entries > ctx->cap_order) {
             cudaFree(ctx->d_cost); cudaFree(ctx->d_order); ctx->d_cost = ctx->d_order = nullptr; ctx->cap_order = 0;
-            CK(cudaMalloc(&ctx->d_cost, sizeof(uint32_t) * a.n_rays)); CK(cudaMalloc(&ctx->d_order, sizeof(uint32_t) * a.n_rays));
-            ctx->cap_order = a.n_rays;
+            CK(cudaMalloc(&ctx->d_cost, sizeof(uint32_t) * n_entries)); CK(cudaMalloc(&ctx->d_order, sizeof(uint32_t) * n_entries));
+            ctx->cap_order = n_entries;
         }
         if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 1)));
         CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 1), st));
         uint32_t* cmax = ctx->d_hist + kCostBuckets;
         const int sblocks = (int)std::min<int64_t>((a.n_rays + 127) / 128, (int64_t)ctx->sm_count * 16);
         scout_kernel<typename EQ::Scout><<<sblocks, 128, 0, st>>>(a, ctx->d_cost, cmax);
-        order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, cmax, ctx->d_hist);
+        order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist);
         order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
-        order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, cmax, ctx->d_hist, ctx->d_order);
+        order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
         CK(cudaGetLastError());
+        a.n_claims = n_entries;
         a.order = ctx->d_order;
         ctx->last_launches += 4;
     }

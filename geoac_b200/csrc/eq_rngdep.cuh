@@ -67,7 +67,7 @@ struct Eq3DRD {
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, 3DRngDep.cpp:218-393
     GEOAC_HD static void rhs(const LaunchConsts&, const Grid3D& G, const RayC&, const double* p, double* f, Cur3& cur) {
-        double S[3][10];
+        double (&S)[3][10] = *reinterpret_cast<double (*)[3][10]>(G.scratch);      // per-thread block (shared memory on the device)
         ms_sample_tuv<false, AMP>(G, p[0], p[1], p[2], cur, S);
         const double* Tt = S[0]; const double* U = S[1]; const double* V = S[2];
         const RdSound s = rd_sound(Tt[0]);
@@ -245,7 +245,7 @@ struct EqGlobalRD {
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, GlobalRngDep.cpp:226-460
     GEOAC_HD static void rhs(const LaunchConsts&, const Grid3D& G, const RayC&, const double* p, double* f, Cur3& cur) {
-        double S[3][10];
+        double (&S)[3][10] = *reinterpret_cast<double (*)[3][10]>(G.scratch);      // per-thread block (shared memory on the device)
         ms_sample_tuv<true, AMP>(G, p[1], p[2], p[0], cur, S);
         const double* Tt = S[0]; const double* U = S[1]; const double* V = S[2];
         const int D1[3] = { 3, 1, 2 };                                   // d/dr, d/dlat, d/dlon

@@ -30,7 +30,9 @@ struct Grid3D {
     const double* ax0; const double* ax1; const double* axz;
     int n0, n1, nz;
     double amin, amax, bmin, bmax, zmin, zmax;
+    double* scratch;        // per-thread sampler output block (MS_SCRATCH doubles): shared memory on the device
 };
+constexpr int MS_SCRATCH = 30;
 
 struct Cur3 { int ka, kb, kz; };
 
@@ -93,13 +95,34 @@ GEOAC_HD void ms_weights(MsW& w, const MsAxis& A, double slope_scale) {
 GEOAC_HD double ms_HX(const MsW& w, double Q0, double Q1, double Q2, double Q3)  { return w.h00 * Q1 + w.h01 * Q2 + w.P * (Q2 - Q0) + w.Q * (Q3 - Q1); }
 GEOAC_HD double ms_HXd(const MsW& w, double Q0, double Q1, double Q2, double Q3) { return w.e00 * Q1 + w.e01 * Q2 + w.Pd * (Q2 - Q0) + w.Qd * (Q3 - Q1); }
 
-// vertical position shared by every column of a query
-struct MsZ { int kz; double X, omX, XomX, om2X, h, invh; };
+// vertical position shared by every column of a query.  The vertical Hermite spline is LINEAR in a column's four data
+// (f_k, f_k+1, s_k, s_k+1), so its value / first / second derivative at this position are dot products with coefficient
+// triples that depend on the position only -- computed once per query, 3 FMAs per column and quantity instead of ~9:
+//     V   = f_k + cV1 (f_k+1 - f_k) + cVa s_k + cVb s_k+1          (same polynomial as G2S_MultiDimSpline3D.cpp:476-562)
+//     V'  =       cD1 (f_k+1 - f_k) + cDa s_k + cDb s_k+1
+//     V'' =       cE1 (f_k+1 - f_k) + cEa s_k + cEb s_k+1
+struct MsZ { int kz; double cV1, cVa, cVb, cD1, cDa, cDb, cE1, cEa, cEb, cG1; };
+template <bool GLOBAL>
 GEOAC_HD void ms_zpos(MsZ& Z, const Grid3D& g, double z, int kz) {
     const double z0 = g.axz[kz];
-    Z.kz = kz; Z.h = g.axz[kz + 1] - z0; Z.invh = 1.0 / Z.h;
-    Z.X = (z - z0) / Z.h; Z.omX = 1.0 - Z.X; Z.XomX = Z.X * Z.omX; Z.om2X = 1.0 - 2.0 * Z.X;
+    const double h = g.axz[kz + 1] - z0, invh = 1.0 / h;
+    const double X = (z - z0) * invh, omX = 1.0 - X, XomX = X * omX, om2X = 1.0 - 2.0 * X;
+    Z.kz = kz;
+    Z.cV1 = X - XomX * om2X;            Z.cVa = XomX * omX * h;           Z.cVb = -(XomX * X * h);
+    Z.cD1 = (1.0 - om2X * om2X + 2.0 * XomX) * invh;  Z.cDa = om2X * omX - XomX;  Z.cDb = -(om2X * X + XomX);
+    const double inv2 = 2.0 * invh * invh;
+    Z.cE1 = 3.0 * om2X * inv2;          Z.cEa = (3.0 * X - 2.0) * h * inv2;  Z.cEb = (3.0 * X - 1.0) * h * inv2;
+    // vertical derivative of a finite-difference column: the Global file drops the leading (d1 - d0)/h term (App. A-9)
+    Z.cG1 = GLOBAL ? Z.cD1 - invh : Z.cD1;
 }
+GEOAC_HD double ms_v(const MsZ& Z, double f0, double df, double s0, double s1)  { return fma(Z.cV1, df, fma(Z.cVa, s0, fma(Z.cVb, s1, f0))); }
+GEOAC_HD double ms_vz(const MsZ& Z, double df, double s0, double s1)            { return fma(Z.cD1, df, fma(Z.cDa, s0, Z.cDb * s1)); }
+GEOAC_HD double ms_vzz(const MsZ& Z, double df, double s0, double s1)           { return fma(Z.cE1, df, fma(Z.cEa, s0, Z.cEb * s1)); }
+GEOAC_HD double ms_gz(const MsZ& Z, double dd, double s0, double s1)            { return fma(Z.cG1, dd, fma(Z.cDa, s0, Z.cDb * s1)); }
+
+// the four data of one node and level for one field: f, df/dz slope, d(df/dax0)/dz slope, d(df/dax1)/dz slope (32 aligned bytes)
+struct Node4 { double f, s, sa, sb; };
+GEOAC_HD Node4 ms_ld4(const double* p) { const Pair a = ld_pair(p), b = ld_pair(p + 2); Node4 n; n.f = a.a; n.s = a.b; n.sa = b.a; n.sb = b.b; return n; }
 
 // ---------------------------------------------------------------------------------------------------------------
 // Eval_Spline_AllOrder1 / AllOrder2 for T, u and v in one pass.  out[field][..] in GRID-axis order:
@@ -114,14 +137,13 @@ GEOAC_HD void ms_sample_tuv(const Grid3D& g, double a_in, double b_in, double z_
     MsAxis A, B; MsZ Z;
     ms_axis(A, g.ax0, g.n0, cur.ka, a, (unsigned)(g.n1 * g.nz * MS_STRIDE));
     ms_axis(B, g.ax1, g.n1, cur.kb, b, (unsigned)(g.nz * MS_STRIDE));
-    ms_zpos(Z, g, z, cur.kz);
+    ms_zpos<GLOBAL>(Z, g, z, cur.kz);
     MsW wa, wb;
     ms_weights(wa, A, A.d);
     ms_weights(wb, B, B.d);
     // d2f/dz2 block: the Cartesian file scales the ax1 slope data by dx (App. A-8); Global uses dp
     const double qs = GLOBAL ? 1.0 : A.d / B.d;
     const unsigned kofs = (unsigned)cur.kz * MS_STRIDE;
-    const double inv2 = 2.0 * Z.invh * Z.invh;
 
 #pragma unroll 1
     for (int F = 0; F < 3; F++) {
@@ -135,26 +157,24 @@ GEOAC_HD void ms_sample_tuv(const Grid3D& g, double a_in, double b_in, double z_
 #pragma unroll
             for (int ia = 0; ia < 4; ia++) {
                 const double* n0p = base + (A.off[ia] + B.off[jb]);
-                const double f0 = n0p[0], s0 = n0p[1], sa0 = n0p[2], sb0 = n0p[3];
-                const double f1 = n0p[MS_STRIDE], s1 = n0p[MS_STRIDE + 1], sa1 = n0p[MS_STRIDE + 2], sb1 = n0p[MS_STRIDE + 3];
-                const double df = f1 - f0;
-                const double Ac = s0 * Z.h - df, Bc = df - s1 * Z.h, Pc = Ac * Z.omX + Bc * Z.X;
-                V[ia] = Z.omX * f0 + Z.X * f1 + Z.XomX * Pc;
-                Vz[ia] = (df + Z.om2X * Pc + Z.XomX * (Bc - Ac)) * Z.invh;
-                if (ORDER2) Vzz[ia] = (Bc - 2.0 * Ac + 3.0 * (Ac - Bc) * Z.X) * inv2;
+                const Node4 lo = ms_ld4(n0p), hi = ms_ld4(n0p + MS_STRIDE);
+                const double df = hi.f - lo.f;
+                V[ia] = ms_v(Z, lo.f, df, lo.s, hi.s);
+                Vz[ia] = ms_vz(Z, df, lo.s, hi.s);
+                if (ORDER2) Vzz[ia] = ms_vzz(Z, df, lo.s, hi.s);
                 {   // column of the ax0 finite difference (Eval_Vert_Spline_dfdx / ddfdxdz)
                     const double* up = base + (A.offu[ia] + B.off[jb]); const double* dn = base + (A.offd[ia] + B.off[jb]);
                     const double d0 = (up[0] - dn[0]) * A.rg[ia], d1 = (up[MS_STRIDE] - dn[MS_STRIDE]) * A.rg[ia];
-                    const double dd = d1 - d0, A2 = sa0 * Z.h - dd, B2 = dd - sa1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
-                    Ga[ia] = Z.omX * d0 + Z.X * d1 + Z.XomX * P2;
-                    Gaz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;      // Global: App. A-9
+                    const double dd = d1 - d0;
+                    Ga[ia] = ms_v(Z, d0, dd, lo.sa, hi.sa);
+                    Gaz[ia] = ms_gz(Z, dd, lo.sa, hi.sa);
                 }
                 {   // column of the ax1 finite difference
                     const double* up = base + (A.off[ia] + B.offu[jb]); const double* dn = base + (A.off[ia] + B.offd[jb]);
                     const double d0 = (up[0] - dn[0]) * B.rg[jb], d1 = (up[MS_STRIDE] - dn[MS_STRIDE]) * B.rg[jb];
-                    const double dd = d1 - d0, A2 = sb0 * Z.h - dd, B2 = dd - sb1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
-                    Gb[ia] = Z.omX * d0 + Z.X * d1 + Z.XomX * P2;
-                    Gbz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;
+                    const double dd = d1 - d0;
+                    Gb[ia] = ms_v(Z, d0, dd, lo.sb, hi.sb);
+                    Gbz[ia] = ms_gz(Z, dd, lo.sb, hi.sb);
                 }
             }
             // ax1 weights of this row (slot jb): tensor weight, its derivative, FD-of-values weight, FD-of-slopes weight
@@ -221,7 +241,7 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
     MsAxis A, B; MsZ Z;
     ms_axis(A, g.ax0, g.n0, cur.ka, a, (unsigned)(g.n1 * g.nz * MS_STRIDE));
     ms_axis(B, g.ax1, g.n1, cur.kb, b, (unsigned)(g.nz * MS_STRIDE));
-    ms_zpos(Z, g, z, cur.kz);
+    ms_zpos<GLOBAL>(Z, g, z, cur.kz);
     MsW wa, wb;
     ms_weights(wa, A, A.d);
     ms_weights(wb, B, GLOBAL ? B.d : A.d);              // the quirk: ax1 slope data times dx
@@ -241,24 +261,21 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
             for (int ia = 0; ia < 4; ia++) {
                 const unsigned o = (A.off[ia] + B.off[jb]) / shr;
                 const double* n0p = base + ko + o;
-                const double f0 = n0p[0], s0 = n0p[1], f1 = n0p[lvl], s1 = n0p[lvl + 1];
-                const double df = f1 - f0;
-                const double Ac = s0 * Z.h - df, Bc = df - s1 * Z.h, Pc = Ac * Z.omX + Bc * Z.X;
-                V[ia] = Z.omX * f0 + Z.X * f1 + Z.XomX * Pc;
+                const Pair lo = ld_pair(n0p), hi = ld_pair(n0p + lvl);            // (f, slope) at both levels
+                const double df = hi.a - lo.a;
+                V[ia] = ms_v(Z, lo.a, df, lo.b, hi.b);
                 if (WITH_DZ && !is_rho) {
-                    Vz[ia] = (df + Z.om2X * Pc + Z.XomX * (Bc - Ac)) * Z.invh;
-                    const double sa0 = n0p[2], sb0 = n0p[3], sa1 = n0p[lvl + 2], sb1 = n0p[lvl + 3];
+                    Vz[ia] = ms_vz(Z, df, lo.b, hi.b);
+                    const Pair slo = ld_pair(n0p + 2), shi = ld_pair(n0p + lvl + 2);  // (sa, sb) at both levels
                     {
                         const double* up = base + ko + (A.offu[ia] + B.off[jb]); const double* dn = base + ko + (A.offd[ia] + B.off[jb]);
                         const double d0 = (up[0] - dn[0]) * A.rg[ia], d1 = (up[lvl] - dn[lvl]) * A.rg[ia];
-                        const double dd = d1 - d0, A2 = sa0 * Z.h - dd, B2 = dd - sa1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
-                        Gaz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;
+                        Gaz[ia] = ms_gz(Z, d1 - d0, slo.a, shi.a);
                     }
                     {
                         const double* up = base + ko + (A.off[ia] + B.offu[jb]); const double* dn = base + ko + (A.off[ia] + B.offd[jb]);
                         const double d0 = (up[0] - dn[0]) * B.rg[jb], d1 = (up[lvl] - dn[lvl]) * B.rg[jb];
-                        const double dd = d1 - d0, A2 = sb0 * Z.h - dd, B2 = dd - sb1 * Z.h, P2 = A2 * Z.omX + B2 * Z.X;
-                        Gbz[ia] = ((GLOBAL ? 0.0 : dd) + Z.om2X * P2 + Z.XomX * (B2 - A2)) * Z.invh;
+                        Gbz[ia] = ms_gz(Z, d1 - d0, slo.b, shi.b);
                     }
                 }
             }

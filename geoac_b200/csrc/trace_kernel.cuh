@@ -39,7 +39,8 @@ struct TraceArgs {
     unsigned long long* counter;      // next unclaimed ray
     unsigned long long* total_steps;  // RK4 steps taken (all rays)
     unsigned long long* warp_trips;   // trips round the step loop, summed over warps (lane occupancy = steps / (32 trips))
-    const uint32_t* order;            // claim order (longest-predicted ray first) or nullptr = natural order
+    const uint32_t* order;            // claim order (longest-predicted first) or nullptr = natural order; 0xffffffff = empty slot
+    int64_t n_claims;                 // entries of `order` (a multiple of 32 in packet mode), or n_rays
     double* prev;                     // y_{k-1} scratch: [NEQ][grid * block] doubles (variants with a quadratic intercept)
 };
 
@@ -96,6 +97,9 @@ struct LaneI {
     int64_t ray;
 };
 
+// packet scheduling (see the refill step of trace_kernel): the range-dependent sets, whose node tables are read through L1
+template <class EQ> struct PacketMode { static constexpr bool value = std::is_same<typename EQ::Atmo, Grid3D>::value; };
+
 // does the reflection need y_{k-2}?  (quadratic intercept: 2D, 3D, 3D.RngDep; the Global variants fit a line, App. A-7)
 template <class EQ> struct NeedsPrev { static constexpr bool value = !(EQ::VARIANT == GEOAC_GLOBAL || EQ::VARIANT == GEOAC_GLOBAL_RNGDEP); };
 
@@ -106,14 +110,23 @@ GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, cons
     EQ::init(L, T, theta, phi, d.rc, d.y, n.cur);
 }
 
-// prev[i * pstride] holds y_{k-1}[i] (only maintained when NeedsPrev); returns false when the ray has ended
+// Range-dependent sets keep the RK4 accumulator and the stage input in the lane's shared-memory record as well (their
+// right-hand side needs the registers for the 4x4-node sampler); the stratified sets keep them in registers.
+template <class EQ> struct WorkInMem { static constexpr bool value = std::is_same<typename EQ::Atmo, Grid3D>::value; };
+
+// prev[i * pstride] holds y_{k-1}[i] (only maintained when NeedsPrev); work = 2 NEQ doubles (WorkInMem) or nullptr;
+// returns false when the ray has ended
 template <class EQ>
-GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, double* prev, int64_t pstride, const RecOut& o) {
+GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, double* prev, int64_t pstride,
+                           const RecOut& o, double* work) {
     constexpr int NEQ = EQ::NEQ;
+    constexpr bool MEM = WorkInMem<EQ>::value;
     double* const y = d.y;
     d.zmax = fmax(d.zmax, EQ::altitude(y));                     // running turning height over m < k (App. A-3)
     const double ds = EQ::step_size(L, y);
-    double acc[NEQ], p[NEQ], f[NEQ];
+    double acc_r[MEM ? 1 : NEQ], p_r[MEM ? 1 : NEQ], f[NEQ];
+    double* const acc = MEM ? work : acc_r;
+    double* const p = MEM ? work + NEQ : p_r;
 #pragma unroll
     for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = acc[i]; }
 #pragma unroll 1
@@ -209,7 +222,12 @@ __device__ __forceinline__ void tma_stage_table(double* dst, const double* src, 
 }
 
 // odd number of doubles per lane record: conflict-free 64-bit shared-memory accesses with one record per thread
-template <class EQ> struct LaneLayout { static constexpr int STRIDE = (int)((sizeof(LaneD<EQ>) / sizeof(double)) | 1); };
+// layout of a record: [LaneD][WorkInMem: acc (NEQ), stage input (NEQ), sampler outputs (MS_SCRATCH)]
+template <class EQ> struct LaneLayout {
+    static constexpr int WORK = (int)(sizeof(LaneD<EQ>) / sizeof(double));
+    static constexpr int EXTRA = WorkInMem<EQ>::value ? 2 * EQ::NEQ + MS_SCRATCH : 0;
+    static constexpr int STRIDE = (WORK + EXTRA) | 1;
+};
 
 template <class EQ, int BLOCK, bool TABLE_IN_SMEM>
 __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__ TraceArgs a) {
@@ -224,8 +242,10 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
     for (int i = threadIdx.x; i < (int)(sizeof(LaunchConsts) / 8); i += BLOCK)
         reinterpret_cast<double*>(Ls)[i] = reinterpret_cast<const double*>(a.consts)[i];
     typename EQ::Atmo T;
+    double* const work = lanes + (size_t)threadIdx.x * LaneLayout<EQ>::STRIDE + LaneLayout<EQ>::WORK;
     if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) {
         T = a.grid;
+        T.scratch = work + 2 * NEQ;
     } else {
         T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
         if (TABLE_IN_SMEM) {
@@ -251,7 +271,10 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
 
     while (true) {
         // ---------------- refill idle lanes (warp-aggregated claim) ----------------
-        const bool want = !have_ray && !exhausted;
+        // PACKET sets (range dependent): a warp takes 32 rays with neighbouring launch angles at once and refills only
+        // when all of them have ended, so its lanes walk through the same few grid cells and share their node data in L1.
+        const bool busy = PacketMode<EQ>::value && __any_sync(0xffffffffu, have_ray);
+        const bool want = !have_ray && !exhausted && !busy;
         const unsigned wmask = __ballot_sync(0xffffffffu, want);
         if (wmask) {
             unsigned long long base = 0;
@@ -260,9 +283,9 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             base = __shfl_sync(0xffffffffu, base, leader);
             if (want) {
                 const int64_t idx = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
-                if (idx < a.n_rays) {
+                if (idx < a.n_claims) {
                     const int64_t r = a.order ? (int64_t)a.order[idx] : idx;
-                    lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]); have_ray = true;
+                    if (r < a.n_rays) { lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]); have_ray = true; }
                 }
                 else exhausted = true;
             }
@@ -270,7 +293,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
         if (!__any_sync(0xffffffffu, have_ray)) break;
         my_trips++;
         if (have_ray) {
-            have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o);
+            have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o, work);
             my_steps++;
         }
     }
@@ -294,7 +317,8 @@ __global__ void __launch_bounds__(128) scout_kernel(const __grid_constant__ Trac
     constexpr int NEQ = EQ::NEQ;
     const LaunchConsts& L = *a.consts;
     typename EQ::Atmo T;
-    if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) { T = a.grid; }
+    double sbuf[std::is_same<typename EQ::Atmo, Grid3D>::value ? MS_SCRATCH : 1];
+    if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) { T = a.grid; T.scratch = sbuf; }
     else { T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.base = a.table; }
     uint32_t worst = 0;
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_rays; r += (int64_t)gridDim.x * blockDim.x) {
@@ -337,17 +361,25 @@ __global__ void __launch_bounds__(128) scout_kernel(const __grid_constant__ Trac
     if ((threadIdx.x & 31) == 0 && worst) atomicMax(cost_max, worst);
 }
 
-// counting sort by predicted cost, descending: hist[b] of bucket(cost) -> start offsets -> scatter
+// counting sort by predicted cost, descending: hist[b] of bucket(cost) -> start offsets -> scatter.  The sorted items are
+// GROUPS of `group` consecutive rays (1, or 32 in packet mode: a packet's cost is that of its longest ray); `order` gets
+// n_groups * group entries, 0xffffffff where the last group runs past the batch.
 __device__ __forceinline__ int cost_bucket(uint32_t c, uint32_t cmax) {
     return (kCostBuckets - 1) - (int)(((uint64_t)c * (kCostBuckets - 1)) / (cmax ? cmax : 1u));      // longest -> bucket 0
 }
-__global__ void order_hist_kernel(const uint32_t* cost, int64_t n, const uint32_t* cost_max, uint32_t* hist) {
+__device__ __forceinline__ uint32_t group_cost(const uint32_t* cost, int64_t n, int64_t g, int group) {
+    uint32_t c = 0;
+    for (int l = 0; l < group; l++) { const int64_t r = g * group + l; if (r < n) c = max(c, cost[r]); }
+    return c;
+}
+__global__ void order_hist_kernel(const uint32_t* cost, int64_t n, int group, const uint32_t* cost_max, uint32_t* hist) {
     __shared__ uint32_t h[kCostBuckets];
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
     __syncthreads();
     const uint32_t cmax = *cost_max;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[cost_bucket(cost[r], cmax)], 1u);
+    const int64_t ng = (n + group - 1) / group;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&h[cost_bucket(group_cost(cost, n, g, group), cmax)], 1u);
     __syncthreads();
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
 }
@@ -364,10 +396,16 @@ __global__ void order_scan_kernel(uint32_t* hist) {          // one block of kCo
     }
     hist[t] = h[t] - hist[t];
 }
-__global__ void order_scatter_kernel(const uint32_t* cost, int64_t n, const uint32_t* cost_max, uint32_t* offs, uint32_t* order) {
+__global__ void order_scatter_kernel(const uint32_t* cost, int64_t n, int group, const uint32_t* cost_max, uint32_t* offs, uint32_t* order) {
     const uint32_t cmax = *cost_max;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x)
-        order[atomicAdd(&offs[cost_bucket(cost[r], cmax)], 1u)] = (uint32_t)r;
+    const int64_t ng = (n + group - 1) / group;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t pos = atomicAdd(&offs[cost_bucket(group_cost(cost, n, g, group), cmax)], 1u);
+        for (int l = 0; l < group; l++) {
+            const int64_t r = g * group + l;
+            order[(int64_t)pos * group + l] = (r < n) ? (uint32_t)r : 0xffffffffu;
+        }
+    }
 }
 
 #endif  // __CUDACC__

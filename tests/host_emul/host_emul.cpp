@@ -21,11 +21,11 @@ using namespace geoac;
 template <class EQ>
 static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const double* th, const double* ph, RecOut o) {
     long steps = 0;
-    std::vector<double> prev(EQ::NEQ, 0.0);
+    std::vector<double> prev(EQ::NEQ, 0.0), work(2 * EQ::NEQ, 0.0);
     for (long i = 0; i < n; i++) {
         LaneD<EQ> ld; LaneI<EQ> li;
         lane_start<EQ>(ld, li, L, T, i, th[i], ph[i]);
-        while (lane_advance<EQ>(ld, li, L, T, prev.data(), 1, o)) steps++;
+        while (lane_advance<EQ>(ld, li, L, T, prev.data(), 1, o, work.data())) steps++;
         steps++;
     }
     return steps;
@@ -68,6 +68,7 @@ extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1
     build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, Tf, uf, vf, rhof, z, tuv, rh);
     Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = ax0; g.ax1 = ax1; g.axz = z.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
+    static thread_local double scratch[MS_SCRATCH]; g.scratch = scratch;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
     L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
     L.z_grnd = p->z_grnd; L.tweak_abs = p->tweak_abs; L.freq = p->freq;
