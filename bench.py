@@ -282,8 +282,13 @@ def run_ours(args):
     if sharded and world > 1:
         mine = shard_indices(len(th), rank, world)
         th, ph = np.ascontiguousarray(th[mine]), np.ascontiguousarray(ph[mine])
+    if args.rays_cap > 0:
+        th, ph = np.ascontiguousarray(th[: args.rays_cap]), np.ascontiguousarray(ph[: args.rays_cap])
     n = len(th)
     tr, p = setup_tracer(args.workload, local)
+    if args.bounces >= 0:
+        p.bounces = args.bounces
+        tr.params = p
     n_rec = p.bounces + 1
     n_slots = n * n_rec
 
@@ -411,6 +416,8 @@ def main():
     ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-full", action="store_true", help="warm the end-to-end leg up even on the long workloads")
+    ap.add_argument("--rays-cap", type=int, default=0, help="profiling aid: keep only the first N rays of the workload")
+    ap.add_argument("--bounces", type=int, default=-1, help="profiling aid: override the workload's bounce count")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -199,7 +199,7 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     for (int i = 1; i < n1; i++) if (!(ax1[i] > ax1[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "axis 1 must be strictly increasing");
     for (int i = 1; i < nz; i++) if (!(axz[i] > axz[i - 1])) return fail(ctx, GEOAC_ERR_BAD_ARG, "altitudes must be strictly increasing");
     const size_t nodes = (size_t)n0 * n1 * nz;
-    if (nodes * MS_STRIDE >= (size_t)1 << 32) return fail(ctx, GEOAC_ERR_TOO_LARGE, "grid exceeds 2^32/12 nodes (32-bit element offsets in the kernel)");
+    if (nodes * MS_STRIDE >= (size_t)1 << 32) return fail(ctx, GEOAC_ERR_TOO_LARGE, "grid exceeds 2^32/18 nodes (32-bit element offsets in the kernel)");
     cudaSetDevice(ctx->device);
     const bool glob = ctx->variant == GEOAC_GLOBAL_RNGDEP;
     std::vector<double> z, tuv, rh;

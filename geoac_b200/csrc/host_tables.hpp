@@ -35,7 +35,8 @@ inline void column_slopes(const double* z, int n, const double* vals, int vstrid
 }
 
 
-// Interleaved device layout (mspline.cuh): tuv[node][level][field]{f, slope, d/dax0 slope, d/dax1 slope}, rho[node][level]{f, slope}.
+// Interleaved device layout (mspline.cuh): tuv[node][level][field]{f, slope, d/dax0 slope, d/dax1 slope, df/dax0, df/dax1},
+// rho[node][level]{f, slope}.
 // z receives the vertical coordinate as the kernel sees it (altitude, or r = altitude + r_earth for the Global variant).
 inline void build_grid_tables(bool glob, int n0, int n1, int nz, const double* ax0, const double* ax1, const double* axz,
                               const double* T, const double* u, const double* v, const double* rho,
@@ -51,7 +52,7 @@ inline void build_grid_tables(bool glob, int n0, int n1, int nz, const double* a
         for (int i = 0; i < n0; i++) for (int j = 0; j < n1; j++) {
             const size_t col = ((size_t)i * n1 + j) * nz;
             const int iu = std::min(i + 1, n0 - 1), id = std::max(i - 1, 0), ju = std::min(j + 1, n1 - 1), jd = std::max(j - 1, 0);
-            double* o = (F < 3) ? &tuv[col * MS_STRIDE + 4 * F] : &rh[col * 2];
+            double* o = (F < 3) ? &tuv[col * MS_STRIDE + MS_FIELD * F] : &rh[col * 2];
             const int os = (F < 3) ? MS_STRIDE : 2;
             for (int k = 0; k < nz; k++) o[(size_t)k * os] = f[col + k];
             column_slopes(z.data(), nz, f + col, 1, o + 1, os, false, nc, nd);
@@ -62,6 +63,7 @@ inline void build_grid_tables(bool glob, int n0, int n1, int nz, const double* a
                 }
                 column_slopes(z.data(), nz, da.data(), 1, o + 2, os, glob, nc, nd);
                 column_slopes(z.data(), nz, db.data(), 1, o + 3, os, glob, nc, nd);
+                for (int k = 0; k < nz; k++) { o[(size_t)k * os + 4] = da[k]; o[(size_t)k * os + 5] = db[k]; }
             }
         }
     }

@@ -16,9 +16,13 @@
 // leading term, and Global second derivatives are not divided by the cell size.
 //
 // Node data layout in HBM (read through L1/L2; a ray stays in one cell for tens of steps):
-//     tuv[((i0*n1 + i1)*nz + k)*12 + 4*field + {0: f, 1: df/dz slope, 2: d(df/dax0)/dz slope, 3: d(df/dax1)/dz slope}]
+//     tuv[((i0*n1 + i1)*nz + k)*18 + 6*field + {0: f, 1: df/dz slope, 2: d(df/dax0)/dz slope, 3: d(df/dax1)/dz slope,
+//                                              4: df/dax0, 5: df/dax1 (centred node differences, one-sided at the rim)}]
 //     rho[((i0*n1 + i1)*nz + k)*2  + {0: f, 1: slope}]
-// so the two levels a column needs are 2 x 96 contiguous bytes for all three fields.
+// The node differences are what the reference's Eval_Vert_Spline_dfdx / dfdy recompute from the neighbouring columns on
+// every query (G2S_MultiDimSpline3D.cpp:476-562); storing them with the node makes a column self-contained: three
+// aligned 16-byte loads per field and level, no neighbour look-ups, and the two levels a column needs are 2 x 144
+// contiguous bytes for all three fields.
 #pragma once
 #include "core.cuh"
 
@@ -36,7 +40,8 @@ constexpr int MS_SCRATCH = 30;
 
 struct Cur3 { int ka, kb, kz; };
 
-constexpr int MS_STRIDE = 12;
+constexpr int MS_STRIDE = 18;      // doubles per node and level in `tuv`
+constexpr int MS_FIELD = 6;        // doubles per field inside a node record
 
 // Find_Segment from a cold cursor (both reference files): alternate a search from the bottom and from the top, so a point
 // exactly on knot m lands in cell m-1 in the lower half of the axis and in cell m in the upper half.
@@ -56,21 +61,18 @@ GEOAC_HD int ms_find_warm(const double* x, int n, double xq, int k) {
 }
 
 struct MsAxis {
-    unsigned off[4], offu[4], offd[4];   // element offsets of the 4 slot nodes (k-1, k, k+1, k+2 clamped) and of their FD neighbours
-    double rg[4];                        // 1 / (x[up] - x[dn]) of the finite difference centred on each slot node
+    unsigned off[4];                     // element offsets of the 4 slot nodes (k-1, k, k+1, k+2 clamped)
+    double r0, r1;                       // 1 / (x[up] - x[dn]) of the finite differences centred on nodes k and k+1
     double d, t;                         // cell width, scaled coordinate
 };
 
 GEOAC_HD void ms_axis(MsAxis& A, const double* x, int n, int k, double xq, unsigned stride) {
-    const int i[4] = { (k - 1 < 0) ? 0 : k - 1, k, k + 1, (k + 2 > n - 1) ? n - 1 : k + 2 };
-#pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int iu = (i[a] + 1 > n - 1) ? n - 1 : i[a] + 1, id = (i[a] - 1 < 0) ? 0 : i[a] - 1;
-        A.off[a] = (unsigned)i[a] * stride; A.offu[a] = (unsigned)iu * stride; A.offd[a] = (unsigned)id * stride;
-        A.rg[a] = 1.0 / (x[iu] - x[id]);
-    }
-    const double x0 = x[k];
-    A.d = x[k + 1] - x0;
+    const int km = (k - 1 < 0) ? 0 : k - 1, kp = (k + 2 > n - 1) ? n - 1 : k + 2;
+    A.off[0] = (unsigned)km * stride; A.off[1] = (unsigned)k * stride; A.off[2] = (unsigned)(k + 1) * stride; A.off[3] = (unsigned)kp * stride;
+    const double xm = x[km], x0 = x[k], x1 = x[k + 1], xp = x[kp];
+    A.r0 = 1.0 / (x1 - xm);              // node k:   up = k+1, dn = max(k-1, 0)
+    A.r1 = 1.0 / (xp - x0);              // node k+1: up = min(k+2, n-1), dn = k
+    A.d = x1 - x0;
     A.t = (xq - x0) / A.d;
 }
 
@@ -87,7 +89,7 @@ GEOAC_HD void ms_weights(MsW& w, const MsAxis& A, double slope_scale) {
     w.S0 = slope_scale * (t * u * u); w.S1 = slope_scale * (t * t * (t - 1.0));
     w.e00 = 6.0 * t * (t - 1.0); w.e01 = -w.e00;
     w.T0 = slope_scale * (u * (1.0 - 3.0 * t)); w.T1 = slope_scale * (t * (3.0 * t - 2.0));
-    const double r0 = A.rg[1], r1 = A.rg[2];
+    const double r0 = A.r0, r1 = A.r1;
     w.p = w.h00 * r0; w.q = w.h01 * r1; w.P = w.S0 * r0; w.Q = w.S1 * r1;
     w.pd = w.e00 * r0; w.qd = w.e01 * r1; w.Pd = w.T0 * r0; w.Qd = w.T1 * r1;
 }
@@ -120,9 +122,13 @@ GEOAC_HD double ms_vz(const MsZ& Z, double df, double s0, double s1)            
 GEOAC_HD double ms_vzz(const MsZ& Z, double df, double s0, double s1)           { return fma(Z.cE1, df, fma(Z.cEa, s0, Z.cEb * s1)); }
 GEOAC_HD double ms_gz(const MsZ& Z, double dd, double s0, double s1)            { return fma(Z.cG1, dd, fma(Z.cDa, s0, Z.cDb * s1)); }
 
-// the four data of one node and level for one field: f, df/dz slope, d(df/dax0)/dz slope, d(df/dax1)/dz slope (32 aligned bytes)
-struct Node4 { double f, s, sa, sb; };
-GEOAC_HD Node4 ms_ld4(const double* p) { const Pair a = ld_pair(p), b = ld_pair(p + 2); Node4 n; n.f = a.a; n.s = a.b; n.sa = b.a; n.sb = b.b; return n; }
+// the six data of one node and level for one field (48 aligned bytes): f, df/dz slope, the vertical slopes of the two
+// node differences, and the node differences df/dax0, df/dax1 themselves
+struct Node6 { double f, s, sa, sb, da, db; };
+GEOAC_HD Node6 ms_ld6(const double* p) {
+    const Pair a = ld_pair(p), b = ld_pair(p + 2), c = ld_pair(p + 4);
+    Node6 n; n.f = a.a; n.s = a.b; n.sa = b.a; n.sb = b.b; n.da = c.a; n.db = c.b; return n;
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Eval_Spline_AllOrder1 / AllOrder2 for T, u and v in one pass.  out[field][..] in GRID-axis order:
@@ -150,32 +156,22 @@ GEOAC_HD void ms_sample_tuv(const Grid3D& g, double a_in, double b_in, double z_
         double acc[10];
 #pragma unroll
         for (int i = 0; i < 10; i++) acc[i] = 0.0;
-        const double* base = g.tuv + kofs + 4 * F;
+        const double* base = g.tuv + kofs + MS_FIELD * F;
 #pragma unroll
         for (int jb = 0; jb < 4; jb++) {
             double V[4], Vz[4], Vzz[4], Ga[4], Gb[4], Gaz[4], Gbz[4];
 #pragma unroll
             for (int ia = 0; ia < 4; ia++) {
                 const double* n0p = base + (A.off[ia] + B.off[jb]);
-                const Node4 lo = ms_ld4(n0p), hi = ms_ld4(n0p + MS_STRIDE);
-                const double df = hi.f - lo.f;
+                const Node6 lo = ms_ld6(n0p), hi = ms_ld6(n0p + MS_STRIDE);
+                const double df = hi.f - lo.f, dda = hi.da - lo.da, ddb = hi.db - lo.db;
                 V[ia] = ms_v(Z, lo.f, df, lo.s, hi.s);
                 Vz[ia] = ms_vz(Z, df, lo.s, hi.s);
                 if (ORDER2) Vzz[ia] = ms_vzz(Z, df, lo.s, hi.s);
-                {   // column of the ax0 finite difference (Eval_Vert_Spline_dfdx / ddfdxdz)
-                    const double* up = base + (A.offu[ia] + B.off[jb]); const double* dn = base + (A.offd[ia] + B.off[jb]);
-                    const double d0 = (up[0] - dn[0]) * A.rg[ia], d1 = (up[MS_STRIDE] - dn[MS_STRIDE]) * A.rg[ia];
-                    const double dd = d1 - d0;
-                    Ga[ia] = ms_v(Z, d0, dd, lo.sa, hi.sa);
-                    Gaz[ia] = ms_gz(Z, dd, lo.sa, hi.sa);
-                }
-                {   // column of the ax1 finite difference
-                    const double* up = base + (A.off[ia] + B.offu[jb]); const double* dn = base + (A.off[ia] + B.offd[jb]);
-                    const double d0 = (up[0] - dn[0]) * B.rg[jb], d1 = (up[MS_STRIDE] - dn[MS_STRIDE]) * B.rg[jb];
-                    const double dd = d1 - d0;
-                    Gb[ia] = ms_v(Z, d0, dd, lo.sb, hi.sb);
-                    Gbz[ia] = ms_gz(Z, dd, lo.sb, hi.sb);
-                }
+                Ga[ia] = ms_v(Z, lo.da, dda, lo.sa, hi.sa);          // column of the ax0 node difference (Eval_Vert_Spline_dfdx / ddfdxdz)
+                Gaz[ia] = ms_gz(Z, dda, lo.sa, hi.sa);
+                Gb[ia] = ms_v(Z, lo.db, ddb, lo.sb, hi.sb);          // column of the ax1 node difference
+                Gbz[ia] = ms_gz(Z, ddb, lo.sb, hi.sb);
             }
             // ax1 weights of this row (slot jb): tensor weight, its derivative, FD-of-values weight, FD-of-slopes weight
             const double ey  = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
@@ -249,10 +245,10 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
 #pragma unroll 1
     for (int F = 0; F < (WITH_RHO ? 4 : 3); F++) {
         const bool is_rho = (F == 3);
-        const double* base = is_rho ? g.rho : g.tuv + 4 * F;
+        const double* base = is_rho ? g.rho : g.tuv + MS_FIELD * F;
         const int lvl = is_rho ? 2 : MS_STRIDE;          // doubles between vertical levels
         const unsigned ko = is_rho ? (unsigned)cur.kz * 2u : kofs;
-        const unsigned shr = is_rho ? 6u : 1u;           // node offsets were built for the 12-double layout: /6 for the 2-double one
+        const unsigned shr = is_rho ? (unsigned)(MS_STRIDE / 2) : 1u;   // node offsets were built for the tuv layout: /9 for the 2-double one
         double accv = 0.0, accz = 0.0;
 #pragma unroll
         for (int jb = 0; jb < 4; jb++) {
@@ -267,16 +263,9 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
                 if (WITH_DZ && !is_rho) {
                     Vz[ia] = ms_vz(Z, df, lo.b, hi.b);
                     const Pair slo = ld_pair(n0p + 2), shi = ld_pair(n0p + lvl + 2);  // (sa, sb) at both levels
-                    {
-                        const double* up = base + ko + (A.offu[ia] + B.off[jb]); const double* dn = base + ko + (A.offd[ia] + B.off[jb]);
-                        const double d0 = (up[0] - dn[0]) * A.rg[ia], d1 = (up[lvl] - dn[lvl]) * A.rg[ia];
-                        Gaz[ia] = ms_gz(Z, d1 - d0, slo.a, shi.a);
-                    }
-                    {
-                        const double* up = base + ko + (A.off[ia] + B.offu[jb]); const double* dn = base + ko + (A.off[ia] + B.offd[jb]);
-                        const double d0 = (up[0] - dn[0]) * B.rg[jb], d1 = (up[lvl] - dn[lvl]) * B.rg[jb];
-                        Gbz[ia] = ms_gz(Z, d1 - d0, slo.b, shi.b);
-                    }
+                    const Pair dlo = ld_pair(n0p + 4), dhi = ld_pair(n0p + lvl + 4);  // (da, db) at both levels
+                    Gaz[ia] = ms_gz(Z, dhi.a - dlo.a, slo.a, shi.a);
+                    Gbz[ia] = ms_gz(Z, dhi.b - dlo.b, slo.b, shi.b);
                 }
             }
             const double ey = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
