@@ -204,9 +204,9 @@ class Tracer:
 
     def selftest_math(self, n_per_thread=2000):
         """Max relative error of the kernel's rcp / rsqrt / sqrt / exp / exp10 against the CUDA math library."""
-        out = np.zeros(5)
+        out = np.zeros(7)
         self._check(lib().geoac_selftest_math(self._h, n_per_thread, _p(out)), "geoac_selftest_math")
-        return dict(zip(("rcp", "rsqrt", "sqrt", "exp", "exp10"), out.tolist()))
+        return dict(zip(("rcp", "rsqrt", "sqrt", "exp", "exp10", "sin", "cos"), out.tolist()))
 
     def measure_fp64_peak(self):
         ms = C.c_double(0)

@@ -245,6 +245,7 @@ __global__ void setup_consts_grid_kernel(LaunchConsts* out, const LaunchConsts i
 }
 
 static int refresh_consts(geoac_ctx* ctx) {
+    if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");      // the set-up kernel samples the tables
     if (!ctx->consts_dirty) return GEOAC_OK;
     const geoac_params& p = ctx->prm;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
@@ -406,6 +407,7 @@ extern "C" int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, 
                            double* rec, int32_t* status, int32_t* n_steps) {
     if (!ctx || n_rays < 0 || (n_rays > 0 && (!theta || !phi || !rec || !status || !n_steps))) return GEOAC_ERR_BAD_ARG;
     if (n_rays == 0) return GEOAC_OK;
+    if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");
     cudaSetDevice(ctx->device);
     const int n_rec = ctx->prm.bounces + 1;
     const int64_t n_slots = n_rays * n_rec;
@@ -522,10 +524,10 @@ extern "C" int geoac_load_met_grid(const char* prefix, const char* loc0, const c
 }
 
 // ---- accuracy self-test of the branch-free FP64 primitives (core.cuh) against libdevice, on the device ----
-__global__ void selftest_math_kernel(int n, unsigned long long* worst) {        // worst[5]: rcp, rsqrt, sqrt, exp, exp10 (bits of max rel err)
+__global__ void selftest_math_kernel(int n, unsigned long long* worst) {        // worst[7]: rcp, rsqrt, sqrt, exp, exp10, sin, cos (bits of max err)
     unsigned long long s = 0x9E3779B97F4A7C15ull * (blockIdx.x * blockDim.x + threadIdx.x + 1);
     auto uni = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) * (1.0 / 9007199254740992.0); };
-    double w[5] = { 0, 0, 0, 0, 0 };
+    double w[7] = { 0, 0, 0, 0, 0, 0, 0 };
     for (int i = 0; i < n; i++) {
         const double mant = 1.0 + uni(), ex = floor(uni() * 1800.0) - 900.0;
         const double x = ldexp(mant, (int)ex);                                  // 2^-900 .. 2^900
@@ -536,20 +538,23 @@ __global__ void selftest_math_kernel(int n, unsigned long long* worst) {        
         const double got[5] = { g_rcp(x), g_rsqrt(x), sq, oa[0], ob[0] };
         const double ref[5] = { 1.0 / x, rsqrt(x), sqrt(x), exp(xe), exp10(xt) };
         for (int k = 0; k < 5; k++) w[k] = fmax(w[k], fabs(got[k] - ref[k]) / fabs(ref[k]));
+        const double xa = (uni() * 2.0 - 1.0) * 12.0;                            // a few turns; absolute error for sin / cos
+        double gs, gc; g_sincos(xa, &gs, &gc);
+        w[5] = fmax(w[5], fabs(gs - sin(xa))); w[6] = fmax(w[6], fabs(gc - cos(xa)));
     }
-    for (int k = 0; k < 5; k++) atomicMax(worst + k, (unsigned long long)__double_as_longlong(w[k]));   // positive doubles order like integers
+    for (int k = 0; k < 7; k++) atomicMax(worst + k, (unsigned long long)__double_as_longlong(w[k]));   // positive doubles order like integers
 }
 
 extern "C" int geoac_selftest_math(geoac_ctx* ctx, int n_per_thread, double* max_rel_err) {
     if (!ctx || !max_rel_err || n_per_thread <= 0) return GEOAC_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);
     unsigned long long* d = nullptr;
-    CK(cudaMalloc(&d, 5 * sizeof(unsigned long long)));
-    CK(cudaMemset(d, 0, 5 * sizeof(unsigned long long)));
+    CK(cudaMalloc(&d, 7 * sizeof(unsigned long long)));
+    CK(cudaMemset(d, 0, 7 * sizeof(unsigned long long)));
     selftest_math_kernel<<<ctx->sm_count, 256, 0, ctx->stream>>>(n_per_thread, d);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaMemcpy(max_rel_err, d, 5 * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(max_rel_err, d, 7 * sizeof(double), cudaMemcpyDeviceToHost));
     cudaFree(d);
     return GEOAC_OK;
 }

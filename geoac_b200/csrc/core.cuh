@@ -113,6 +113,34 @@ GEOAC_HD void g_exp_n(const double (&x)[N], double (&out)[N]) {     // caller gu
 #pragma unroll
     for (int j = 0; j < N; j++) out[j] = g_scale2(p[j], n[j]);
 }
+// sin and cos together for |x| up to a few hundred (latitudes, half-angle differences): Cody-Waite reduction by pi/2 with
+// the FMA, the classic minimax kernels on |r| <= pi/4 (error < 2^-58), quadrant fix-up by selects -- no slow path.
+GEOAC_CONST_TABLE double kSinC[6] = { -1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                      2.75573137070700676789e-06, -2.50507602534068634195e-08, 1.58969099521155010221e-10 };
+GEOAC_CONST_TABLE double kCosC[6] = { 4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                      -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11 };
+GEOAC_HD void g_sincos(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    const double MAGIC = 6755399441055744.0;
+    const double t = fma(x, 0.6366197723675814, MAGIC);                      // x * 2/pi, rounded to an integer by addition
+    const int q = g_lo32(t);
+    const double k = t - MAGIC;
+    double r = fma(-k, 1.5707963267948966, x);
+    r = fma(-k, 6.123233995736766e-17, r);
+    const double z = r * r;
+    double ps = kSinC[5], pc = kCosC[5];
+#pragma unroll
+    for (int i = 4; i >= 0; i--) { ps = fma(ps, z, kSinC[i]); pc = fma(pc, z, kCosC[i]); }
+    const double sr = fma(r * z, ps, r);
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));
+    const double ss = (q & 1) ? cr : sr, cc = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -ss : ss;
+    *c = ((q + 1) & 2) ? -cc : cc;
+#else
+    sincos(x, s, c);
+#endif
+}
+
 GEOAC_HD double g_exp(double x) { const double a[1] = { x }; double o[1]; g_exp_n<false, 1>(a, o); return o[0]; }
 
 // ---------------------------------------------------------------------------------------------------------------

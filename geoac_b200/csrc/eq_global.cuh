@@ -81,7 +81,7 @@ struct EqGlobal {
         const double cn = s.c * inv_nm;
         const double g0 = cn * nu0, g1 = cn * nu1 + v, g2 = cn * nu2 + u;          // group velocity (w = 0)
         const double inv_cgm = g_rsqrt(g0 * g0 + g1 * g1 + g2 * g2);
-        double st, ct; sincos(p[1], &st, &ct);
+        double st, ct; g_sincos(p[1], &st, &ct);
         const double inv_r = g_rcp(r), inv_ct = g_rcp(ct), tant = st * inv_ct;
         const double GC1 = inv_r, GC2 = inv_r * inv_ct;
         const double nug = nu1 * g1 + nu2 * g2;
@@ -128,11 +128,16 @@ struct EqGlobal {
     // range = 2 r_e asin(sqrt(h)) > limit  <=>  h > sin^2(limit / 2 r_e); the cheap form decides unless h is within
     // 1e-9 of the threshold, where the reference's own expression is evaluated so that the decision is the reference's.
     GEOAC_HD static bool left_region(const LaunchConsts& L, const RayC& rc, const double* y) {
-        const double s1 = sin((y[1] - L.src[1]) * 0.5), s2 = sin((y[2] - L.src[2]) * 0.5);
+        if (y[0] > L.vert_limit) return true;
+        // h = sin^2(dlat/2) + cos cos sin^2(dlon/2) <= (dlat^2 + dlon^2)/4: while that bound is below the limit the ray cannot
+        // have left, and the trigonometry is skipped (most of a ray's life); beyond it the exact test decides
+        const double dlat = y[1] - L.src[1], dlon = y[2] - L.src[2];
+        if (0.25 * (dlat * dlat + dlon * dlon) <= rc.hav_limit) return false;
+        const double s1 = sin(dlat * 0.5), s2 = sin(dlon * 0.5);
         const double h = s1 * s1 + rc.cos_lat_src * cos(y[1]) * (s2 * s2);
         bool far = h > rc.hav_limit;
         if (fabs(h - rc.hav_limit) <= 1e-9 * rc.hav_limit) far = 2.0 * kREarth * asin(sqrt(h)) > L.range_limit;
-        return (y[0] > L.vert_limit) || far;
+        return far;
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[0] < L.ground; }
 
@@ -142,7 +147,7 @@ struct EqGlobal {
                                  int& cur, double& dtt, double& datt) {
         const double dr = yb[0] - ya[0], dt = yb[1] - ya[1], dp = yb[2] - ya[2];
         const double rm = ya[0] + dr * 0.5, tm = ya[1] + dt * 0.5;
-        double st, ct; sincos(tm, &st, &ct);
+        double st, ct; g_sincos(tm, &st, &ct);
         const double a = rm * dt, bc = rm * ct * dp, bs = rm * st * dp;
         const double ds_tt = g_sqrt(fmax(dr * dr + a * a + bc * bc, 1e-290));
         const double ds_sb = g_sqrt(fmax(dr * dr + a * a + bs * bs, 1e-290));

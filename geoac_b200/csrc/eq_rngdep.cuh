@@ -261,7 +261,7 @@ struct EqGlobalRD {
         const double cn = s.c * inv_nm;
         const double g0 = cn * nu0, g1 = cn * nu1 + v, g2 = cn * nu2 + u;
         const double inv_cgm = g_rsqrt(g0 * g0 + g1 * g1 + g2 * g2);
-        double st, ct; sincos(p[1], &st, &ct);
+        double st, ct; g_sincos(p[1], &st, &ct);
         const double inv_r = g_rcp(r), inv_ct = g_rcp(ct), tant = st * inv_ct;
         const double GC[3] = { 1.0, inv_r, inv_r * inv_ct };
         const double nug = nu1 * g1 + nu2 * g2;
@@ -322,7 +322,7 @@ struct EqGlobalRD {
                                  Cur3& cur, double& dtt, double& datt) {
         const double dr = yb[0] - ya[0], dt = yb[1] - ya[1], dp = yb[2] - ya[2];
         const double rm = ya[0] + dr * 0.5, tm = ya[1] + dt * 0.5, pm = ya[2] + dp * 0.5;
-        double st, ct; sincos(tm, &st, &ct);
+        double st, ct; g_sincos(tm, &st, &ct);
         const double a = rm * dt, bc = rm * ct * dp, bs = rm * st * dp;
         const double ds_tt = g_sqrt(fmax(dr * dr + a * a + bc * bc, 1e-290)), ds_sb = g_sqrt(fmax(dr * dr + a * a + bs * bs, 1e-290));
         const double n0 = ya[3] + (yb[3] - ya[3]) * 0.5, n1 = ya[4] + (yb[4] - ya[4]) * 0.5, n2 = ya[5] + (yb[5] - ya[5]) * 0.5;

@@ -163,8 +163,9 @@ int geoac_eq_count(int variant, int calc_amp);
  * when the longest-ray-first claim order was built: cost scout, histogram, scan, scatter).  Either pointer may be NULL. */
 int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kernel_launches);
 
-/* Device self-test of the kernel's branch-free FP64 primitives (reciprocal, reciprocal square root, square root, exp, 10^x)
- * against the CUDA math library on n_per_thread random operands per thread: max_rel_err[5] in that order. */
+/* Device self-test of the kernel's branch-free FP64 primitives against the CUDA math library on n_per_thread random
+ * operands per thread: max_err[7] = maximum relative error of reciprocal, reciprocal square root, square root, exp, 10^x
+ * and maximum absolute error of sin, cos (arguments within a few turns), in that order. */
 int geoac_selftest_math(geoac_ctx* ctx, int n_per_thread, double* max_rel_err);
 
 /* FP64 DFMA micro-benchmark on ctx's device: returns measured TFLOP/s (2 flops per DFMA) -- the roofline denominator. */

@@ -134,8 +134,8 @@ def test_reciprocity_at_scale():
 
 
 def test_branch_free_math_primitives():
-    """The hot loop's own reciprocal / rsqrt / sqrt / exp / 10^x (core.cuh) against the CUDA math library on random
-    operands over the whole normal range: <= 4 ulp (9e-16) -- seven orders inside the 1e-9 parity budget."""
+    """The hot loop's own reciprocal / rsqrt / sqrt / exp / 10^x / sincos (core.cuh) against the CUDA math library on
+    random operands: <= 4 ulp (9e-16 relative; absolute for sin / cos) -- seven orders inside the 1e-9 parity budget."""
     tr = g.Tracer(abi.GEOAC_3D, 0)
     errs = tr.selftest_math(4000)
     assert all(0.0 <= e < 9e-16 for e in errs.values()), errs

@@ -1,0 +1,132 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties (no oracle: the CPU reference would
+need hours): determinism, independence of the claim order / scheduling mode, record sanity, sharded == unsharded, and
+the error paths of the C ABI.  Parity proper (against the reference's golden vectors) is tests/test_gpu_parity.py."""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import geoac_b200 as g
+from geoac_b200 import abi, api, sharding
+from tests import util
+
+sys.path.insert(0, util.ROOT)
+import bench            # noqa: E402  (workload definitions only)
+
+pytestmark = pytest.mark.gpu
+
+
+def _checksum(out):
+    """Order-sensitive checksum of checksums over every record field (bit patterns, so NaN-safe and exact)."""
+    M = (1 << 64) - 1
+    h = 1469598103934665603
+    for k in ("status", "n_steps"):
+        h = ((h * 1099511628211) & M) ^ (int(out[k].astype(np.int64).sum()) & M)
+    bits = np.ascontiguousarray(out["rec"]).view(np.uint64)
+    w = (np.arange(bits.size, dtype=np.uint64).reshape(bits.shape) | np.uint64(1))
+    with np.errstate(over="ignore"):
+        x = int(np.bitwise_xor.reduce((bits * w).ravel()))
+    return ((h * 1099511628211) & M) ^ x
+
+
+def test_config2_full_grid_properties(monkeypatch):
+    """216 000 rays (config 2): two runs are bitwise identical, the longest-ray-first schedule does not change a bit, every
+    slot is accounted for, arrivals carry sane records, and the azimuthal structure of the stratified problem holds."""
+    _, th_deg, ph_deg, th, ph = bench.workload_angles("config2")
+    tr, p = bench.setup_tracer("config2", 0)
+    a = tr.trace(th, ph)
+    occ = tr.last_lane_occupancy()
+    b = tr.trace(th, ph)
+    assert _checksum(a) == _checksum(b)
+    monkeypatch.setenv("GEOAC_B200_LPT", "0")
+    tr2, _ = bench.setup_tracer("config2", 0)
+    c = tr2.trace(th, ph)
+    assert tr2.last_kernel_launches() == 1 and _checksum(a) == _checksum(c)
+    assert occ > 0.93                                                   # the scheduling pass keeps the warps full
+    st = a["status"]
+    assert set(np.unique(st)) <= {abi.ST_NONE, abi.ST_ARRIVAL, abi.ST_BREAK, abi.ST_LIMIT}
+    assert (st[:, 0] != abi.ST_NONE).all()                              # every ray produced a first-segment outcome
+    arr = st == abi.ST_ARRIVAL
+    assert 400000 < arr.sum() <= st.size
+    tt = a["rec"][abi.F_TRAVELTIME][arr]
+    assert np.isfinite(a["rec"][:, arr]).all() and (tt > 0).all() and (a["n_steps"][arr] > 2).all()
+    # a slot after a BREAK / LIMIT is never filled
+    ended = (st[:, :-1] != abi.ST_ARRIVAL)
+    assert (st[:, 1:][ended] == abi.ST_NONE).all()
+    # celerity of every arrival (range / travel time) is physical: 0.2 ... 0.36 km/s
+    rng = np.hypot(a["rec"][0][arr], a["rec"][1][arr])
+    cel = rng / tt
+    assert cel.min() > 0.15 and cel.max() < 0.40
+
+
+def test_rngdep_scale_run_is_schedule_independent(monkeypatch):
+    """Range-dependent variant on a 50x50x300 grid, 10 000 rays: packet scheduling + longest-first order vs natural order,
+    and two host-thread-driven contexts vs one: bitwise identical."""
+    _, _, _, th, ph = bench.workload_angles("config4s")
+    th, ph = th[::3].copy(), ph[::3].copy()
+    tr, p = bench.setup_tracer("config4s", 0)
+    monkeypatch.setenv("GEOAC_B200_LPT", "2")
+    a = tr.trace(th, ph)
+    monkeypatch.setenv("GEOAC_B200_LPT", "0")
+    b = tr.trace(th, ph)
+    assert _checksum(a) == _checksum(b)
+    assert (a["status"][:, 0] != abi.ST_NONE).all() and (a["status"] == abi.ST_ARRIVAL).sum() > 1000
+    tr2, _ = bench.setup_tracer("config4s", 0)
+    c = sharding.trace_multi([tr, tr2], th, ph, block=256)
+    assert _checksum(a) == _checksum(c)
+
+
+def test_abi_error_paths():
+    L = api.lib()
+    st = C.c_int(0)
+    assert not L.geoac_create(99, 0, C.byref(st)) and st.value == abi.GEOAC_ERR_BAD_ARG
+    assert not L.geoac_create(abi.GEOAC_3D, 4096, C.byref(st)) and st.value == abi.GEOAC_ERR_BAD_ARG
+    tr = g.Tracer(abi.GEOAC_3D, 0)
+    one = np.zeros(1)
+    rec = np.zeros((abi.NFIELDS, 1, 3)); s = np.zeros((1, 3), dtype=np.int32)
+    dp, ip = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+    call = lambda n: L.geoac_trace(tr._h, n, one.ctypes.data_as(dp), one.ctypes.data_as(dp), rec.ctypes.data_as(dp), s.ctypes.data_as(ip), s.ctypes.data_as(ip))
+    assert call(1) == abi.GEOAC_ERR_NO_ATMO and b"atmosphere" in L.geoac_last_error(tr._h)
+    assert call(-1) == abi.GEOAC_ERR_BAD_ARG
+    z, T, u, v, rho = g.load_met_1d(util.TOY)
+    with pytest.raises(g.GeoAcError):
+        tr.set_atmosphere_1d(z[::-1], T, u, v, rho)                    # altitudes must increase
+    with pytest.raises(g.GeoAcError):
+        tr.set_atmosphere_1d(z[:2], T[:2], u[:2], v[:2], rho[:2])      # too few levels
+    with pytest.raises(g.GeoAcError):
+        tr.set_atmosphere_3d(z, z, z, np.zeros((3, 3, 3)), np.zeros((3, 3, 3)), np.zeros((3, 3, 3)), np.zeros((3, 3, 3)))   # wrong variant
+    rd = g.Tracer(abi.GEOAC_3D_RNGDEP, 0)
+    with pytest.raises(g.GeoAcError):
+        rd.set_atmosphere_1d(z, T, u, v, rho)
+    p = tr.params
+    p.bounces = -1
+    with pytest.raises(g.GeoAcError):
+        tr.params = p
+    tr.set_atmosphere_1d(z, T, u, v, rho)
+    assert call(0) == abi.GEOAC_OK and call(1) == abi.GEOAC_OK         # recovers after errors
+
+
+def test_table_too_large_for_shared_memory_still_traces():
+    """A profile with more levels than fit beside the lane records in shared memory falls back to reading the table through
+    L1/L2 (TABLE_IN_SMEM = false) and gives the same records as the shared-memory path on the same spline."""
+    z, T, u, v, rho = g.load_met_1d(util.TOY)
+    th, ph = util.angles_rad(np.linspace(4, 40, 19), np.full(19, 20.0))
+    tr = g.Tracer(abi.GEOAC_3D, 0)
+    tr.set_atmosphere_1d(z, T, u, v, rho)
+    a = tr.trace(th, ph)
+    # same profile resampled on a 4x finer grid by the spline's own knots would change the spline; instead append levels
+    # above the propagation ceiling, which the rays never see (vert_limit stays at the original top)
+    zx = np.concatenate([z, z[-1] + 0.1 * np.arange(1, 2001)])
+    ext = lambda f: np.concatenate([f, np.full(2000, f[-1])])
+    big = g.Tracer(abi.GEOAC_3D, 0)
+    big.set_atmosphere_1d(zx, ext(T), ext(u), ext(v), ext(rho))
+    pb = big.params
+    pb.vert_limit = tr.params.vert_limit
+    big.params = pb
+    b = big.trace(th, ph)
+    assert np.array_equal(a["status"], b["status"]) and (np.abs(a["n_steps"] - b["n_steps"]) <= 1).all()
+    m = a["status"] == abi.ST_ARRIVAL
+    # the natural spline's end condition moves to the new top, which perturbs the slopes of the last original levels a little
+    assert np.allclose(a["rec"][abi.F_TRAVELTIME][m], b["rec"][abi.F_TRAVELTIME][m], rtol=1e-6)
