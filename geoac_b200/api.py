@@ -22,7 +22,9 @@ class GeoAcError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libgeoac_b200.so")
+    """The product library; GEOAC_B200_LIB names an experimental build in the same directory (A/B measurements only)."""
+    name = os.environ.get("GEOAC_B200_LIB", "libgeoac_b200.so")
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", os.path.basename(name))
 
 
 def lib():

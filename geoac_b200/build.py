@@ -9,6 +9,7 @@ LIBDIR = os.path.join(PKG, "_lib")
 LIB = os.path.join(LIBDIR, "libgeoac_b200.so")
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-diag-suppress", "20091",      # __constant__ tables named inside __host__ __device__ code that only the device runs
               "-Xcompiler", "-fPIC", "-shared"]
 
 
@@ -31,14 +32,17 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source into one shared library. Returns its path."""
-    if not force and not _stale():
+def build(force=False, verbose=False, defines=(), out=None):
+    """Compile every CUDA source into one shared library. Returns its path.
+    `defines` / `out` build an experimental variant next to the product library (A/B measurements only; select it with
+    the GEOAC_B200_LIB environment variable, see api.library_path)."""
+    target = os.path.join(LIBDIR, out) if out else LIB
+    if not force and not out and not _stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", LIB]
+    cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", target]
     subprocess.check_call(cmd)
-    return LIB
+    return target
 
 
 if __name__ == "__main__":

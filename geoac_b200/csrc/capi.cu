@@ -360,7 +360,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
             const int blk = e ? std::atoi(e) : 384;
             if (blk == 256) return launch_trace<Eq3D<true>, 256>(ctx, a, st);
             if (blk == 512) return launch_trace<Eq3D<true>, 512>(ctx, a, st);
-            return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 168 registers, no spills: 8.06 vs 6.95 (512) / 7.13 (256) G steps/s
+            return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 168 registers, no spills: 8.4 G steps/s vs 7.3 (320) / 7.1 (448) / 6.95 (512) / 7.13 (256)
         }
 #ifdef GEOAC_HAVE_GLOBAL
         case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 384>(ctx, a, st) : launch_trace<EqGlobal<false>, 512>(ctx, a, st);

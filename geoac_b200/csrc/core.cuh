@@ -276,7 +276,7 @@ GEOAC_CONST_TABLE double kSBX5[6] = { -53.746, 1.5439, -1.8824E-2, 1.1587E-4, -3
 //   * the remaining exponentials (gas fractions 10^poly(z), rotational collision numbers, vibrational Boltzmann factors)
 //     are evaluated in lock step by the branch-free g_exp_n; the polynomials in z are Horner forms;
 //   * every quotient is a product with one of five reciprocals (two of them batched inversions).
-GEOAC_HD_NOINLINE double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho) {
+GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho) {
     const double mu_o = 18.192E-6, S = 117.0;
     const double inv_c2 = inv_c * inv_c;
     const double c2 = (c * c) * 1.0e6;                                      // (1000 c)^2
