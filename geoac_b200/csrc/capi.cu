@@ -313,8 +313,24 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 1)));
         CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 1), st));
         uint32_t* cmax = ctx->d_hist + kCostBuckets;
-        const int sblocks = (int)std::min<int64_t>((a.n_rays + 127) / 128, (int64_t)ctx->sm_count * 16);
-        scout_kernel<typename EQ::Scout><<<sblocks, 128, 0, st>>>(a, ctx->d_cost, cmax);
+        {   // cost scout: persistent, the table in shared memory when it fits
+            using SEQ = typename EQ::Scout;
+            constexpr int kScoutBlock = ScoutBlock<SEQ>::value;
+            const size_t s_tab = kGrid ? 0 : 16 + tab_bytes;
+            const bool s_in = !kGrid && s_tab <= (size_t)max_optin;
+            const void* sfn = s_in ? (const void*)scout_kernel<SEQ, true> : (const void*)scout_kernel<SEQ, false>;
+            const size_t s_smem = s_in ? s_tab : 16;
+            CK(cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
+            int s_per_sm = 1;
+            CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_per_sm, sfn, kScoutBlock, s_smem));
+            const int64_t s_need = (a.n_rays + kScoutBlock - 1) / kScoutBlock;
+            const int sblocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * std::max(1, s_per_sm), s_need);
+            unsigned long long* scounter = ctx->d_counters + 3;
+            const char* ce = std::getenv("GEOAC_B200_SCOUT_COARSE");        // experiments: step-size multiple of the scout
+            int coarse = ce ? std::max(1, std::atoi(ce)) : kScoutCoarse;
+            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&scounter, (void*)&coarse };
+            CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
+        }
         order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist);
         order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
         order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);

@@ -312,53 +312,87 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
 constexpr int kScoutCoarse = 16;
 constexpr int kCostBuckets = 256;
 
-template <class EQ>
-__global__ void __launch_bounds__(128) scout_kernel(const __grid_constant__ TraceArgs a, uint32_t* cost, uint32_t* cost_max) {
+// lanes per CTA of the scout: 512 (<= 128 registers) for the stratified sets, 256 for the range-dependent sampler
+template <class EQ> struct ScoutBlock { static constexpr int value = std::is_same<typename EQ::Atmo, Grid3D>::value ? 256 : 512; };
+
+// Persistent like the trace kernel: lanes are refilled from a counter as their rays end (a warp of rays with different
+// lifetimes never idles), the 1-D table sits in shared memory; the ray state (<= 6 equations, no auxiliary set) fits
+// in registers.
+template <class EQ, bool TABLE_IN_SMEM>
+__global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const __grid_constant__ TraceArgs a, uint32_t* cost, uint32_t* cost_max,
+                                                               unsigned long long* counter, int coarse) {
     constexpr int NEQ = EQ::NEQ;
+    constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+    double* tab_s = reinterpret_cast<double*>(smem_raw + 16);
     const LaunchConsts& L = *a.consts;
     typename EQ::Atmo T;
-    double sbuf[std::is_same<typename EQ::Atmo, Grid3D>::value ? MS_SCRATCH : 1];
-    if constexpr (std::is_same<typename EQ::Atmo, Grid3D>::value) { T = a.grid; T.scratch = sbuf; }
-    else { T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.base = a.table; }
-    uint32_t worst = 0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < a.n_rays; r += (int64_t)gridDim.x * blockDim.x) {
-        double y[NEQ], ym1[NEQ], acc[NEQ], p[NEQ], f[NEQ];
-        typename EQ::RayC rc; typename EQ::Cursor cur = typename EQ::Cursor{};
-        EQ::init(L, T, a.theta[r], a.phi[r], rc, y, cur);
+    double sbuf[kGrid ? MS_SCRATCH : 1];
+    if constexpr (kGrid) { T = a.grid; T.scratch = sbuf; }
+    else {
+        T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.base = a.table;
+        if (TABLE_IN_SMEM) { tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_n * sizeof(double)), bar); T.base = tab_s; }
+    }
+    __syncthreads();
+    const unsigned lane = threadIdx.x & 31;
+    const uint32_t cap = (uint32_t)L.step_limit;
+    double y[NEQ], ym1[NEQ];
+    typename EQ::RayC rc; typename EQ::Cursor cur = typename EQ::Cursor{};
+    uint32_t est = 0, seg = 0, worst = 0; int bounce = 0; int64_t ray = 0;
+    bool have_ray = false, exhausted = false;
+    while (true) {
+        const bool want = !have_ray && !exhausted;
+        const unsigned wmask = __ballot_sync(0xffffffffu, want);
+        if (wmask) {
+            unsigned long long base = 0;
+            const int leader = __ffs(wmask) - 1;
+            if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(wmask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (want) {
+                ray = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
+                if (ray < a.n_rays) {
+                    cur = typename EQ::Cursor{};
+                    EQ::init(L, T, a.theta[ray], a.phi[ray], rc, y, cur);
 #pragma unroll
-        for (int i = 0; i < NEQ; i++) ym1[i] = y[i];
-        uint32_t est = 0, seg = 0; int bounce = 0;
-        const uint32_t cap = (uint32_t)L.step_limit;
-        while (true) {
-            const double ds = (double)kScoutCoarse * EQ::step_size(L, y);
-#pragma unroll
-            for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = y[i]; }
-#pragma unroll 1
-            for (int s = 0; s < 4; s++) {
-                EQ::rhs(L, T, rc, p, f, cur);
-                const double dsa = ds * ((s == 2) ? 1.0 : 0.5), dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
-#pragma unroll
-                for (int i = 0; i < NEQ; i++) { acc[i] = fma(f[i], dsb, acc[i]); p[i] = fma(f[i], dsa, y[i]); }
+                    for (int i = 0; i < NEQ; i++) ym1[i] = y[i];
+                    est = 0; seg = 0; bounce = 0; have_ray = true;
+                } else exhausted = true;
             }
-            est += kScoutCoarse; seg += kScoutCoarse;
-            if (EQ::left_region(L, rc, acc) || seg >= cap) break;
-            if (EQ::below_ground(L, acc)) {
-                if (bounce >= L.bounces) break;
+        }
+        if (!__any_sync(0xffffffffu, have_ray)) break;
+        if (!have_ray) continue;
+        double acc[NEQ], p[NEQ], f[NEQ];
+        const double ds = (double)coarse * EQ::step_size(L, y);
+#pragma unroll
+        for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = y[i]; }
+#pragma unroll 1
+        for (int s = 0; s < 4; s++) {
+            EQ::rhs(L, T, rc, p, f, cur);
+            const double dsa = ds * ((s == 2) ? 1.0 : 0.5), dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+#pragma unroll
+            for (int i = 0; i < NEQ; i++) { acc[i] = fma(f[i], dsb, acc[i]); p[i] = fma(f[i], dsa, y[i]); }
+        }
+        est += (uint32_t)coarse; seg += (uint32_t)coarse;
+        bool done = EQ::left_region(L, rc, acc) || seg >= cap;
+        if (!done && EQ::below_ground(L, acc)) {
+            if (bounce >= L.bounces) done = true;
+            else {
                 double y0[NEQ];
                 EQ::reflect(L, T, rc, ym1, y, acc, y0, cur);
 #pragma unroll
-                for (int i = 0; i < NEQ; i++) { y[i] = y0[i]; ym1[i] = y0[i]; }
+                for (int i = 0; i < NEQ; i++) { acc[i] = y0[i]; y[i] = y0[i]; }      // restart: y = ym1 = reflected state
                 bounce++; seg = 0;
-                continue;
             }
+        }
+        if (done) { cost[ray] = est; worst = max(worst, est); have_ray = false; }
+        else {
 #pragma unroll
             for (int i = 0; i < NEQ; i++) { ym1[i] = y[i]; y[i] = acc[i]; }
         }
-        cost[r] = est;
-        worst = max(worst, est);
     }
     worst = __reduce_max_sync(0xffffffffu, worst);
-    if ((threadIdx.x & 31) == 0 && worst) atomicMax(cost_max, worst);
+    if (lane == 0 && worst) atomicMax(cost_max, worst);
 }
 
 // counting sort by predicted cost, descending: hist[b] of bucket(cost) -> start offsets -> scatter.  The sorted items are
