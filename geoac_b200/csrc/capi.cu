@@ -101,7 +101,7 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
            && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess
            && cudaMalloc(&ctx->d_consts, sizeof(LaunchConsts)) == cudaSuccess
-           && cudaMalloc(&ctx->d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess;
+           && cudaMalloc(&ctx->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); delete ctx; return bail(GEOAC_ERR_CUDA, "context allocation failed: " + m); }
     if (status) *status = GEOAC_OK;
     return ctx;
@@ -215,7 +215,7 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     CK(cudaMemcpy(ctx->d_ax + n0 + n1, z.data(), nz * sizeof(double), cudaMemcpyHostToDevice));
     Grid3D& g = ctx->grid;
     g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + n0; g.axz = ctx->d_ax + n0 + n1;
-    g.n0 = n0; g.n1 = n1; g.nz = nz; g.scratch = nullptr;
+    g.n0 = n0; g.n1 = n1; g.nz = nz; g.scratch = nullptr; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
     // GeoAc_SetPropRegion: G2S_MultiDimSpline3D.cpp:22-33 / G2S_GlobalMultiDimSpline3D.cpp:22-33
     ctx->prm.vert_limit = g.zmax;
@@ -296,7 +296,8 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         }
     }
     a.prev = ctx->d_prev;
-    a.order = nullptr; a.n_claims = a.n_rays;
+    a.order = nullptr; a.n_claims = a.n_rays; a.n_long = nullptr; a.counter_long = ctx->d_counters + 4;
+    { const char* pe = std::getenv("GEOAC_B200_PACKET"); a.packet_refill = pe ? std::atoi(pe) : 0; }   // experiments only
     ctx->last_launches = 0;
     // longest-predicted-ray-first claim order, when a lane will process more than one ray (see trace_kernel.cuh)
     // GEOAC_B200_LPT: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
@@ -310,9 +311,12 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             CK(cudaMalloc(&ctx->d_cost, sizeof(uint32_t) * n_entries)); CK(cudaMalloc(&ctx->d_order, sizeof(uint32_t) * n_entries));
             ctx->cap_order = n_entries;
         }
-        if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 1)));
-        CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 1), st));
+        // d_hist: [0..255] buckets, [256] largest cost, [257] number of long packets, [258..259] cost sum (64 bit)
+        if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 8)));
+        CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 8), st));
         uint32_t* cmax = ctx->d_hist + kCostBuckets;
+        uint32_t* n_long = ctx->d_hist + kCostBuckets + 1;
+        unsigned long long* cost_sum = reinterpret_cast<unsigned long long*>(ctx->d_hist + kCostBuckets + 2);
         {   // cost scout: persistent, the table in shared memory when it fits
             using SEQ = typename EQ::Scout;
             constexpr int kScoutBlock = ScoutBlock<SEQ>::value;
@@ -328,14 +332,16 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             unsigned long long* scounter = ctx->d_counters + 3;
             const char* ce = std::getenv("GEOAC_B200_SCOUT_COARSE");        // experiments: step-size multiple of the scout
             int coarse = ce ? std::max(1, std::atoi(ce)) : kScoutCoarse;
-            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&scounter, (void*)&coarse };
+            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
         }
-        order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist);
+        order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long);
         order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
         order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
         CK(cudaGetLastError());
         a.n_claims = n_entries;
+        static const bool coop_off = [] { const char* e = std::getenv("GEOAC_B200_COOP"); return e && std::atoi(e) == 0; }();
+        a.n_long = (PacketMode<EQ>::value && !coop_off) ? n_long : nullptr;
         a.order = ctx->d_order;
         ctx->last_launches += 4;
     }
@@ -356,7 +362,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     }
     const int n_rec = ctx->prm.bounces + 1;
     const int64_t n_slots = n_rays * n_rec;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 6 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(d_rec, 0, sizeof(double) * GEOAC_NFIELDS * n_slots, st));
     CK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_slots, st));
     CK(cudaMemsetAsync(d_n_steps, 0, sizeof(int32_t) * n_slots, st));

@@ -35,6 +35,9 @@ struct Grid3D {
     int n0, n1, nz;
     double amin, amax, bmin, bmax, zmin, zmax;
     double* scratch;        // per-thread sampler output block (MS_SCRATCH doubles): shared memory on the device
+    // cooperative mode (trace_kernel.cuh, straggler acceleration): `nrole` = 4 lanes advance ONE ray together, lane `role`
+    // evaluates row `role` of the 4x4 node block; lanes glane0 .. glane0+3 (mask gmask) form the group.  nrole = 1: serial.
+    int role, nrole, glane0; unsigned gmask;
 };
 constexpr int MS_SCRATCH = 30;
 
@@ -131,6 +134,112 @@ GEOAC_HD Node6 ms_ld6(const double* p) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Row-wise accumulation with PINNED arithmetic.  A query sums the contributions of the four ax1 rows of the node block.
+// The serial path adds them row after row; the cooperative path has four lanes evaluate one row each and passes the
+// accumulator from lane to lane in the same order.  Every operation that combines rows is an explicit fma, so both paths
+// produce the same bits whatever the compiler would otherwise contract -- a ray's record does not depend on how many
+// lanes worked on it (tests: schedule neutrality, multi-context == single).
+// ---------------------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+GEOAC_HD double p_mul(double a, double b) { return __dmul_rn(a, b); }
+GEOAC_HD double p_add(double a, double b) { return __dadd_rn(a, b); }
+GEOAC_HD double p_sub(double a, double b) { return __dsub_rn(a, b); }
+#else
+GEOAC_HD double p_mul(double a, double b) { return a * b; }
+GEOAC_HD double p_add(double a, double b) { return a + b; }
+GEOAC_HD double p_sub(double a, double b) { return a - b; }
+#endif
+
+// ax1 weights of one row (slot jb): tensor weight and its derivative, slope weights, FD-of-values and FD-of-slopes weights
+struct MsRowW { double ey, eyd, sy, syd, al, ald, be, bed; };
+GEOAC_HD MsRowW ms_row_weights(const MsW& wb, int jb) {
+    MsRowW r;
+    r.ey  = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
+    r.eyd = (jb == 1) ? wb.e00 : ((jb == 2) ? wb.e01 : 0.0);
+    r.sy  = (jb == 1) ? wb.S0 : ((jb == 2) ? wb.S1 : 0.0);
+    r.syd = (jb == 1) ? wb.T0 : ((jb == 2) ? wb.T1 : 0.0);
+    r.al  = (jb == 0) ? -wb.p  : ((jb == 1) ? -wb.q  : ((jb == 2) ? wb.p  : wb.q));
+    r.ald = (jb == 0) ? -wb.pd : ((jb == 1) ? -wb.qd : ((jb == 2) ? wb.pd : wb.qd));
+    r.be  = (jb == 0) ? -wb.P  : ((jb == 1) ? -wb.Q  : ((jb == 2) ? wb.P  : wb.Q));
+    r.bed = (jb == 0) ? -wb.Pd : ((jb == 1) ? -wb.Qd : ((jb == 2) ? wb.Pd : wb.Qd));
+    return r;
+}
+// a_0 Q1 + a_1 Q2 + b_0 (Q2 - Q0) + b_1 (Q3 - Q1), pinned
+GEOAC_HD double p_row4(double a0, double a1, double b0, double b1, double Q0, double Q1, double Q2, double Q3) {
+    return fma(b1, p_sub(Q3, Q1), fma(b0, p_sub(Q2, Q0), fma(a1, Q2, p_mul(a0, Q1))));
+}
+GEOAC_HD double p_row2(double a0, double a1, double Q1, double Q2) { return fma(a1, Q2, p_mul(a0, Q1)); }
+
+// the row-level partial results of one field on one row of four nodes
+struct MsRowVals { double Fv, FXv, FGb, EVz, BVz, GXZ, GYZ, FXd, EVzd, BVzd, GXZd, GYZd, EVzz, BVzz; };
+
+template <bool GLOBAL, bool ORDER2>
+GEOAC_HD void ms_row_vals(MsRowVals& R, const double* base, const unsigned (&aoff)[4], unsigned boff, const MsZ& Z, const MsW& wa) {
+    double V[4], Vz[4], Vzz[4], Ga[4], Gb[4], Gaz[4], Gbz[4];
+#pragma unroll
+    for (int ia = 0; ia < 4; ia++) {
+        const double* n0p = base + (aoff[ia] + boff);
+        const Node6 lo = ms_ld6(n0p), hi = ms_ld6(n0p + MS_STRIDE);
+        const double df = hi.f - lo.f, dda = hi.da - lo.da, ddb = hi.db - lo.db;
+        V[ia] = ms_v(Z, lo.f, df, lo.s, hi.s);
+        Vz[ia] = ms_vz(Z, df, lo.s, hi.s);
+        if (ORDER2) Vzz[ia] = ms_vzz(Z, df, lo.s, hi.s); else Vzz[ia] = 0.0;
+        Ga[ia] = ms_v(Z, lo.da, dda, lo.sa, hi.sa);          // column of the ax0 node difference (Eval_Vert_Spline_dfdx / ddfdxdz)
+        Gaz[ia] = ms_gz(Z, dda, lo.sa, hi.sa);
+        Gb[ia] = ms_v(Z, lo.db, ddb, lo.sb, hi.sb);          // column of the ax1 node difference
+        Gbz[ia] = ms_gz(Z, ddb, lo.sb, hi.sb);
+    }
+    R.Fv  = p_row4(wa.h00, wa.h01, wa.P, wa.Q, V[0], V[1], V[2], V[3]);
+    const double dV0 = p_sub(V[2], V[0]), dV1 = p_sub(V[3], V[1]), dG0 = p_sub(Ga[2], Ga[0]), dG1 = p_sub(Ga[3], Ga[1]);
+    R.FXv = fma(wa.Q, dG1, fma(wa.P, dG0, fma(wa.q, dV1, p_mul(wa.p, dV0))));
+    R.FGb = p_row4(wa.h00, wa.h01, wa.P, wa.Q, Gb[0], Gb[1], Gb[2], Gb[3]);
+    R.EVz = p_row2(wa.h00, wa.h01, Vz[1], Vz[2]);
+    R.BVz = fma(wa.Q, p_sub(Vz[3], Vz[1]), p_mul(wa.P, p_sub(Vz[2], Vz[0])));
+    R.GXZ = p_row2(wa.S0, wa.S1, Gaz[1], Gaz[2]);            // used only on the corner rows (ey != 0)
+    R.GYZ = p_row2(wa.h00, wa.h01, Gbz[1], Gbz[2]);
+    if (ORDER2) {
+        R.FXd  = fma(wa.Qd, dG1, fma(wa.Pd, dG0, fma(wa.qd, dV1, p_mul(wa.pd, dV0))));
+        R.EVzd = p_row2(wa.e00, wa.e01, Vz[1], Vz[2]);
+        R.BVzd = fma(wa.Qd, p_sub(Vz[3], Vz[1]), p_mul(wa.Pd, p_sub(Vz[2], Vz[0])));
+        R.GXZd = p_row2(wa.T0, wa.T1, Gaz[1], Gaz[2]);
+        R.GYZd = p_row2(wa.e00, wa.e01, Gbz[1], Gbz[2]);
+        R.EVzz = p_row2(wa.h00, wa.h01, Vzz[1], Vzz[2]);
+        R.BVzz = fma(wa.Q, p_sub(Vzz[3], Vzz[1]), p_mul(wa.P, p_sub(Vzz[2], Vzz[0])));
+    }
+}
+
+// acc += contribution of one row (explicit fma chains on the accumulator: the order of the rows is the order of the calls)
+template <bool ORDER2>
+GEOAC_HD void ms_row_acc(double (&acc)[10], const MsRowVals& R, const MsRowW& w, double qs) {
+    const double wy = p_add(w.ey, w.be), wyd = p_add(w.eyd, w.bed);
+    const double EG = p_add(R.EVz, R.GXZ);
+    acc[0] = fma(wy, R.Fv, acc[0]);
+    acc[1] = fma(wy, R.FXv, acc[1]);
+    acc[2] = fma(w.be, R.FGb, fma(w.al, R.Fv, acc[2]));
+    acc[3] = fma(w.sy, R.GYZ, fma(w.be, R.BVz, fma(w.ey, EG, acc[3])));
+    if (ORDER2) {
+        acc[4] = fma(wy, R.FXd, acc[4]);
+        acc[5] = fma(w.bed, R.FGb, fma(w.ald, R.Fv, acc[5]));
+        // d2f/dz2 block: only its Py data carry the dx-for-dy slip, the Pxy data are scaled by dx*dy
+        acc[6] = fma(w.be, R.BVzz, fma(p_mul(w.be, qs), R.EVzz, fma(w.ey, p_add(R.EVzz, R.BVzz), acc[6])));
+        acc[7] = fma(wyd, R.FXv, acc[7]);
+        acc[8] = fma(w.sy, R.GYZd, fma(w.be, R.BVzd, fma(w.ey, p_add(R.EVzd, R.GXZd), acc[8])));
+        acc[9] = fma(w.syd, R.GYZ, fma(w.bed, R.BVz, fma(w.eyd, EG, acc[9])));
+    }
+}
+
+// cooperative hand-over: every lane of the group takes the accumulator of lane `src` (glane0 + row)
+template <int N>
+GEOAC_HD void ms_group_take(double (&acc)[N], const Grid3D& g, int row) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+    for (int i = 0; i < N; i++) acc[i] = __shfl_sync(g.gmask, acc[i], g.glane0 + row);
+#else
+    (void)acc; (void)g; (void)row;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Eval_Spline_AllOrder1 / AllOrder2 for T, u and v in one pass.  out[field][..] in GRID-axis order:
 //   0 f, 1 d/da, 2 d/db, 3 d/dz, 4 d2/da2, 5 d2/db2, 6 d2/dz2, 7 d2/dadb, 8 d2/dadz, 9 d2/dbdz   (a = ax0, b = ax1, z = vertical)
 // ---------------------------------------------------------------------------------------------------------------
@@ -151,72 +260,34 @@ GEOAC_HD void ms_sample_tuv(const Grid3D& g, double a_in, double b_in, double z_
     const double qs = GLOBAL ? 1.0 : A.d / B.d;
     const unsigned kofs = (unsigned)cur.kz * MS_STRIDE;
 
+    const double ida = 1.0 / A.d, idb = 1.0 / B.d;
 #pragma unroll 1
     for (int F = 0; F < 3; F++) {
         double acc[10];
 #pragma unroll
         for (int i = 0; i < 10; i++) acc[i] = 0.0;
         const double* base = g.tuv + kofs + MS_FIELD * F;
+        if (g.nrole == 1) {
 #pragma unroll
-        for (int jb = 0; jb < 4; jb++) {
-            double V[4], Vz[4], Vzz[4], Ga[4], Gb[4], Gaz[4], Gbz[4];
-#pragma unroll
-            for (int ia = 0; ia < 4; ia++) {
-                const double* n0p = base + (A.off[ia] + B.off[jb]);
-                const Node6 lo = ms_ld6(n0p), hi = ms_ld6(n0p + MS_STRIDE);
-                const double df = hi.f - lo.f, dda = hi.da - lo.da, ddb = hi.db - lo.db;
-                V[ia] = ms_v(Z, lo.f, df, lo.s, hi.s);
-                Vz[ia] = ms_vz(Z, df, lo.s, hi.s);
-                if (ORDER2) Vzz[ia] = ms_vzz(Z, df, lo.s, hi.s);
-                Ga[ia] = ms_v(Z, lo.da, dda, lo.sa, hi.sa);          // column of the ax0 node difference (Eval_Vert_Spline_dfdx / ddfdxdz)
-                Gaz[ia] = ms_gz(Z, dda, lo.sa, hi.sa);
-                Gb[ia] = ms_v(Z, lo.db, ddb, lo.sb, hi.sb);          // column of the ax1 node difference
-                Gbz[ia] = ms_gz(Z, ddb, lo.sb, hi.sb);
+            for (int jb = 0; jb < 4; jb++) {
+                MsRowVals R;
+                ms_row_vals<GLOBAL, ORDER2>(R, base, A.off, B.off[jb], Z, wa);
+                ms_row_acc<ORDER2>(acc, R, ms_row_weights(wb, jb), qs);
             }
-            // ax1 weights of this row (slot jb): tensor weight, its derivative, FD-of-values weight, FD-of-slopes weight
-            const double ey  = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
-            const double eyd = (jb == 1) ? wb.e00 : ((jb == 2) ? wb.e01 : 0.0);
-            const double sy  = (jb == 1) ? wb.S0 : ((jb == 2) ? wb.S1 : 0.0);
-            const double syd = (jb == 1) ? wb.T0 : ((jb == 2) ? wb.T1 : 0.0);
-            const double al  = (jb == 0) ? -wb.p  : ((jb == 1) ? -wb.q  : ((jb == 2) ? wb.p  : wb.q));
-            const double ald = (jb == 0) ? -wb.pd : ((jb == 1) ? -wb.qd : ((jb == 2) ? wb.pd : wb.qd));
-            const double be  = (jb == 0) ? -wb.P  : ((jb == 1) ? -wb.Q  : ((jb == 2) ? wb.P  : wb.Q));
-            const double bed = (jb == 0) ? -wb.Pd : ((jb == 1) ? -wb.Qd : ((jb == 2) ? wb.Pd : wb.Qd));
-            const double wy = ey + be, wyd = eyd + bed;
-
-            const double Fv = ms_HX(wa, V[0], V[1], V[2], V[3]);
-            const double dV0 = V[2] - V[0], dV1 = V[3] - V[1], dG0 = Ga[2] - Ga[0], dG1 = Ga[3] - Ga[1];
-            const double FXv = wa.p * dV0 + wa.q * dV1 + wa.P * dG0 + wa.Q * dG1;
-            const double FGb = ms_HX(wa, Gb[0], Gb[1], Gb[2], Gb[3]);
-            const double EVz = wa.h00 * Vz[1] + wa.h01 * Vz[2];
-            const double BVz = wa.P * (Vz[2] - Vz[0]) + wa.Q * (Vz[3] - Vz[1]);
-            const double GXZ = wa.S0 * Gaz[1] + wa.S1 * Gaz[2];          // used only on the corner rows (ey != 0)
-            const double GYZ = wa.h00 * Gbz[1] + wa.h01 * Gbz[2];
-            acc[0] += wy * Fv;
-            acc[1] += wy * FXv;
-            acc[2] += al * Fv + be * FGb;
-            acc[3] += ey * (EVz + GXZ) + be * BVz + sy * GYZ;
-            if (ORDER2) {
-                const double FXd = wa.pd * dV0 + wa.qd * dV1 + wa.Pd * dG0 + wa.Qd * dG1;
-                const double EVzd = wa.e00 * Vz[1] + wa.e01 * Vz[2];
-                const double BVzd = wa.Pd * (Vz[2] - Vz[0]) + wa.Qd * (Vz[3] - Vz[1]);
-                const double GXZd = wa.T0 * Gaz[1] + wa.T1 * Gaz[2];
-                const double GYZd = wa.e00 * Gbz[1] + wa.e01 * Gbz[2];
-                acc[4] += wy * FXd;
-                acc[5] += ald * Fv + bed * FGb;
-                {   // d2f/dz2 block: only its Py data carry the dx-for-dy slip, the Pxy data are scaled by dx*dy
-                    const double EVzz = wa.h00 * Vzz[1] + wa.h01 * Vzz[2];
-                    const double BVzz = wa.P * (Vzz[2] - Vzz[0]) + wa.Q * (Vzz[3] - Vzz[1]);
-                    acc[6] += ey * (EVzz + BVzz) + (be * qs) * EVzz + be * BVzz;
-                }
-                acc[7] += wyd * FXv;
-                acc[8] += ey * (EVzd + GXZd) + be * BVzd + sy * GYZd;
-                acc[9] += eyd * (EVz + GXZ) + bed * BVz + syd * GYZ;
+        } else {                                    // four lanes, one row each; the accumulator travels lane 0 -> 1 -> 2 -> 3 -> all
+            const int jb = g.role;
+            const unsigned boff = (jb == 0) ? B.off[0] : ((jb == 1) ? B.off[1] : ((jb == 2) ? B.off[2] : B.off[3]));
+            MsRowVals R;
+            ms_row_vals<GLOBAL, ORDER2>(R, base, A.off, boff, Z, wa);
+            const MsRowW w = ms_row_weights(wb, jb);
+#pragma unroll 1
+            for (int r = 0; r < 4; r++) {
+                if (r == jb) ms_row_acc<ORDER2>(acc, R, w, qs);
+                ms_group_take<10>(acc, g, r);
             }
         }
         if (ORDER2 && !GLOBAL) {            // Global leaves the second derivatives in scaled units (App. A-9)
-            const double ida = 1.0 / A.d, idb = 1.0 / B.d;
-            acc[4] *= ida; acc[5] *= idb; acc[7] *= idb; acc[8] *= ida; acc[9] *= idb;
+            acc[4] = p_mul(acc[4], ida); acc[5] = p_mul(acc[5], idb); acc[7] = p_mul(acc[7], idb); acc[8] = p_mul(acc[8], ida); acc[9] = p_mul(acc[9], idb);
         }
 #pragma unroll
         for (int i = 0; i < 10; i++) out[F][i] = acc[i];
@@ -249,17 +320,18 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
         const int lvl = is_rho ? 2 : MS_STRIDE;          // doubles between vertical levels
         const unsigned ko = is_rho ? (unsigned)cur.kz * 2u : kofs;
         const unsigned shr = is_rho ? (unsigned)(MS_STRIDE / 2) : 1u;   // node offsets were built for the tuv layout: /9 for the 2-double one
-        double accv = 0.0, accz = 0.0;
-#pragma unroll
-        for (int jb = 0; jb < 4; jb++) {
+        double av[2] = { 0.0, 0.0 };               // value, d/dz
+        const double bscale = GLOBAL ? 1.0 : B.d / A.d;
+        auto row = [&](int jb, unsigned boff) {
             double V[4], Vz[4], Gaz[4], Gbz[4];
 #pragma unroll
             for (int ia = 0; ia < 4; ia++) {
-                const unsigned o = (A.off[ia] + B.off[jb]) / shr;
+                const unsigned o = (A.off[ia] + boff) / shr;
                 const double* n0p = base + ko + o;
                 const Pair lo = ld_pair(n0p), hi = ld_pair(n0p + lvl);            // (f, slope) at both levels
                 const double df = hi.a - lo.a;
                 V[ia] = ms_v(Z, lo.a, df, lo.b, hi.b);
+                Vz[ia] = 0.0; Gaz[ia] = 0.0; Gbz[ia] = 0.0;
                 if (WITH_DZ && !is_rho) {
                     Vz[ia] = ms_vz(Z, df, lo.b, hi.b);
                     const Pair slo = ld_pair(n0p + 2), shi = ld_pair(n0p + lvl + 2);  // (sa, sb) at both levels
@@ -268,24 +340,38 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
                     Gbz[ia] = ms_gz(Z, dhi.b - dlo.b, slo.b, shi.b);
                 }
             }
-            const double ey = (jb == 1) ? wb.h00 : ((jb == 2) ? wb.h01 : 0.0);
-            const double sy = (jb == 1) ? wb.S0 : ((jb == 2) ? wb.S1 : 0.0);
-            const double be = (jb == 0) ? -wb.P : ((jb == 1) ? -wb.Q : ((jb == 2) ? wb.P : wb.Q));
+            const MsRowW w = ms_row_weights(wb, jb);
             // the Pxy block of Eval_Spline_f / _df is scaled by dx*dy, only the Py block by the slipped scale: separate the two
-            const double be_true = GLOBAL ? be : be * (B.d / A.d);
-            {
-                const double EV = wa.h00 * V[1] + wa.h01 * V[2];
-                const double BV = wa.P * (V[2] - V[0]) + wa.Q * (V[3] - V[1]);
-                accv += ey * (EV + BV) + be * EV + be_true * BV;
-            }
+            const double be_true = GLOBAL ? w.be : p_mul(w.be, bscale);
+            const double EV = p_row2(wa.h00, wa.h01, V[1], V[2]);
+            const double BV = fma(wa.Q, p_sub(V[3], V[1]), p_mul(wa.P, p_sub(V[2], V[0])));
+            struct { double EV, BV, EVz, BVz, GXZ, GYZ, ey, be, bt, sy; } r = { EV, BV, 0, 0, 0, 0, w.ey, w.be, be_true, w.sy };
             if (WITH_DZ && !is_rho) {
-                const double EVz = wa.h00 * Vz[1] + wa.h01 * Vz[2];
-                const double BVz = wa.P * (Vz[2] - Vz[0]) + wa.Q * (Vz[3] - Vz[1]);
-                const double GXZ = wa.S0 * Gaz[1] + wa.S1 * Gaz[2];
-                const double GYZ = wa.h00 * Gbz[1] + wa.h01 * Gbz[2];
-                accz += ey * (EVz + GXZ) + be_true * BVz + sy * GYZ;
+                r.EVz = p_row2(wa.h00, wa.h01, Vz[1], Vz[2]);
+                r.BVz = fma(wa.Q, p_sub(Vz[3], Vz[1]), p_mul(wa.P, p_sub(Vz[2], Vz[0])));
+                r.GXZ = p_row2(wa.S0, wa.S1, Gaz[1], Gaz[2]);
+                r.GYZ = p_row2(wa.h00, wa.h01, Gbz[1], Gbz[2]);
+            }
+            return r;
+        };
+        auto accumulate = [&](const auto& r) {
+            av[0] = fma(r.bt, r.BV, fma(r.be, r.EV, fma(r.ey, p_add(r.EV, r.BV), av[0])));
+            if (WITH_DZ && !is_rho) av[1] = fma(r.sy, r.GYZ, fma(r.bt, r.BVz, fma(r.ey, p_add(r.EVz, r.GXZ), av[1])));
+        };
+        if (g.nrole == 1) {
+#pragma unroll
+            for (int jb = 0; jb < 4; jb++) accumulate(row(jb, B.off[jb]));
+        } else {
+            const int jb = g.role;
+            const unsigned boff = (jb == 0) ? B.off[0] : ((jb == 1) ? B.off[1] : ((jb == 2) ? B.off[2] : B.off[3]));
+            const auto r = row(jb, boff);
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {
+                if (k == jb) accumulate(r);
+                ms_group_take<2>(av, g, k);
             }
         }
+        const double accv = av[0], accz = av[1];
         vals[F] = accv;
         if (WITH_DZ && !is_rho) dz[F] = accz;
     }

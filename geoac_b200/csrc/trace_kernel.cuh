@@ -41,6 +41,9 @@ struct TraceArgs {
     unsigned long long* warp_trips;   // trips round the step loop, summed over warps (lane occupancy = steps / (32 trips))
     const uint32_t* order;            // claim order (longest-predicted first) or nullptr = natural order; 0xffffffff = empty slot
     int64_t n_claims;                 // entries of `order` (a multiple of 32 in packet mode), or n_rays
+    const uint32_t* n_long;           // packet mode: number of leading packets of `order` to trace four-lanes-per-ray from the start (or nullptr)
+    unsigned long long* counter_long; // next unclaimed entry of that leading region (claimed 8 rays at a time)
+    int packet_refill;                // experiment knob: refill a warp only when all of its lanes are idle (always on for PacketMode sets)
     double* prev;                     // y_{k-1} scratch: [NEQ][grid * block] doubles (variants with a quadratic intercept)
 };
 
@@ -265,7 +268,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
     // y_{k-1} history (quadratic intercept only): [eq][global thread] in an L2-resident global scratch, written once per step
     const int64_t pstride = (int64_t)gridDim.x * BLOCK;
     double* prev = a.prev + ((int64_t)blockIdx.x * BLOCK + threadIdx.x);
-    bool have_ray = false, exhausted = false;
+    bool have_ray = false, exhausted = false, long_done = false;
     unsigned long long my_steps = 0;
     unsigned my_trips = 0;
 
@@ -273,16 +276,36 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
         // ---------------- refill idle lanes (warp-aggregated claim) ----------------
         // PACKET sets (range dependent): a warp takes 32 rays with neighbouring launch angles at once and refills only
         // when all of them have ended, so its lanes walk through the same few grid cells and share their node data in L1.
-        const bool busy = PacketMode<EQ>::value && __any_sync(0xffffffffu, have_ray);
+        const bool busy = (PacketMode<EQ>::value || a.packet_refill) && __any_sync(0xffffffffu, have_ray);
         const bool want = !have_ray && !exhausted && !busy;
         const unsigned wmask = __ballot_sync(0xffffffffu, want);
         if (wmask) {
             unsigned long long base = 0;
+            int width = __popc(wmask);                                   // entries this claim takes
             const int leader = __ffs(wmask) - 1;
-            if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(wmask));
+            if ((int)lane == leader) {
+                bool got = false;
+                if (PacketMode<EQ>::value && a.n_long && !long_done) {
+                    // the longest packets are traced four lanes per ray from the start (see the straggler path below): a warp
+                    // takes a quarter packet, so the packet's critical path runs on four warps at ~2.4x the serial rate
+                    const unsigned long long nl = (unsigned long long)(*a.n_long) * 32ull;
+                    if (nl) {
+                        const unsigned long long q = atomicAdd(a.counter_long, 8ull);
+                        if (q < nl) { base = q; width = 8; got = true; }
+                    }
+                    if (!got) width = -width;                            // tells the warp that the leading region is used up
+                }
+                if (!got) {
+                    const unsigned long long nl = (PacketMode<EQ>::value && a.n_long) ? (unsigned long long)(*a.n_long) * 32ull : 0ull;
+                    base = nl + atomicAdd(a.counter, (unsigned long long)__popc(wmask));
+                }
+            }
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (want) {
-                const int64_t idx = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
+            width = __shfl_sync(0xffffffffu, width, leader);
+            if (width < 0) { long_done = true; width = -width; }
+            const int rank = __popc(wmask & ((1u << lane) - 1u));
+            if (want && rank < width) {
+                const int64_t idx = (int64_t)base + rank;
                 if (idx < a.n_claims) {
                     const int64_t r = a.order ? (int64_t)a.order[idx] : idx;
                     if (r < a.n_rays) { lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]); have_ray = true; }
@@ -290,8 +313,48 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
                 else exhausted = true;
             }
         }
-        if (!__any_sync(0xffffffffu, have_ray)) break;
+        const unsigned act = __ballot_sync(0xffffffffu, have_ray);
+        if (!act) break;
         my_trips++;
+        if constexpr (PacketMode<EQ>::value) {
+            // ---------------- straggler acceleration: <= 8 rays left in the packet -> four lanes per ray ----------------
+            // The lane records live in shared memory, so any lane can work on any ray of its warp: group g (lanes 4g..4g+3)
+            // advances the g-th live ray, each lane evaluating one row of the 4x4 node block per sample (mspline.cuh); every
+            // other operation is executed redundantly and identically by the four lanes.  Same bits as the serial path.
+            const int nact = __popc(act);
+            if (nact <= 8) {
+                const int grp = (int)lane >> 2;
+                const bool gact = grp < nact;
+                const int owner = gact ? (int)__fns(act, 0, grp + 1) : (int)lane;
+                LaneI<EQ> gi;
+                gi.cur.ka = __shfl_sync(0xffffffffu, li.cur.ka, owner); gi.cur.kb = __shfl_sync(0xffffffffu, li.cur.kb, owner);
+                gi.cur.kz = __shfl_sync(0xffffffffu, li.cur.kz, owner);
+                gi.bounce = __shfl_sync(0xffffffffu, li.bounce, owner); gi.ksteps = __shfl_sync(0xffffffffu, li.ksteps, owner);
+                gi.ray = __shfl_sync(0xffffffffu, (long long)li.ray, owner);
+                bool alive = false;
+                if (gact) {
+                    const int othread = (int)(threadIdx.x & ~31u) + owner;
+                    double* const rec = lanes + (size_t)othread * LaneLayout<EQ>::STRIDE;
+                    LaneD<EQ>& gd = *reinterpret_cast<LaneD<EQ>*>(rec);
+                    double* const gwork = rec + LaneLayout<EQ>::WORK;
+                    typename EQ::Atmo Tg = T;
+                    Tg.scratch = gwork + 2 * NEQ;
+                    Tg.role = (int)lane & 3; Tg.nrole = 4; Tg.glane0 = (int)lane & ~3; Tg.gmask = 0xFu << ((int)lane & ~3);
+                    alive = lane_advance<EQ>(gd, gi, L, Tg, a.prev + ((int64_t)blockIdx.x * BLOCK + othread), pstride, o, gwork);
+                }
+                const int src = have_ray ? 4 * __popc(act & ((1u << lane) - 1u)) : (int)lane;
+                const int bka = __shfl_sync(0xffffffffu, gi.cur.ka, src), bkb = __shfl_sync(0xffffffffu, gi.cur.kb, src);
+                const int bkz = __shfl_sync(0xffffffffu, gi.cur.kz, src);
+                const int bbo = __shfl_sync(0xffffffffu, gi.bounce, src), bks = __shfl_sync(0xffffffffu, gi.ksteps, src);
+                const int bal = __shfl_sync(0xffffffffu, (int)alive, src);
+                if (have_ray) {
+                    li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks;
+                    have_ray = bal != 0;
+                    my_steps++;
+                }
+                continue;
+            }
+        }
         if (have_ray) {
             have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o, work);
             my_steps++;
@@ -320,7 +383,7 @@ template <class EQ> struct ScoutBlock { static constexpr int value = std::is_sam
 // in registers.
 template <class EQ, bool TABLE_IN_SMEM>
 __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const __grid_constant__ TraceArgs a, uint32_t* cost, uint32_t* cost_max,
-                                                               unsigned long long* counter, int coarse) {
+                                                               unsigned long long* cost_sum, unsigned long long* counter, int coarse) {
     constexpr int NEQ = EQ::NEQ;
     constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -340,6 +403,7 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
     double y[NEQ], ym1[NEQ];
     typename EQ::RayC rc; typename EQ::Cursor cur = typename EQ::Cursor{};
     uint32_t est = 0, seg = 0, worst = 0; int bounce = 0; int64_t ray = 0;
+    unsigned long long total = 0;
     bool have_ray = false, exhausted = false;
     while (true) {
         const bool want = !have_ray && !exhausted;
@@ -385,14 +449,15 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
                 bounce++; seg = 0;
             }
         }
-        if (done) { cost[ray] = est; worst = max(worst, est); have_ray = false; }
+        if (done) { cost[ray] = est; worst = max(worst, est); total += est; have_ray = false; }
         else {
 #pragma unroll
             for (int i = 0; i < NEQ; i++) { ym1[i] = y[i]; y[i] = acc[i]; }
         }
     }
     worst = __reduce_max_sync(0xffffffffu, worst);
-    if (lane == 0 && worst) atomicMax(cost_max, worst);
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
+    if (lane == 0 && worst) { atomicMax(cost_max, worst); atomicAdd(cost_sum, total); }
 }
 
 // counting sort by predicted cost, descending: hist[b] of bucket(cost) -> start offsets -> scatter.  The sorted items are
@@ -406,16 +471,26 @@ __device__ __forceinline__ uint32_t group_cost(const uint32_t* cost, int64_t n, 
     for (int l = 0; l < group; l++) { const int64_t r = g * group + l; if (r < n) c = max(c, cost[r]); }
     return c;
 }
-__global__ void order_hist_kernel(const uint32_t* cost, int64_t n, int group, const uint32_t* cost_max, uint32_t* hist) {
+// Also counts the LONG groups: those whose predicted cost exceeds the average work of a lane (cost_sum / lanes) -- traced
+// serially such a packet alone would outlast the rest of the batch, so it is traced four lanes per ray instead.
+__global__ void order_hist_kernel(const uint32_t* cost, int64_t n, int group, const uint32_t* cost_max, uint32_t* hist,
+                                  const unsigned long long* cost_sum, long long lanes, uint32_t* n_long) {
     __shared__ uint32_t h[kCostBuckets];
+    __shared__ uint32_t nl;
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
+    if (threadIdx.x == 0) nl = 0;
     __syncthreads();
     const uint32_t cmax = *cost_max;
+    const unsigned long long thr = *cost_sum / (unsigned long long)lanes;
     const int64_t ng = (n + group - 1) / group;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(&h[cost_bucket(group_cost(cost, n, g, group), cmax)], 1u);
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = group_cost(cost, n, g, group);
+        atomicAdd(&h[cost_bucket(c, cmax)], 1u);
+        if (group == 32 && (unsigned long long)c > thr) atomicAdd(&nl, 1u);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
+    if (threadIdx.x == 0 && nl) atomicAdd(n_long, nl);
 }
 __global__ void order_scan_kernel(uint32_t* hist) {          // one block of kCostBuckets threads: exclusive prefix in place
     __shared__ uint32_t h[kCostBuckets];

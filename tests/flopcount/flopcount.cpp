@@ -83,7 +83,7 @@ extern "C" int flopcount_3d(int variant, const geoac_params* p, int n0, int n1, 
     build_grid_tables(glob, n0, n1, nz, a0.data(), a1.data(), az.data(), T_.data(), u_.data(), v_.data(), r_.data(), z, tuv, rh);
     Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = a0.data(); g.ax1 = a1.data(); g.axz = z.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
     g.amin = a0[0]; g.amax = a0[n0 - 1]; g.bmin = a1[0]; g.bmax = a1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
-    static Cnt scratch[MS_SCRATCH]; g.scratch = scratch;
+    static Cnt scratch[MS_SCRATCH]; g.scratch = scratch; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     LaunchConsts L; base_consts(L, variant, p);
     if (!glob) L.src[2] = std::max(p->z_grnd, p->src[2]); else L.src[0] = std::max(p->z_grnd, p->src[0]);
     fill_launch_consts_3d(L, g, variant);

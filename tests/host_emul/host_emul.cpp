@@ -68,7 +68,7 @@ extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1
     build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, Tf, uf, vf, rhof, z, tuv, rh);
     Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = ax0; g.ax1 = ax1; g.axz = z.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
-    static thread_local double scratch[MS_SCRATCH]; g.scratch = scratch;
+    static thread_local double scratch[MS_SCRATCH]; g.scratch = scratch; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
     L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
     L.z_grnd = p->z_grnd; L.tweak_abs = p->tweak_abs; L.freq = p->freq;
