@@ -207,14 +207,16 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax); ctx->d_tuv = ctx->d_rho = ctx->d_ax = nullptr;
     CK(cudaMalloc(&ctx->d_tuv, tuv.size() * sizeof(double)));
     CK(cudaMalloc(&ctx->d_rho, rh.size() * sizeof(double)));
-    CK(cudaMalloc(&ctx->d_ax, (size_t)(n0 + n1 + nz) * sizeof(double)));
+    std::vector<double> r0, r1, rz;
+    build_axis_records(ax0, n0, r0); build_axis_records(ax1, n1, r1); build_axis_records(z.data(), nz, rz);
+    CK(cudaMalloc(&ctx->d_ax, (size_t)(n0 + n1 + nz) * AX * sizeof(double)));
     CK(cudaMemcpy(ctx->d_tuv, tuv.data(), tuv.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_rho, rh.data(), rh.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ax, ax0, n0 * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ax + n0, ax1, n1 * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ax + n0 + n1, z.data(), nz * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ax, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ax + (size_t)n0 * AX, r1.data(), r1.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ax + (size_t)(n0 + n1) * AX, rz.data(), rz.size() * sizeof(double), cudaMemcpyHostToDevice));
     Grid3D& g = ctx->grid;
-    g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + n0; g.axz = ctx->d_ax + n0 + n1;
+    g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + (size_t)n0 * AX; g.axz = ctx->d_ax + (size_t)(n0 + n1) * AX;
     g.n0 = n0; g.n1 = n1; g.nz = nz; g.scratch = nullptr; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
     // GeoAc_SetPropRegion: G2S_MultiDimSpline3D.cpp:22-33 / G2S_GlobalMultiDimSpline3D.cpp:22-33

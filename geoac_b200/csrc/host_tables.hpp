@@ -35,6 +35,20 @@ inline void column_slopes(const double* z, int n, const double* vals, int vstrid
 }
 
 
+// Axis records (mspline.cuh): { x[k], 1/(x[k+1]-x[k]), 1/(x[k+1]-x[max(k-1,0)]), 1/(x[min(k+2,n-1)]-x[k]) } per node index.
+inline void build_axis_records(const double* x, int n, std::vector<double>& out) {
+    out.assign((size_t)n * AX, 0.0);
+    for (int k = 0; k < n; k++) {
+        const int km = std::max(k - 1, 0), kp = std::min(k + 2, n - 1), k1 = std::min(k + 1, n - 1);
+        out[(size_t)k * AX] = x[k];
+        if (k1 > k) {
+            out[(size_t)k * AX + 1] = 1.0 / (x[k1] - x[k]);
+            out[(size_t)k * AX + 2] = 1.0 / (x[k1] - x[km]);
+            out[(size_t)k * AX + 3] = 1.0 / (x[kp] - x[k]);
+        }
+    }
+}
+
 // Interleaved device layout (mspline.cuh): tuv[node][level][field]{f, slope, d/dax0 slope, d/dax1 slope, df/dax0, df/dax1},
 // rho[node][level]{f, slope}.
 // z receives the vertical coordinate as the kernel sees it (altitude, or r = altitude + r_earth for the Global variant).

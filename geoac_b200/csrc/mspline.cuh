@@ -43,6 +43,13 @@ constexpr int MS_SCRATCH = 30;
 
 struct Cur3 { int ka, kb, kz; };
 
+// Axis tables: one 32-byte record per node index k,
+//   { x[k], 1/(x[k+1]-x[k]), 1/(x[k+1]-x[max(k-1,0)]), 1/(x[min(k+2,n-1)]-x[k]) }
+// i.e. the coordinate and the three reciprocals a query in cell k needs (cell width, and the spans of the node differences
+// centred on nodes k and k+1).  The reference divides by these spans on every query; they depend on the cell only, so the
+// host computes them once with the same divisions (host_tables.hpp: build_axis_records) and a query does no division.
+constexpr int AX = 4;
+
 constexpr int MS_STRIDE = 18;      // doubles per node and level in `tuv`
 constexpr int MS_FIELD = 6;        // doubles per field inside a node record
 
@@ -50,33 +57,33 @@ constexpr int MS_FIELD = 6;        // doubles per field inside a node record
 // exactly on knot m lands in cell m-1 in the lower half of the axis and in cell m in the upper half.
 GEOAC_HD int ms_find_cold(const double* x, int n, double xq) {
     for (int i = 0; i < n; i++) {
-        if (xq >= x[i] && xq <= x[i + 1]) return i;
-        if (xq >= x[n - 2 - i] && xq < x[n - 1 - i]) return n - 2 - i;
+        if (xq >= x[AX * i] && xq <= x[AX * (i + 1)]) return i;
+        if (xq >= x[AX * (n - 2 - i)] && xq < x[AX * (n - 1 - i)]) return n - 2 - i;
     }
     return 0;
 }
 // warm cursor: stay in the current cell when the point is on one of its knots (the reference's first test)
 GEOAC_HD int ms_find_warm(const double* x, int n, double xq, int k) {
     k = (k < 0) ? 0 : ((k > n - 2) ? n - 2 : k);
-    while (xq < x[k]) --k;
-    while (xq > x[k + 1]) ++k;
+    while (xq < x[AX * k]) --k;
+    while (xq > x[AX * (k + 1)]) ++k;
     return k;
 }
 
 struct MsAxis {
     unsigned off[4];                     // element offsets of the 4 slot nodes (k-1, k, k+1, k+2 clamped)
     double r0, r1;                       // 1 / (x[up] - x[dn]) of the finite differences centred on nodes k and k+1
-    double d, t;                         // cell width, scaled coordinate
+    double d, inv_d, t;                  // cell width, its reciprocal, scaled coordinate
 };
 
 GEOAC_HD void ms_axis(MsAxis& A, const double* x, int n, int k, double xq, unsigned stride) {
     const int km = (k - 1 < 0) ? 0 : k - 1, kp = (k + 2 > n - 1) ? n - 1 : k + 2;
     A.off[0] = (unsigned)km * stride; A.off[1] = (unsigned)k * stride; A.off[2] = (unsigned)(k + 1) * stride; A.off[3] = (unsigned)kp * stride;
-    const double xm = x[km], x0 = x[k], x1 = x[k + 1], xp = x[kp];
-    A.r0 = 1.0 / (x1 - xm);              // node k:   up = k+1, dn = max(k-1, 0)
-    A.r1 = 1.0 / (xp - x0);              // node k+1: up = min(k+2, n-1), dn = k
-    A.d = x1 - x0;
-    A.t = (xq - x0) / A.d;
+    const Pair xd = ld_pair(x + AX * k), rr = ld_pair(x + AX * k + 2);     // (x[k], 1/d), (r0, r1)
+    A.r0 = rr.a; A.r1 = rr.b;
+    A.d = x[AX * (k + 1)] - xd.a;
+    A.inv_d = xd.b;
+    A.t = (xq - xd.a) * xd.b;
 }
 
 // 1-D weights of one axis: Hermite basis at t (and its t-derivative) combined with the corner finite differences
@@ -109,8 +116,9 @@ GEOAC_HD double ms_HXd(const MsW& w, double Q0, double Q1, double Q2, double Q3)
 struct MsZ { int kz; double cV1, cVa, cVb, cD1, cDa, cDb, cE1, cEa, cEb, cG1; };
 template <bool GLOBAL>
 GEOAC_HD void ms_zpos(MsZ& Z, const Grid3D& g, double z, int kz) {
-    const double z0 = g.axz[kz];
-    const double h = g.axz[kz + 1] - z0, invh = 1.0 / h;
+    const Pair zh = ld_pair(g.axz + AX * kz);                            // (z[k], 1/h)
+    const double z0 = zh.a, invh = zh.b;
+    const double h = g.axz[AX * (kz + 1)] - z0;
     const double X = (z - z0) * invh, omX = 1.0 - X, XomX = X * omX, om2X = 1.0 - 2.0 * X;
     Z.kz = kz;
     Z.cV1 = X - XomX * om2X;            Z.cVa = XomX * omX * h;           Z.cVb = -(XomX * X * h);
@@ -257,10 +265,10 @@ GEOAC_HD void ms_sample_tuv(const Grid3D& g, double a_in, double b_in, double z_
     ms_weights(wa, A, A.d);
     ms_weights(wb, B, B.d);
     // d2f/dz2 block: the Cartesian file scales the ax1 slope data by dx (App. A-8); Global uses dp
-    const double qs = GLOBAL ? 1.0 : A.d / B.d;
+    const double qs = GLOBAL ? 1.0 : A.d * B.inv_d;
     const unsigned kofs = (unsigned)cur.kz * MS_STRIDE;
 
-    const double ida = 1.0 / A.d, idb = 1.0 / B.d;
+    const double ida = A.inv_d, idb = B.inv_d;
 #pragma unroll 1
     for (int F = 0; F < 3; F++) {
         double acc[10];
@@ -321,7 +329,7 @@ GEOAC_HD void ms_wrappers(const Grid3D& g, double a_in, double b_in, double z_in
         const unsigned ko = is_rho ? (unsigned)cur.kz * 2u : kofs;
         const unsigned shr = is_rho ? (unsigned)(MS_STRIDE / 2) : 1u;   // node offsets were built for the tuv layout: /9 for the 2-double one
         double av[2] = { 0.0, 0.0 };               // value, d/dz
-        const double bscale = GLOBAL ? 1.0 : B.d / A.d;
+        const double bscale = GLOBAL ? 1.0 : B.d * A.inv_d;
         auto row = [&](int jb, unsigned boff) {
             double V[4], Vz[4], Gaz[4], Gbz[4];
 #pragma unroll

@@ -81,7 +81,9 @@ extern "C" int flopcount_3d(int variant, const geoac_params* p, int n0, int n1, 
     std::vector<Cnt> a0 = lift(ax0, n0), a1 = lift(ax1, n1), az = lift(axz, nz), T_ = lift(Tf, nodes), u_ = lift(uf, nodes), v_ = lift(vf, nodes), r_ = lift(rhof, nodes);
     std::vector<Cnt> z, tuv, rh;
     build_grid_tables(glob, n0, n1, nz, a0.data(), a1.data(), az.data(), T_.data(), u_.data(), v_.data(), r_.data(), z, tuv, rh);
-    Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = a0.data(); g.ax1 = a1.data(); g.axz = z.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
+    std::vector<Cnt> r0, r1, rz;
+    build_axis_records(a0.data(), n0, r0); build_axis_records(a1.data(), n1, r1); build_axis_records(z.data(), nz, rz);
+    Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = r0.data(); g.ax1 = r1.data(); g.axz = rz.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
     g.amin = a0[0]; g.amax = a0[n0 - 1]; g.bmin = a1[0]; g.bmax = a1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
     static Cnt scratch[MS_SCRATCH]; g.scratch = scratch; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     LaunchConsts L; base_consts(L, variant, p);

@@ -66,7 +66,9 @@ extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1
     const bool glob = variant == GEOAC_GLOBAL_RNGDEP;
     std::vector<double> z, tuv, rh;
     build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, Tf, uf, vf, rhof, z, tuv, rh);
-    Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = ax0; g.ax1 = ax1; g.axz = z.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
+    std::vector<double> r0, r1, rz;
+    build_axis_records(ax0, n0, r0); build_axis_records(ax1, n1, r1); build_axis_records(z.data(), nz, rz);
+    Grid3D g; g.tuv = tuv.data(); g.rho = rh.data(); g.ax0 = r0.data(); g.ax1 = r1.data(); g.axz = rz.data(); g.n0 = n0; g.n1 = n1; g.nz = nz;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
     static thread_local double scratch[MS_SCRATCH]; g.scratch = scratch; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
