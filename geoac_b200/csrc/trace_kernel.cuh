@@ -320,47 +320,45 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
         if (!act) break;
         my_trips++;
         if constexpr (PacketMode<EQ>::value) {
-            // ---------------- straggler acceleration: <= 8 rays left in the packet -> four lanes per ray ----------------
+            // ---------------- four lanes per ray when <= 8 rays of the packet are live ----------------
             // The lane records live in shared memory, so any lane can work on any ray of its warp: group g (lanes 4g..4g+3)
             // advances the g-th live ray, each lane evaluating one row of the 4x4 node block per sample (mspline.cuh); every
             // other operation is executed redundantly and identically by the four lanes.  Same bits as the serial path.
+            // One call site serves both modes (the step function is large; two inlined copies would double the kernel).
             const int nact = __popc(act);
-            if (nact <= 8) {
-                const int grp = (int)lane >> 2;
-                const bool gact = grp < nact;
-                const int owner = gact ? (int)__fns(act, 0, grp + 1) : (int)lane;
-                LaneI<EQ> gi;
-                gi.cur.ka = __shfl_sync(0xffffffffu, li.cur.ka, owner); gi.cur.kb = __shfl_sync(0xffffffffu, li.cur.kb, owner);
-                gi.cur.kz = __shfl_sync(0xffffffffu, li.cur.kz, owner);
-                gi.bounce = __shfl_sync(0xffffffffu, li.bounce, owner); gi.ksteps = __shfl_sync(0xffffffffu, li.ksteps, owner);
-                gi.ray = __shfl_sync(0xffffffffu, (long long)li.ray, owner);
-                bool alive = false;
-                if (gact) {
-                    const int othread = (int)(threadIdx.x & ~31u) + owner;
-                    double* const rec = lanes + (size_t)othread * LaneLayout<EQ>::STRIDE;
-                    LaneD<EQ>& gd = *reinterpret_cast<LaneD<EQ>*>(rec);
-                    double* const gwork = rec + LaneLayout<EQ>::WORK;
-                    typename EQ::Atmo Tg = T;
-                    Tg.scratch = gwork + 2 * NEQ;
-                    Tg.role = (int)lane & 3; Tg.nrole = 4; Tg.glane0 = (int)lane & ~3; Tg.gmask = 0xFu << ((int)lane & ~3);
-                    alive = lane_advance<EQ>(gd, gi, L, Tg, a.prev + ((int64_t)blockIdx.x * BLOCK + othread), pstride, o, gwork);
-                }
-                const int src = have_ray ? 4 * __popc(act & ((1u << lane) - 1u)) : (int)lane;
-                const int bka = __shfl_sync(0xffffffffu, gi.cur.ka, src), bkb = __shfl_sync(0xffffffffu, gi.cur.kb, src);
-                const int bkz = __shfl_sync(0xffffffffu, gi.cur.kz, src);
-                const int bbo = __shfl_sync(0xffffffffu, gi.bounce, src), bks = __shfl_sync(0xffffffffu, gi.ksteps, src);
-                const int bal = __shfl_sync(0xffffffffu, (int)alive, src);
-                if (have_ray) {
-                    li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks;
-                    have_ray = bal != 0;
-                    my_steps++;
-                }
-                continue;
+            const bool coop = nact <= 8;
+            const int grp = (int)lane >> 2;
+            const int owner = (coop && grp < nact) ? (int)__fns(act, 0, grp + 1) : (int)lane;
+            const bool run = coop ? (grp < nact) : have_ray;
+            LaneI<EQ> gi;
+            gi.cur.ka = __shfl_sync(0xffffffffu, li.cur.ka, owner); gi.cur.kb = __shfl_sync(0xffffffffu, li.cur.kb, owner);
+            gi.cur.kz = __shfl_sync(0xffffffffu, li.cur.kz, owner);
+            gi.bounce = __shfl_sync(0xffffffffu, li.bounce, owner); gi.ksteps = __shfl_sync(0xffffffffu, li.ksteps, owner);
+            gi.ray = __shfl_sync(0xffffffffu, (long long)li.ray, owner);
+            const int othread = (int)(threadIdx.x & ~31u) + owner;
+            double* const rec = lanes + (size_t)othread * LaneLayout<EQ>::STRIDE;
+            double* const gwork = rec + LaneLayout<EQ>::WORK;
+            typename EQ::Atmo Tg = T;
+            Tg.scratch = gwork + 2 * NEQ;
+            if (coop) { Tg.role = (int)lane & 3; Tg.nrole = 4; Tg.glane0 = (int)lane & ~3; Tg.gmask = 0xFu << ((int)lane & ~3); }
+            bool alive = false;
+            if (run) alive = lane_advance<EQ>(*reinterpret_cast<LaneD<EQ>*>(rec), gi, L, Tg, a.prev + ((int64_t)blockIdx.x * BLOCK + othread), pstride, o, gwork);
+            // hand the integer state back to the lane that owns the ray (itself in serial mode)
+            const int src = (coop && have_ray) ? 4 * __popc(act & ((1u << lane) - 1u)) : (int)lane;
+            const int bka = __shfl_sync(0xffffffffu, gi.cur.ka, src), bkb = __shfl_sync(0xffffffffu, gi.cur.kb, src);
+            const int bkz = __shfl_sync(0xffffffffu, gi.cur.kz, src);
+            const int bbo = __shfl_sync(0xffffffffu, gi.bounce, src), bks = __shfl_sync(0xffffffffu, gi.ksteps, src);
+            const int bal = __shfl_sync(0xffffffffu, (int)alive, src);
+            if (have_ray) {
+                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks;
+                have_ray = bal != 0;
+                my_steps++;
             }
-        }
-        if (have_ray) {
-            have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o, work);
-            my_steps++;
+        } else {
+            if (have_ray) {
+                have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o, work);
+                my_steps++;
+            }
         }
     }
     for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
