@@ -54,10 +54,11 @@ def _taper(z, width):
     return (2.0 / (1.0 + np.exp(-(z - 0.0) / width)) - 1.0) / 1000.0     # m/s -> km/s and ground taper (z_grnd = 0 at load)
 
 
-def config4_grid(nx=200, ny=200, nz=300):
-    """Cartesian range-dependent grid of config 4: x, y = -500 ... 500 km, z = 0 ... (nz-1)/2 km; fields [nx][ny][nz]."""
-    x = np.linspace(-500.0, 500.0, nx)
-    y = np.linspace(-500.0, 500.0, ny)
+def config4_grid(nx=200, ny=200, nz=300, x=None, y=None):
+    """Cartesian range-dependent grid of config 4: x, y = -500 ... 500 km (or the given node coordinates),
+    z = 0 ... (nz-1)/2 km; fields [nx][ny][nz]."""
+    x = np.linspace(-500.0, 500.0, nx) if x is None else np.asarray(x, dtype=np.float64)
+    y = np.linspace(-500.0, 500.0, ny) if y is None else np.asarray(y, dtype=np.float64)
     z = np.arange(nz) * 0.5
     T0, u0, v0, rho0, _ = base_profile(z)
     X, Y = x[:, None, None], y[None, :, None]
@@ -69,11 +70,11 @@ def config4_grid(nx=200, ny=200, nz=300):
     return x, y, z, np.ascontiguousarray(T), np.ascontiguousarray(u), np.ascontiguousarray(v), np.ascontiguousarray(rho)
 
 
-def config5_grid(nlat=181, nlon=361, nr=300):
-    """Global range-dependent grid of config 5: lat -90 ... 90, lon -180 ... 180 (radians, as the loader converts them),
-    altitude 0 ... (nr-1)/2 km; fields [nlat][nlon][nr]."""
-    lat = np.radians(np.linspace(-90.0, 90.0, nlat))
-    lon = np.radians(np.linspace(-180.0, 180.0, nlon))
+def config5_grid(nlat=181, nlon=361, nr=300, lat_deg=None, lon_deg=None):
+    """Global range-dependent grid of config 5: lat -90 ... 90, lon -180 ... 180 (or the given node coordinates in degrees;
+    returned in radians, as the loader converts them), altitude 0 ... (nr-1)/2 km; fields [nlat][nlon][nr]."""
+    lat = np.radians(np.linspace(-90.0, 90.0, nlat) if lat_deg is None else np.asarray(lat_deg, dtype=np.float64))
+    lon = np.radians(np.linspace(-180.0, 180.0, nlon) if lon_deg is None else np.asarray(lon_deg, dtype=np.float64))
     z = np.arange(nr) * 0.5
     T0, u0, v0, rho0, _ = base_profile(z)
     LA, LO = lat[:, None, None], lon[None, :, None]
@@ -83,3 +84,46 @@ def config5_grid(nlat=181, nlon=361, nr=300):
     v = (v0[None, None, :] + 8.0 * np.sin(5.0 * LO) * np.exp(-(((z - 50.0) / 20.0) ** 2))[None, None, :]) * tap * np.ones_like(LA)
     rho = np.broadcast_to(rho0[None, None, :], T.shape)
     return lat, lon, z, np.ascontiguousarray(T), np.ascontiguousarray(u), np.ascontiguousarray(v), np.ascontiguousarray(rho)
+
+
+# ---- the same atmospheres as .met node files (file units: m/s, g/cm^3, mbar), for the reference binaries / golden vectors ----
+def _raw_cart(x, y, z):
+    T0, u0, v0, rho0, p0 = base_profile(z)
+    T = T0 * (1.0 + 0.02 * np.sin(2 * np.pi * x / 700.0) * np.cos(2 * np.pi * y / 900.0))
+    u = u0 * (1.0 + 0.2 * np.cos(2 * np.pi * x / 600.0))
+    v = v0 + 8.0 * np.sin(2 * np.pi * y / 800.0) * np.exp(-(((z - 50.0) / 20.0) ** 2))
+    return T, u, v, rho0, p0
+
+
+def _raw_glob(lat, lon, z):
+    T0, u0, v0, rho0, p0 = base_profile(z)
+    T = T0 * (1.0 + 0.02 * np.sin(3.0 * lat) * np.cos(2.0 * lon))
+    u = u0 * np.cos(lat) ** 2 * (1.0 + 0.2 * np.cos(4.0 * lon))
+    v = v0 + 8.0 * np.sin(5.0 * lon) * np.exp(-(((z - 50.0) / 20.0) ** 2))
+    return T, u, v, rho0, p0
+
+
+def write_config4_files(outdir, xs, ys, nz=300, prefix="p"):
+    """Node files of a config-4 style grid on the given node coordinates (km): <prefix><ix*ny+iy>.met, x.loc, y.loc."""
+    import os
+    z = np.arange(nz) * 0.5
+    os.makedirs(outdir, exist_ok=True)
+    np.savetxt(os.path.join(outdir, "x.loc"), xs, fmt="%.6f")
+    np.savetxt(os.path.join(outdir, "y.loc"), ys, fmt="%.6f")
+    for ix, x in enumerate(xs):
+        for iy, y in enumerate(ys):
+            write_met(os.path.join(outdir, f"{prefix}{ix * len(ys) + iy}.met"), (z,) + _raw_cart(x, y, z))
+    return os.path.join(outdir, prefix), os.path.join(outdir, "x.loc"), os.path.join(outdir, "y.loc")
+
+
+def write_config5_files(outdir, lats_deg, lons_deg, nz=300, prefix="p"):
+    """Node files of a config-5 style grid on the given node coordinates (degrees): <prefix><it*np+ip>.met, lat.loc, lon.loc."""
+    import os
+    z = np.arange(nz) * 0.5
+    os.makedirs(outdir, exist_ok=True)
+    np.savetxt(os.path.join(outdir, "lat.loc"), lats_deg, fmt="%.6f")
+    np.savetxt(os.path.join(outdir, "lon.loc"), lons_deg, fmt="%.6f")
+    for it, la in enumerate(lats_deg):
+        for ip, lo in enumerate(lons_deg):
+            write_met(os.path.join(outdir, f"{prefix}{it * len(lons_deg) + ip}.met"), (z,) + _raw_glob(np.radians(la), np.radians(lo), z))
+    return os.path.join(outdir, prefix), os.path.join(outdir, "lat.loc"), os.path.join(outdir, "lon.loc")

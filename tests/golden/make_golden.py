@@ -22,7 +22,19 @@ TOY = os.path.join(GOLD, "ToyAtmo.met")
 
 # synthetic range-dependent grids (tests/golden/make_grid.py); sources are placed OFF the node lines on purpose: on a
 # node line the reference's cell choice depends on the spline cursor left behind by earlier look-ups
+from geoac_b200 import synth   # noqa: E402
+
+
+def _c3_profile(d):
+    path = os.path.join(d, "c3.met")
+    synth.write_met(path, synth.config3_profile())
+    return [path]
+
+
 GRIDS = {
+    # coarse node grids carrying the SAME analytic atmospheres bench.py uses for configs 4 / 5 (geoac_b200/synth.py)
+    "grid_c4": dict(is_global=False, build=lambda d: synth.write_config4_files(d, np.arange(-500.0, 501.0, 250.0), np.arange(-500.0, 501.0, 200.0), nz=300)),
+    "grid_c5": dict(is_global=True, build=lambda d: synth.write_config5_files(d, np.arange(25.0, 46.0, 5.0), np.arange(-12.0, 13.0, 4.0), nz=300)),
     "grid_cart": dict(is_global=False, build=lambda d: make_grid.write_cartesian(d, np.arange(-500.0, 501.0, 200.0), np.arange(-450.0, 451.0, 150.0))),
     "grid_glob": dict(is_global=True, build=lambda d: make_grid.write_global(d, np.arange(20.0, 51.0, 6.0), np.arange(-15.0, 16.0, 5.0))),
 }
@@ -50,6 +62,13 @@ CASES = {
                                                                     lat_src=33.3, lon_src=1.7)),
     "globalrngdep_noamp": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(theta_min=8, theta_max=30, theta_step=11, phi_min=30, phi_max=300, phi_step=135, bounces=1,
                                                                       lat_src=36.1, lon_src=-3.4, CalcAmp=0, accum_mode=1, z_src=2.5)),
+    # the synthetic atmospheres of BASELINE configs 3-5 themselves, on a few rays / a coarse node grid
+    "global_c3": (abi.GEOAC_GLOBAL, _c3_profile, dict(theta_min=4, theta_max=40, theta_step=12, phi_min=30, phi_max=300, phi_step=90, bounces=5,
+                                                     lat_src=30, lon_src=0, rng_max=3000)),
+    "3drngdep_c4": (abi.GEOAC_3D_RNGDEP, "grid_c4", dict(theta_min=6, theta_max=46, theta_step=20, phi_min=20, phi_max=200, phi_step=140, bounces=2,
+                                                         x_src=0, y_src=0)),
+    "globalrngdep_c5": (abi.GEOAC_GLOBAL_RNGDEP, "grid_c5", dict(theta_min=6, theta_max=46, theta_step=20, phi_min=20, phi_max=200, phi_step=140, bounces=2,
+                                                                 lat_src=35, lon_src=0)),
     "3d_elevated": (abi.GEOAC_3D, [TOY], dict(theta_min=-10, theta_max=40, theta_step=10, azimuth=-60, bounces=2, z_src=12.5, z_grnd=1.2, freq=0.5, rng_max=600, alt_max=120)),
 }
 
@@ -59,6 +78,9 @@ def main(names):
         variant, prof, kv = CASES[name]
         extra = {}
         with tempfile.TemporaryDirectory(dir="/tmp", prefix="g") as td:       # short paths: the reference's name buffers are char[50]
+            if callable(prof):
+                prof = prof(td)
+                extra["profile"] = "config3"
             if isinstance(prof, str):
                 grid = GRIDS[prof]
                 files = list(grid["build"](td))

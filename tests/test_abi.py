@@ -89,3 +89,28 @@ def test_no_cpu_fallback(built_lib):
     with pytest.raises(api.GeoAcError) as e:
         api.Tracer(abi.GEOAC_3D, 0)
     assert "no CUDA device" in str(e.value) or "failed (1)" in str(e.value)
+
+
+def test_synthetic_grids_match_their_node_files(built_lib, tmp_path):
+    """bench.py builds the config 4 / 5 atmospheres in memory (geoac_b200/synth.py); the golden vectors trace the same
+    formulas through .met node files and the reference's loader.  The two must agree to the files' text precision, so the
+    parity shown on the file-based cases carries over to the in-memory grids the full-size runs use."""
+    from geoac_b200 import synth
+    xs, ys = np.arange(-500.0, 501.0, 250.0), np.arange(-500.0, 501.0, 200.0)
+    files = synth.write_config4_files(str(tmp_path / "c4"), xs, ys, nz=40)
+    got = api.load_met_grid(*files, is_global=False)
+    want = synth.config4_grid(nz=40, x=xs, y=ys)
+    lats, lons = np.arange(25.0, 46.0, 5.0), np.arange(-12.0, 13.0, 4.0)
+    files5 = synth.write_config5_files(str(tmp_path / "c5"), lats, lons, nz=40)
+    got5 = api.load_met_grid(*files5, is_global=True)
+    want5 = synth.config5_grid(nr=40, lat_deg=lats, lon_deg=lons)
+    for g_, w_ in ((got, want), (got5, want5)):
+        names = ("ax0", "ax1", "axz", "T", "u", "v", "rho")
+        atol = dict(ax0=1e-6, ax1=1e-6, axz=1e-9, T=1e-6, u=2e-9, v=2e-9)        # %.6f text: 5e-7 in file units (winds m/s -> km/s)
+        for nm, a, b in zip(names, g_, w_):
+            a, b = np.asarray(a), np.asarray(b)
+            assert a.shape == b.shape, nm
+            if nm == "rho":
+                assert np.allclose(a, b, rtol=2e-6, atol=0.0), nm                   # %.6e text
+            else:
+                assert np.allclose(a, b, rtol=0.0, atol=atol[nm]), (nm, float(np.abs(a - b).max()))

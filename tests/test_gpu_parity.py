@@ -17,7 +17,7 @@ def _tracer_for(variant, kv, case=None):
     if util.is_rngdep(variant):
         tr.set_atmosphere_3d(*util.load_grid(case))
     else:
-        z, T, u, v, rho = g.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+        z, T, u, v, rho = g.load_met_1d(util.profile_path(case) if case is not None else util.TOY, global_taper=util.is_global(variant))
         tr.set_atmosphere_1d(z, T, u, v, rho)
     tr.params = util.apply_keys(variant, tr.params, kv)
     return tr

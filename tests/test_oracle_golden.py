@@ -13,7 +13,7 @@ def _run_oracle(po, name):
     if util.is_rngdep(variant):
         at = po.atmo3d(util.is_global(variant), *util.load_grid(d))
     else:
-        z, T, u, v, rho = po.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+        z, T, u, v, rho = po.load_met_1d(util.profile_path(d), global_taper=util.is_global(variant))
         at = po.atmo1d(util.is_global(variant), z, T, u, v, rho)
     p = util.apply_keys(variant, po.default_params(variant, at), kv)
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
@@ -47,7 +47,8 @@ def test_golden_has_reference_invariants():
     assert np.allclose(r[:, 2] / r[:, 0], 3.0, rtol=2e-3)
 
 
-@pytest.mark.parametrize("name", ["3d_elevated", "2d_noamp", "3d_noamp", "global_segmode", "3drngdep_sub", "globalrngdep_sub"])
+@pytest.mark.parametrize("name", ["3d_elevated", "2d_noamp", "3d_noamp", "global_segmode", "3drngdep_sub", "globalrngdep_sub",
+                                  "global_c3", "3drngdep_c4", "globalrngdep_c5"])
 def test_device_math_host_emulation(oracle, name):
     """The per-ray device code (geoac_b200/csrc/*.cuh, GEOAC_HD) compiled with g++ -mfma must agree with the reference
     golden vectors to the GPU tolerance.  This is a build-container debugging aid, not a product path; the real gate
@@ -62,7 +63,7 @@ def test_device_math_host_emulation(oracle, name):
         p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
         out = emul.trace_grid(variant, p, arrs, th, ph)
     else:
-        arrs = oracle.load_met_1d(util.TOY, global_taper=util.is_global(variant))
+        arrs = oracle.load_met_1d(util.profile_path(d), global_taper=util.is_global(variant))
         at = oracle.atmo1d(util.is_global(variant), *arrs)
         p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
         out = emul.trace(variant, p, arrs, th, ph)

@@ -31,6 +31,18 @@ def load_grid(d):
     return [g[k] for k in ("ax0", "ax1", "axz", "T", "u", "v", "rho")]
 
 
+def profile_path(d, tmpdir=None):
+    """The .met profile a stratified golden case was traced on: the shipped ToyAtmo.met, or the synthetic config-3 profile
+    (geoac_b200/synth.py) written to a temporary file exactly as the golden generator wrote it."""
+    if "profile" in d.files and str(d["profile"]) == "config3":
+        import tempfile
+        from geoac_b200 import synth
+        path = os.path.join(tmpdir or tempfile.mkdtemp(prefix="g"), "c3.met")
+        synth.write_met(path, synth.config3_profile())
+        return path
+    return TOY
+
+
 def load_case(name):
     d = np.load(os.path.join(GOLD, name + ".npz"))
     kv = dict(s.split("=", 1) for s in d["keys"].tolist())
