@@ -233,7 +233,7 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
 __global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, const double* table, int n,
                                     double xmin, double xmax, int variant) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    Table1D T; T.base = table; T.n = n; T.xmin = xmin; T.xmax = xmax;
+    Table1D T; T.base = table; T.n = n; T.xmin = xmin; T.xmax = xmax; T.jump_scale = 0.0;
     LaunchConsts L = in;
     fill_launch_consts_1d(L, T, variant);
     *out = L;

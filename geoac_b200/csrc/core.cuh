@@ -155,6 +155,7 @@ struct Table1D {
     const double* base;     // shared or global memory, 16-byte aligned on the device
     int n;
     double xmin, xmax;
+    double jump_scale;      // > 0 (cost scout only): (n-1)/(xmax-xmin), lets a far query jump near its interval before the walk
     GEOAC_HD const double* lvl(int k) const { return base + (size_t)k * TAB_NARR; }
 };
 
@@ -182,6 +183,11 @@ GEOAC_HD SegPos seg_locate(const Table1D& t, double xq, int& k) {
     double xc = xq;
     if (!(xq >= lo.a && xq <= x1)) {
         xc = clampd(xq, t.xmin, t.xmax);
+        if (t.jump_scale > 0.0) {            // the scout strides many levels per stage; knot tie-breaking does not matter to it
+            int kg = (int)((xc - t.xmin) * t.jump_scale);
+            kg = (kg < 0) ? 0 : ((kg > t.n - 2) ? t.n - 2 : kg);
+            k = kg; r = t.lvl(k); lo = ld_pair(r); x1 = r[TAB_NARR];
+        }
         while (xc < lo.a) { --k; r -= TAB_NARR; x1 = lo.a; lo = ld_pair(r); }
         while (xc > x1)   { ++k; r += TAB_NARR; lo = ld_pair(r); x1 = r[TAB_NARR]; }
     }

@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
         T = a.grid;
         T.scratch = work + 2 * NEQ;
     } else {
-        T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax;
+        T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.jump_scale = 0.0;
         if (TABLE_IN_SMEM) {
             tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_n * sizeof(double)), bar);
             T.base = tab_s;
@@ -396,6 +396,7 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
     if constexpr (kGrid) { T = a.grid; T.scratch = sbuf; }
     else {
         T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.base = a.table;
+        T.jump_scale = (double)(a.table_n - 1) / (a.table_xmax - a.table_xmin);
         if (TABLE_IN_SMEM) { tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_n * sizeof(double)), bar); T.base = tab_s; }
     }
     __syncthreads();

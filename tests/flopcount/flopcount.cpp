@@ -60,7 +60,7 @@ static void run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const
 // 1-D variants: table = n records of TAB_NARR doubles (as geoac_set_atmosphere_1d builds it)
 extern "C" int flopcount_1d(int variant, const geoac_params* p, int n, const double* table, long n_rays, const double* th, const double* ph) {
     std::vector<Cnt> tab(table, table + (size_t)n * TAB_NARR);
-    Table1D T; T.base = tab.data(); T.n = n; T.xmin = tab[TAB_X]; T.xmax = tab[(size_t)(n - 1) * TAB_NARR + TAB_X];
+    Table1D T; T.base = tab.data(); T.n = n; T.xmin = tab[TAB_X]; T.xmax = tab[(size_t)(n - 1) * TAB_NARR + TAB_X]; T.jump_scale = 0.0;
     LaunchConsts L; base_consts(L, variant, p);
     if (variant == GEOAC_2D || variant == GEOAC_3D) L.src[2] = std::max(p->z_grnd, p->src[2]); else L.src[0] = std::max(p->z_grnd, p->src[0]);
     fill_launch_consts_1d(L, T, variant);

@@ -33,7 +33,7 @@ static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const
 
 extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const double* table, long n_rays,
                               const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps) {
-    Table1D T; T.base = table; T.n = n; T.xmin = table[TAB_X]; T.xmax = table[(size_t)(n - 1) * TAB_NARR + TAB_X];
+    Table1D T; T.base = table; T.n = n; T.xmin = table[TAB_X]; T.xmax = table[(size_t)(n - 1) * TAB_NARR + TAB_X]; T.jump_scale = 0.0;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
     L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
     L.z_grnd = p->z_grnd; L.tweak_abs = p->tweak_abs; L.freq = p->freq;
