@@ -47,6 +47,7 @@ def lib():
         L.geoac_get_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
         L.geoac_set_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
         L.geoac_trace.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip]
+        L.geoac_trace_paths.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int64, _dp, _ip]
         L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.geoac_reserve.argtypes = [C.c_void_p, C.c_int64]
         L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -64,7 +65,7 @@ def lib():
 
 EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
-    "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_device",
+    "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
 ]
 
@@ -175,6 +176,20 @@ class Tracer:
                    "n_steps": np.empty((n, n_rec), dtype=np.int32)}
         self._check(lib().geoac_trace(self._h, n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip),
                                       out["n_steps"].ctypes.data_as(_ip)), "geoac_trace")
+        return out
+
+    def trace_paths(self, theta, phi, stride=25, cap=2400):
+        """trace() plus the raypath rows of WriteRays=True: adds path [n][cap][PATH_NF] and path_rows [n] to the result."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        n = len(theta)
+        n_rec = self.params.bounces + 1
+        out = {"rec": np.empty((abi.NFIELDS, n, n_rec)), "status": np.empty((n, n_rec), dtype=np.int32),
+               "n_steps": np.empty((n, n_rec), dtype=np.int32), "path": np.zeros((n, cap, abi.PATH_NF)),
+               "path_rows": np.zeros(n, dtype=np.int32)}
+        self._check(lib().geoac_trace_paths(self._h, n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip),
+                                            out["n_steps"].ctypes.data_as(_ip), stride, cap, _p(out["path"]),
+                                            out["path_rows"].ctypes.data_as(_ip)), "geoac_trace_paths")
         return out
 
     def reserve(self, n_rays):

@@ -44,6 +44,7 @@ struct geoac_ctx {
     LaunchConsts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;     // [0] ray counter, [1] total steps
     double* d_prev = nullptr; size_t cap_prev = 0; // y_{k-1} scratch of the trace kernel
+    double* d_path = nullptr; size_t cap_path = 0; int32_t* d_path_rows = nullptr; int64_t cap_path_rows = 0;   // raypath capture staging
     uint32_t *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr; int64_t cap_order = 0;   // longest-ray-first scheduling
     int last_launches = 0;
     // staging for the host-buffer entry point
@@ -111,7 +112,7 @@ extern "C" void geoac_destroy(geoac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters); cudaFree(ctx->d_prev);
-    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist);
+    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows);
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -269,7 +270,7 @@ static int refresh_consts(geoac_ctx* ctx) {
 }
 
 // ---- kernel launch ----
-template <class EQ, int BLOCK>
+template <class EQ, int BLOCK, bool PATHS = false>
 static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
     const size_t lane_doubles = ((size_t)LaneLayout<EQ>::STRIDE * BLOCK + 1) & ~(size_t)1;
@@ -280,7 +281,10 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     if (fixed > (size_t)max_optin) return fail(ctx, GEOAC_ERR_CUDA, "lane records do not fit in shared memory");
     const bool in_smem = !kGrid && fixed + tab_bytes <= (size_t)max_optin;
     const size_t smem = in_smem ? fixed + tab_bytes : fixed;
-    const void* fn = in_smem ? (const void*)trace_kernel<EQ, BLOCK, true> : (const void*)trace_kernel<EQ, BLOCK, false>;
+    if (PATHS && !kGrid && !in_smem) return fail(ctx, GEOAC_ERR_TOO_LARGE, "raypath capture needs the profile table in shared memory");
+    const void* fn;
+    if constexpr (PATHS) fn = (const void*)trace_kernel<EQ, BLOCK, !kGrid, true>;
+    else fn = in_smem ? (const void*)trace_kernel<EQ, BLOCK, true> : (const void*)trace_kernel<EQ, BLOCK, false>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BLOCK, smem));
@@ -353,8 +357,10 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     return GEOAC_OK;
 }
 
+struct PathArgs { double* path = nullptr; int32_t* rows = nullptr; int stride = 0; int64_t cap = 0; };
+
 static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
-                         double* d_rec, int32_t* d_status, int32_t* d_n_steps, cudaStream_t st) {
+                         double* d_rec, int32_t* d_status, int32_t* d_n_steps, cudaStream_t st, const PathArgs& pa = PathArgs()) {
     if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");
     int rc = refresh_consts(ctx);
     if (rc) return rc;
@@ -374,7 +380,17 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     a.consts = ctx->d_consts; a.theta = d_theta; a.phi = d_phi; a.n_rays = n_rays; a.n_rec = n_rec;
     a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
     a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1; a.warp_trips = ctx->d_counters + 2;
+    a.path = pa.path; a.path_rows = pa.rows; a.path_stride = pa.stride; a.path_cap = pa.cap;
     const bool amp = ctx->prm.calc_amp != 0;
+    if (pa.stride > 0) {          // raypath capture: the PATHS instantiations (same lanes per SM as the plain ones)
+        switch (ctx->variant) {
+            case GEOAC_2D:     return amp ? launch_trace<Eq2D<true>, 512, true>(ctx, a, st)     : launch_trace<Eq2D<false>, 512, true>(ctx, a, st);
+            case GEOAC_3D:     return amp ? launch_trace<Eq3D<true>, 384, true>(ctx, a, st)     : launch_trace<Eq3D<false>, 512, true>(ctx, a, st);
+            case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 384, true>(ctx, a, st) : launch_trace<EqGlobal<false>, 512, true>(ctx, a, st);
+            case GEOAC_3D_RNGDEP:     return amp ? launch_trace<Eq3DRD<true>, 128, true>(ctx, a, st)     : launch_trace<Eq3DRD<false>, 128, true>(ctx, a, st);
+            case GEOAC_GLOBAL_RNGDEP: return amp ? launch_trace<EqGlobalRD<true>, 128, true>(ctx, a, st) : launch_trace<EqGlobalRD<false>, 128, true>(ctx, a, st);
+        }
+    }
     switch (ctx->variant) {
         case GEOAC_2D:     return amp ? launch_trace<Eq2D<true>, 512>(ctx, a, st)     : launch_trace<Eq2D<false>, 512>(ctx, a, st);
         case GEOAC_3D: {
@@ -427,9 +443,12 @@ extern "C" int geoac_reserve(geoac_ctx* ctx, int64_t n_rays) {
     return reserve_staging(ctx, n_rays);
 }
 
-extern "C" int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
-                           double* rec, int32_t* status, int32_t* n_steps) {
+static int trace_host(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                      double* rec, int32_t* status, int32_t* n_steps, int path_stride, int64_t path_cap, double* path, int32_t* path_rows) {
     if (!ctx || n_rays < 0 || (n_rays > 0 && (!theta || !phi || !rec || !status || !n_steps))) return GEOAC_ERR_BAD_ARG;
+    if (path_stride > 0 && (path_cap <= 0 || !path || !path_rows)) return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath capture needs path buffers and a positive row capacity");
+    if (path_stride > 0 && ctx->variant != GEOAC_2D && !ctx->prm.accum_per_segment)
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath rows need accum_per_segment = 1 (the mains' WriteRays accumulation, SURVEY App. A-2)");
     if (n_rays == 0) return GEOAC_OK;
     if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");
     cudaSetDevice(ctx->device);
@@ -437,24 +456,57 @@ extern "C" int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, 
     const int64_t n_slots = n_rays * n_rec;
     int rsv = reserve_staging(ctx, n_rays);
     if (rsv) return rsv;
+    PathArgs pa;
     cudaStream_t st = ctx->stream;
+    if (path_stride > 0) {
+        const size_t need = (size_t)n_rays * path_cap * GEOAC_PATH_NF * sizeof(double);
+        if (need > ctx->cap_path) {
+            cudaFree(ctx->d_path); ctx->d_path = nullptr; ctx->cap_path = 0;
+            CK(cudaMalloc(&ctx->d_path, need));
+            ctx->cap_path = need;
+        }
+        if (n_rays > ctx->cap_path_rows) {
+            cudaFree(ctx->d_path_rows); ctx->d_path_rows = nullptr; ctx->cap_path_rows = 0;
+            CK(cudaMalloc(&ctx->d_path_rows, sizeof(int32_t) * n_rays));
+            ctx->cap_path_rows = n_rays;
+        }
+        CK(cudaMemsetAsync(ctx->d_path, 0, need, st));
+        CK(cudaMemsetAsync(ctx->d_path_rows, 0, sizeof(int32_t) * n_rays, st));
+        pa.path = ctx->d_path; pa.rows = ctx->d_path_rows; pa.stride = path_stride; pa.cap = path_cap;
+    }
     CK(cudaMemcpyAsync(ctx->d_theta, theta, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_phi, phi, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
     int rc = refresh_consts(ctx);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev0, st));
-    rc = enqueue_trace(ctx, n_rays, ctx->d_theta, ctx->d_phi, ctx->d_rec, ctx->d_status, ctx->d_nsteps, st);
+    rc = enqueue_trace(ctx, n_rays, ctx->d_theta, ctx->d_phi, ctx->d_rec, ctx->d_status, ctx->d_nsteps, st, pa);
     if (rc) return rc;
     CK(cudaEventRecord(ctx->ev1, st));
     CK(cudaMemcpyAsync(rec, ctx->d_rec, sizeof(double) * GEOAC_NFIELDS * n_slots, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, ctx->d_status, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(n_steps, ctx->d_nsteps, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, st));
+    if (path_stride > 0) {
+        CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)n_rays * path_cap * GEOAC_PATH_NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(path_rows, ctx->d_path_rows, sizeof(int32_t) * n_rays, cudaMemcpyDeviceToHost, st));
+    }
     unsigned long long cnt[2] = { 0, 0 };
     CK(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
     ctx->last_ms = ms; ctx->last_steps = (int64_t)cnt[1];
     return GEOAC_OK;
+}
+
+extern "C" int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                           double* rec, int32_t* status, int32_t* n_steps) {
+    return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, 0, 0, nullptr, nullptr);
+}
+
+extern "C" int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                                 double* rec, int32_t* status, int32_t* n_steps,
+                                 int path_stride, int64_t path_cap, double* path, int32_t* path_rows) {
+    if (path_stride <= 0) return ctx ? fail(ctx, GEOAC_ERR_BAD_ARG, "path_stride must be positive") : GEOAC_ERR_BAD_ARG;
+    return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, path_stride, path_cap, path, path_rows);
 }
 
 extern "C" int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_ms) {

@@ -152,6 +152,29 @@ struct Eq3D {
         }
     }
 
+    // GeoAc_Amplitude at an arbitrary state (also evaluated along the path for the raypath rows)
+    GEOAC_HD static double amplitude(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
+        if (!AMP) return 0.0;
+        const SegPos sp = seg_locate(T, yk[2], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
+        const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
+        const double rho = spl_f(T, TAB_RHO, sp);
+        const double c0 = L.c_src, u0 = L.u_src, v0 = L.v_src;
+        const double nz = yk[3];
+        const double nu_mag = (c0 - rc.nx * u - rc.ny * v) / c;
+        const double nu_mag0 = 1.0 - (rc.nx * u0 - rc.ny * v0) / c0;             // sign slip kept (App. A-5)
+        const double cp[3] = { c * rc.nx / nu_mag + u, c * rc.ny / nu_mag + v, c * nz / nu_mag };
+        const double ax = rc.nx / nu_mag0, ay = rc.ny / nu_mag0;
+        const double cq[3] = { c0 * ax + u0, c0 * ay + v0, c0 * sqrt(1.0 - ax * ax - ay * ay) };
+        const double cpm = sqrt(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]);
+        const double cqm = sqrt(cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2]);
+        const double xs = cp[0] / cpm, ys = cp[1] / cpm, zs = cp[2] / cpm;
+        const double D = xs * (yk[5] * yk[10] - yk[9] * yk[6]) - yk[4] * (ys * yk[10] - zs * yk[9]) + yk[8] * (ys * yk[6] - zs * yk[5]);
+        const double num = rho * nu_mag * (c * c * c) * cqm * rc.costh;
+        const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
+        return 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
+    }
+
     // GeoAc_Jacobian + GeoAc_Amplitude (3DStratified.cpp:410-451) and the results row of GeoAc3D_main.cpp:281-298
     GEOAC_HD static void arrival(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ym1, const double* yk,
                                  double tt, int& cur, double& amp, double& incl, double& backaz, double& aux, double& margin) {
@@ -162,27 +185,7 @@ struct Eq3D {
         while (b < -180.0) b += 360.0;
         backaz = b; aux = 0.0;
         margin = (yk[2] - L.z_grnd) / fabs(yk[2] - ym1[2]);
-        amp = 0.0;
-        if (AMP) {
-            const SegPos sp = seg_locate(T, yk[2], cur);
-            const double c = sound_speed0(spl_f(T, TAB_T, sp));
-            const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
-            const double rho = spl_f(T, TAB_RHO, sp);
-            const double c0 = L.c_src, u0 = L.u_src, v0 = L.v_src;
-            const double nz = yk[3];
-            const double nu_mag = (c0 - rc.nx * u - rc.ny * v) / c;
-            const double nu_mag0 = 1.0 - (rc.nx * u0 - rc.ny * v0) / c0;             // sign slip kept (App. A-5)
-            const double cp[3] = { c * rc.nx / nu_mag + u, c * rc.ny / nu_mag + v, c * nz / nu_mag };
-            const double ax = rc.nx / nu_mag0, ay = rc.ny / nu_mag0;
-            const double cq[3] = { c0 * ax + u0, c0 * ay + v0, c0 * sqrt(1.0 - ax * ax - ay * ay) };
-            const double cpm = sqrt(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]);
-            const double cqm = sqrt(cq[0] * cq[0] + cq[1] * cq[1] + cq[2] * cq[2]);
-            const double xs = cp[0] / cpm, ys = cp[1] / cpm, zs = cp[2] / cpm;
-            const double D = xs * (yk[5] * yk[10] - yk[9] * yk[6]) - yk[4] * (ys * yk[10] - zs * yk[9]) + yk[8] * (ys * yk[6] - zs * yk[5]);
-            const double num = rho * nu_mag * (c * c * c) * cqm * rc.costh;
-            const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
-            amp = 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
-        }
+        amp = amplitude(L, T, rc, yk, cur);
     }
 };
 
@@ -286,21 +289,24 @@ struct Eq2D {
         }
     }
 
+    // GeoAc_Amplitude at an arbitrary state (also evaluated along the path for the raypath rows)
+    GEOAC_HD static double amplitude(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
+        if (!AMP) return 0.0;
+        const SegPos sp = seg_locate(T, yk[1], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
+        const double rho = spl_f(T, TAB_RHO, sp);
+        const double drds = c / rc.ceff0 * rc.costh, dzds = c / rc.ceff0 * yk[2];
+        const double D = yk[0] * (drds * yk[4] - dzds * yk[3]);
+        return 1.0 / (4.0 * kPi) * sqrt(fabs((rho * c * rc.costh) / (L.rho_gnd * rc.ceff0 * D)));
+    }
+
     // GeoAc_Jacobian + GeoAc_Amplitude, 2DStratified.cpp:291-312; results row GeoAc2D_main.cpp:216-226
     GEOAC_HD static void arrival(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ym1, const double* yk,
                                  double tt, int& cur, double& amp, double& incl, double& backaz, double& aux, double& margin) {
         (void)tt;
         incl = -rc.theta_deg; backaz = 0.0; aux = 0.0;
         margin = (yk[1] - L.z_grnd) / fabs(yk[1] - ym1[1]);
-        amp = 0.0;
-        if (AMP) {
-            const SegPos sp = seg_locate(T, yk[1], cur);
-            const double c = sound_speed0(spl_f(T, TAB_T, sp));
-            const double rho = spl_f(T, TAB_RHO, sp);
-            const double drds = c / rc.ceff0 * rc.costh, dzds = c / rc.ceff0 * yk[2];
-            const double D = yk[0] * (drds * yk[4] - dzds * yk[3]);
-            amp = 1.0 / (4.0 * kPi) * sqrt(fabs((rho * c * rc.costh) / (L.rho_gnd * rc.ceff0 * D)));
-        }
+        amp = amplitude(L, T, rc, yk, cur);
     }
 };
 

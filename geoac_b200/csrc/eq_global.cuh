@@ -191,6 +191,40 @@ struct EqGlobal {
         }
     }
 
+    // GeoAc_Amplitude at an arbitrary state (Global.cpp:594-629; also evaluated along the path for the raypath rows)
+    GEOAC_HD static double amplitude(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
+        if (!AMP) return 0.0;
+        const SegPos sp = seg_locate(T, yk[0], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
+        const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
+        const double rho = spl_f(T, TAB_RHO, sp);
+        const double r = yk[0], th = yk[1];
+        const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
+        double sl, cl; sincos(th, &sl, &cl);
+        // Jacobian: c_prop with |nu| = sqrt(nu.nu); dp/ds carries 1/(r sin lat) while the volume factor is
+        // r^2 cos lat (App. A-6)
+        {
+            const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
+            const double q0 = c * nu0 / nm, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm + u;
+            const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+            const double dr_ds = q0 / qm, dt_ds = 1.0 / r * q1 / qm, dp_ds = 1.0 / (r * sl) * q2 / qm;
+            const double D = r * r * cl * (dr_ds * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (dt_ds * yk[14] - dp_ds * yk[13])
+                                           + yk[12] * (dt_ds * yk[8] - dp_ds * yk[7]));
+            // amplitude: eikonal |nu| = (c0 - nu.v)/c; source c_prop0[1..2] divided by nu_mag, not nu_mag0 (App. A-6)
+            const double c0 = L.c_src;
+            const double n0v[3] = { rc.sth, rc.cth * rc.sph, rc.cth * rc.cph };
+            const double nu_mag = (c0 - nu1 * v - nu2 * u) / c;
+            const double nu_mag0 = rc.nu0;
+            const double cp0 = c * nu0 / nu_mag, cp1 = c * nu1 / nu_mag + v, cp2 = c * nu2 / nu_mag + u;
+            const double cs0 = c0 * n0v[0] / nu_mag0, cs1 = c0 * n0v[1] / nu_mag + L.v_src, cs2 = c0 * n0v[2] / nu_mag + L.u_src;
+            const double cpm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
+            const double csm = sqrt(cs0 * cs0 + cs1 * cs1 + cs2 * cs2);
+            const double num = rho * nu_mag * (c * c * c) * csm * rc.cth;
+            const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
+            return 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
+        }
+    }
+
     // GeoAc_Jacobian + GeoAc_Amplitude (Global.cpp:594-629) and the results row of GeoAcGlobal_main.cpp:294-317
     GEOAC_HD static void arrival(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ym1, const double* yk,
                                  double tt, int& cur, double& amp, double& incl, double& backaz, double& aux, double& margin) {
@@ -205,36 +239,7 @@ struct EqGlobal {
         const double h = s1 * s1 + rc.cos_lat_src * cos(yk[1]) * (s2 * s2);
         aux = 2.0 * kREarth * asin(sqrt(h)) / tt;                                      // celerity
         margin = (yk[0] - L.ground) / fabs(yk[0] - ym1[0]);
-        amp = 0.0;
-        if (AMP) {
-            const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
-            const double rho = spl_f(T, TAB_RHO, sp);
-            const double r = yk[0], th = yk[1];
-            const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
-            double sl, cl; sincos(th, &sl, &cl);
-            // Jacobian: c_prop with |nu| = sqrt(nu.nu); dp/ds carries 1/(r sin lat) while the volume factor is
-            // r^2 cos lat (App. A-6)
-            {
-                const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
-                const double q0 = c * nu0 / nm, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm + u;
-                const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
-                const double dr_ds = q0 / qm, dt_ds = 1.0 / r * q1 / qm, dp_ds = 1.0 / (r * sl) * q2 / qm;
-                const double D = r * r * cl * (dr_ds * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (dt_ds * yk[14] - dp_ds * yk[13])
-                                               + yk[12] * (dt_ds * yk[8] - dp_ds * yk[7]));
-                // amplitude: eikonal |nu| = (c0 - nu.v)/c; source c_prop0[1..2] divided by nu_mag, not nu_mag0 (App. A-6)
-                const double c0 = L.c_src;
-                const double n0v[3] = { rc.sth, rc.cth * rc.sph, rc.cth * rc.cph };
-                const double nu_mag = (c0 - nu1 * v - nu2 * u) / c;
-                const double nu_mag0 = rc.nu0;
-                const double cp0 = c * nu0 / nu_mag, cp1 = c * nu1 / nu_mag + v, cp2 = c * nu2 / nu_mag + u;
-                const double cs0 = c0 * n0v[0] / nu_mag0, cs1 = c0 * n0v[1] / nu_mag + L.v_src, cs2 = c0 * n0v[2] / nu_mag + L.u_src;
-                const double cpm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
-                const double csm = sqrt(cs0 * cs0 + cs1 * cs1 + cs2 * cs2);
-                const double num = rho * nu_mag * (c * c * c) * csm * rc.cth;
-                const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
-                amp = 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
-            }
-        }
+        amp = amplitude(L, T, rc, yk, cur);
     }
 };
 

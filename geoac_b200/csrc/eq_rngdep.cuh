@@ -160,6 +160,32 @@ struct Eq3DRD {
         }
     }
 
+    // GeoAc_Amplitude at an arbitrary state (3DRngDep.cpp:547-592; also evaluated along the path for the raypath rows)
+    GEOAC_HD static double amplitude(const LaunchConsts& L, const Grid3D& G, const RayC& rc, const double* yk, Cur3& cur) {
+        if (!AMP) return 0.0;
+        double w[4], dzs[3];
+        ms_wrappers<false, true, false>(G, yk[0], yk[1], yk[2], cur, w, dzs);
+        const double c = sqrt(kGamR * w[0]), u = w[1], v = w[2], rho = w[3];
+        const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
+        const double c0 = L.c_src, u0 = L.u_src, v0 = L.v_src;
+        double D;
+        {
+            const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
+            const double q0 = c * nu0 / nm + u, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm;
+            const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+            const double xs = q0 / qm, ys = q1 / qm, zs = q2 / qm;
+            D = xs * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (ys * yk[14] - zs * yk[13]) + yk[12] * (ys * yk[8] - zs * yk[7]);
+        }
+        const double nu_mag = (c0 - nu0 * u - nu1 * v) / c;
+        const double nu_mag0 = 1.0 - nu0 * u0 / c0 - nu1 * v0 / c0;
+        const double cp0 = c * nu0 / nu_mag + u, cp1 = c * nu1 / nu_mag + v, cp2 = c * nu2 / nu_mag;
+        const double cs0 = c0 * rc.cth * rc.cph + u0, cs1 = c0 * rc.cth * rc.sph + v0, cs2 = c0 * rc.sth;
+        const double cpm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2), csm = sqrt(cs0 * cs0 + cs1 * cs1 + cs2 * cs2);
+        const double num = rho * nu_mag * (c * c * c) * csm * rc.cth;
+        const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
+        return 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
+    }
+
     // GeoAc_Jacobian + GeoAc_Amplitude (3DRngDep.cpp:547-592) and the results row of GeoAc3D.RngDep_main.cpp:296-318
     GEOAC_HD static void arrival(const LaunchConsts& L, const Grid3D& G, const RayC& rc, const double* ym1, const double* yk,
                                  double tt, Cur3& cur, double& amp, double& incl, double& backaz, double& aux, double& margin) {
@@ -172,29 +198,7 @@ struct Eq3DRD {
         while (b > 180.0) b -= 360.0;
         backaz = b; aux = 0.0;
         margin = (yk[2] - L.z_grnd) / fabs(yk[2] - ym1[2]);
-        amp = 0.0;
-        if (AMP) {
-            ms_wrappers<false, true, false>(G, yk[0], yk[1], yk[2], cur, w, dzs);
-            const double c = sqrt(kGamR * w[0]), u = w[1], v = w[2], rho = w[3];
-            const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
-            const double c0 = L.c_src, u0 = L.u_src, v0 = L.v_src;
-            double D;
-            {
-                const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
-                const double q0 = c * nu0 / nm + u, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm;
-                const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
-                const double xs = q0 / qm, ys = q1 / qm, zs = q2 / qm;
-                D = xs * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (ys * yk[14] - zs * yk[13]) + yk[12] * (ys * yk[8] - zs * yk[7]);
-            }
-            const double nu_mag = (c0 - nu0 * u - nu1 * v) / c;
-            const double nu_mag0 = 1.0 - nu0 * u0 / c0 - nu1 * v0 / c0;
-            const double cp0 = c * nu0 / nu_mag + u, cp1 = c * nu1 / nu_mag + v, cp2 = c * nu2 / nu_mag;
-            const double cs0 = c0 * rc.cth * rc.cph + u0, cs1 = c0 * rc.cth * rc.sph + v0, cs2 = c0 * rc.sth;
-            const double cpm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2), csm = sqrt(cs0 * cs0 + cs1 * cs1 + cs2 * cs2);
-            const double num = rho * nu_mag * (c * c * c) * csm * rc.cth;
-            const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
-            amp = 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
-        }
+        amp = amplitude(L, G, rc, yk, cur);
     }
 };
 
@@ -362,6 +366,32 @@ struct EqGlobalRD {
         }
     }
 
+    // GeoAc_Amplitude at an arbitrary state (as Global.cpp:594-629; also evaluated along the path for the raypath rows)
+    GEOAC_HD static double amplitude(const LaunchConsts& L, const Grid3D& G, const RayC& rc, const double* yk, Cur3& cur) {
+        if (!AMP) return 0.0;
+        double w[4], dzs[3];
+        ms_wrappers<true, true, false>(G, yk[1], yk[2], yk[0], cur, w, dzs);
+        const double c = sqrt(kGamR * w[0]);
+        const double u = w[1], v = w[2], rho = w[3];
+        const double r = yk[0];
+        const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
+        double sl, cl; sincos(yk[1], &sl, &cl);
+        const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
+        const double q0 = c * nu0 / nm, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm + u;
+        const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double dr_ds = q0 / qm, dt_ds = 1.0 / r * q1 / qm, dp_ds = 1.0 / (r * sl) * q2 / qm;
+        const double D = r * r * cl * (dr_ds * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (dt_ds * yk[14] - dp_ds * yk[13])
+                                       + yk[12] * (dt_ds * yk[8] - dp_ds * yk[7]));
+        const double c0 = L.c_src;
+        const double nu_mag = (c0 - nu1 * v - nu2 * u) / c, nu_mag0 = rc.nu0;
+        const double cp0 = c * nu0 / nu_mag, cp1 = c * nu1 / nu_mag + v, cp2 = c * nu2 / nu_mag + u;
+        const double cs0 = c0 * rc.sth / nu_mag0, cs1 = c0 * rc.cth * rc.sph / nu_mag + L.v_src, cs2 = c0 * rc.cth * rc.cph / nu_mag + L.u_src;
+        const double cpm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2), csm = sqrt(cs0 * cs0 + cs1 * cs1 + cs2 * cs2);
+        const double num = rho * nu_mag * (c * c * c) * csm * rc.cth;
+        const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
+        return 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
+    }
+
     // Jacobian / amplitude (as Global.cpp:594-629) and the results row of GeoAcGlobal.RngDep_main.cpp:304-328 (+asin: App. A-16)
     GEOAC_HD static void arrival(const LaunchConsts& L, const Grid3D& G, const RayC& rc, const double* ym1, const double* yk,
                                  double tt, Cur3& cur, double& amp, double& incl, double& backaz, double& aux, double& margin) {
@@ -377,27 +407,7 @@ struct EqGlobalRD {
         const double h = s1 * s1 + rc.cos_lat_src * cos(yk[1]) * (s2 * s2);
         aux = 2.0 * kREarth * asin(sqrt(h)) / tt;
         margin = (yk[0] - L.ground) / fabs(yk[0] - ym1[0]);
-        amp = 0.0;
-        if (AMP) {
-            const double u = w[1], v = w[2], rho = w[3];
-            const double r = yk[0];
-            const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
-            double sl, cl; sincos(yk[1], &sl, &cl);
-            const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
-            const double q0 = c * nu0 / nm, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm + u;
-            const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
-            const double dr_ds = q0 / qm, dt_ds = 1.0 / r * q1 / qm, dp_ds = 1.0 / (r * sl) * q2 / qm;
-            const double D = r * r * cl * (dr_ds * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (dt_ds * yk[14] - dp_ds * yk[13])
-                                           + yk[12] * (dt_ds * yk[8] - dp_ds * yk[7]));
-            const double c0 = L.c_src;
-            const double nu_mag = (c0 - nu1 * v - nu2 * u) / c, nu_mag0 = rc.nu0;
-            const double cp0 = c * nu0 / nu_mag, cp1 = c * nu1 / nu_mag + v, cp2 = c * nu2 / nu_mag + u;
-            const double cs0 = c0 * rc.sth / nu_mag0, cs1 = c0 * rc.cth * rc.sph / nu_mag + L.v_src, cs2 = c0 * rc.cth * rc.cph / nu_mag + L.u_src;
-            const double cpm = sqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2), csm = sqrt(cs0 * cs0 + cs1 * cs1 + cs2 * cs2);
-            const double num = rho * nu_mag * (c * c * c) * csm * rc.cth;
-            const double den = L.rho_src * nu_mag0 * (c0 * c0 * c0) * cpm * D;
-            amp = 1.0 / (4.0 * kPi) * sqrt(fabs(num / den));
-        }
+        amp = amplitude(L, G, rc, yk, cur);
     }
 };
 

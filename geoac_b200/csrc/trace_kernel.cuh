@@ -44,6 +44,7 @@ struct TraceArgs {
     const uint32_t* n_long;           // packet mode: number of leading packets of `order` to trace four-lanes-per-ray from the start (or nullptr)
     unsigned long long* counter_long; // next unclaimed entry of that leading region (claimed 8 rays at a time)
     int packet_refill;                // experiment knob: refill a warp only when all of its lanes are idle (always on for PacketMode sets)
+    double* path; int32_t* path_rows; int path_stride; int64_t path_cap;   // raypath capture (PATHS kernels), else unused
     double* prev;                     // y_{k-1} scratch: [NEQ][grid * block] doubles (variants with a quadratic intercept)
 };
 
@@ -76,7 +77,11 @@ GEOAC_HD void fill_launch_consts_1d(LaunchConsts& L, const Table1D& T, int varia
     suthbass_setup(L, c, rho);
 }
 
-struct RecOut { double* rec; int32_t* status; int32_t* n_steps; int64_t n_slots; int n_rec; };
+struct RecOut {
+    double* rec; int32_t* status; int32_t* n_steps; int64_t n_slots; int n_rec;
+    // raypath capture (PATHS kernels only): rows of GEOAC_PATH_NF doubles, `path_cap` rows reserved per ray
+    double* path; int32_t* path_rows; int path_stride; int64_t path_cap;
+};
 
 // ---------------------------------------------------------------------------------------------------------------
 // One lane = one ray in flight.  The FP64 part of its state (LaneD: y_k, the per-ray constants, the running sums) lives
@@ -97,6 +102,7 @@ template <class EQ>
 struct LaneI {
     typename EQ::Cursor cur;
     int bounce, ksteps;
+    int path_n;             // raypath rows emitted so far (PATHS kernels)
     int64_t ray;
 };
 
@@ -108,7 +114,7 @@ template <class EQ> struct NeedsPrev { static constexpr bool value = !(EQ::VARIA
 
 template <class EQ>
 GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, int64_t idx, double theta, double phi) {
-    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.cur = typename EQ::Cursor{};
+    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.path_n = 0; n.cur = typename EQ::Cursor{};
     d.tt_total = d.att_total = d.tt_b = d.att_b = d.zmax = 0.0;
     EQ::init(L, T, theta, phi, d.rc, d.y, n.cur);
 }
@@ -118,8 +124,9 @@ GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, cons
 template <class EQ> struct WorkInMem { static constexpr bool value = std::is_same<typename EQ::Atmo, Grid3D>::value; };
 
 // prev[i * pstride] holds y_{k-1}[i] (only maintained when NeedsPrev); work = 2 NEQ doubles (WorkInMem) or nullptr;
-// returns false when the ray has ended
-template <class EQ>
+// returns false when the ray has ended.  PATHS: also emit one raypath row every o.path_stride steps (WriteRays=True of the
+// mains, Code/GeoAc3D_main.cpp:249-262: position, amplitude at that point, absorption and travel-time sums so far).
+template <class EQ, bool PATHS = false>
 GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, double* prev, int64_t pstride,
                            const RecOut& o, double* work) {
     constexpr int NEQ = EQ::NEQ;
@@ -153,6 +160,18 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     else            { d.tt_b += dtt; d.att_b += datt; }
 
     if (!(brk || gnd || lim)) {
+        if (PATHS) {
+            if (n.ksteps % o.path_stride == 0) {                  // row for state m = ksteps (m < k: never the sub-ground point)
+                if (n.path_n < o.path_cap) {
+                    double* row = o.path + ((int64_t)n.ray * o.path_cap + n.path_n) * GEOAC_PATH_NF;
+                    row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2];
+                    row[3] = EQ::amplitude(L, T, d.rc, acc, n.cur);
+                    row[4] = d.att_total; row[5] = d.tt_total;
+                    row[6] = (double)n.bounce; row[7] = (double)n.ksteps;
+                }
+                n.path_n++;
+            }
+        }
 #pragma unroll
         for (int i = 0; i < NEQ; i++) {
             if (NeedsPrev<EQ>::value) prev[i * pstride] = y[i];
@@ -165,6 +184,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     if (!gnd) {
         o.status[slot] = brk ? GEOAC_ST_BREAK : GEOAC_ST_LIMIT;
         o.n_steps[slot] = brk ? n.ksteps : L.step_limit;
+        if (PATHS) o.path_rows[n.ray] = n.path_n;
         return false;
     }
     if (!L.seg_mode) { d.tt_total += d.tt_b; d.att_total += d.att_b; d.tt_b = 0.0; d.att_b = 0.0; }
@@ -182,7 +202,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     o.rec[(int64_t)GEOAC_F_MARGIN * o.n_slots + slot] = margin;
     o.status[slot] = GEOAC_ST_ARRIVAL;
     o.n_steps[slot] = n.ksteps;
-    if (n.bounce >= L.bounces) return false;
+    if (n.bounce >= L.bounces) { if (PATHS) o.path_rows[n.ray] = n.path_n; return false; }
     double ym2[NEQ], y0[NEQ];
 #pragma unroll
     for (int i = 0; i < NEQ; i++) ym2[i] = NeedsPrev<EQ>::value ? prev[i * pstride] : 0.0;
@@ -232,7 +252,7 @@ template <class EQ> struct LaneLayout {
     static constexpr int STRIDE = (WORK + EXTRA) | 1;
 };
 
-template <class EQ, int BLOCK, bool TABLE_IN_SMEM>
+template <class EQ, int BLOCK, bool TABLE_IN_SMEM, bool PATHS = false>
 __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__ TraceArgs a) {
     constexpr int NEQ = EQ::NEQ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -263,6 +283,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
 
     const unsigned lane = threadIdx.x & 31;
     RecOut o; o.rec = a.rec; o.status = a.status; o.n_steps = a.n_steps; o.n_rec = a.n_rec; o.n_slots = a.n_rays * a.n_rec;
+    o.path = a.path; o.path_rows = a.path_rows; o.path_stride = a.path_stride; o.path_cap = a.path_cap;
     LaneD<EQ>& ld = *reinterpret_cast<LaneD<EQ>*>(lanes + (size_t)threadIdx.x * LaneLayout<EQ>::STRIDE);
     LaneI<EQ> li;
     // y_{k-1} history (quadratic intercept only): [eq][global thread] in an L2-resident global scratch, written once per step
@@ -335,6 +356,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             gi.cur.kz = __shfl_sync(0xffffffffu, li.cur.kz, owner);
             gi.bounce = __shfl_sync(0xffffffffu, li.bounce, owner); gi.ksteps = __shfl_sync(0xffffffffu, li.ksteps, owner);
             gi.ray = __shfl_sync(0xffffffffu, (long long)li.ray, owner);
+            gi.path_n = __shfl_sync(0xffffffffu, li.path_n, owner);
             const int othread = (int)(threadIdx.x & ~31u) + owner;
             double* const rec = lanes + (size_t)othread * LaneLayout<EQ>::STRIDE;
             double* const gwork = rec + LaneLayout<EQ>::WORK;
@@ -342,21 +364,22 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             Tg.scratch = gwork + 2 * NEQ;
             if (coop) { Tg.role = (int)lane & 3; Tg.nrole = 4; Tg.glane0 = (int)lane & ~3; Tg.gmask = 0xFu << ((int)lane & ~3); }
             bool alive = false;
-            if (run) alive = lane_advance<EQ>(*reinterpret_cast<LaneD<EQ>*>(rec), gi, L, Tg, a.prev + ((int64_t)blockIdx.x * BLOCK + othread), pstride, o, gwork);
+            if (run) alive = lane_advance<EQ, PATHS>(*reinterpret_cast<LaneD<EQ>*>(rec), gi, L, Tg, a.prev + ((int64_t)blockIdx.x * BLOCK + othread), pstride, o, gwork);
             // hand the integer state back to the lane that owns the ray (itself in serial mode)
             const int src = (coop && have_ray) ? 4 * __popc(act & ((1u << lane) - 1u)) : (int)lane;
             const int bka = __shfl_sync(0xffffffffu, gi.cur.ka, src), bkb = __shfl_sync(0xffffffffu, gi.cur.kb, src);
             const int bkz = __shfl_sync(0xffffffffu, gi.cur.kz, src);
             const int bbo = __shfl_sync(0xffffffffu, gi.bounce, src), bks = __shfl_sync(0xffffffffu, gi.ksteps, src);
             const int bal = __shfl_sync(0xffffffffu, (int)alive, src);
+            const int bpn = __shfl_sync(0xffffffffu, gi.path_n, src);
             if (have_ray) {
-                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks;
+                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks; li.path_n = bpn;
                 have_ray = bal != 0;
                 my_steps++;
             }
         } else {
             if (have_ray) {
-                have_ray = lane_advance<EQ>(ld, li, L, T, prev, pstride, o, work);
+                have_ray = lane_advance<EQ, PATHS>(ld, li, L, T, prev, pstride, o, work);
                 my_steps++;
             }
         }

@@ -56,7 +56,9 @@ enum {
     GEOAC_F_AUX        = 24,   /* Global variants: celerity [km/s]; otherwise 0                    */
     GEOAC_F_MARGIN     = 25,   /* (z_k - z_grnd)/|z_k - z_{k-1}|  in (-1,0): how far into the last step the ground
                                   was crossed; values within ~1e-9 of 0 or -1 flag near-threshold rays */
-    GEOAC_NFIELDS      = 26
+    GEOAC_NFIELDS      = 26,
+    /* one raypath row (geoac_trace_paths): state[0..2], amplitude (linear), absorption sum, travel-time sum, bounce, step */
+    GEOAC_PATH_NF      = 8
 };
 
 /* per-slot status */
@@ -130,6 +132,18 @@ int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const doubl
  * (a cudaStream_t passed as void*, NULL = default stream); returns without synchronising. */
 int geoac_trace_device(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
                        double* d_rec, int32_t* d_status, int32_t* d_n_steps, void* cuda_stream);
+
+/* geoac_trace() plus the raypath rows of the mains' WriteRays=True mode (Code/GeoAc3D_main.cpp:249-262 and siblings; the
+ * same call serves `-interactive`, which plots one ray): every `path_stride` steps (the mains use 25) one row of
+ * GEOAC_PATH_NF doubles { state[0], state[1], state[2], amplitude (linear, 0 with calc_amp = 0), absorption sum, travel-time
+ * sum, bounce index, step index within the bounce } is stored for the ray, at most `path_cap` rows per ray:
+ *   path      : n_rays * path_cap * GEOAC_PATH_NF doubles, row r of ray i at path[(i*path_cap + r)*GEOAC_PATH_NF]
+ *   path_rows : n_rays int32, rows PRODUCED for the ray (if > path_cap the surplus was dropped)
+ * The front end prints lat/lon in degrees, max(z, 0), 20 log10(amplitude) and -absorption exactly as it does today.
+ * Requires params.accum_per_segment = 1 (the accumulation convention of that mode; always so for 2D). */
+int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                      double* rec, int32_t* status, int32_t* n_steps,
+                      int path_stride, int64_t path_cap, double* path, int32_t* path_rows);
 
 /* Optional: allocate the device staging geoac_trace() needs for batches of up to n_rays rays (with the current
  * `bounces`) ahead of time, so that the first trace call does not pay for it.  geoac_trace() grows it on demand anyway. */

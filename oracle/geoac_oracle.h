@@ -77,6 +77,11 @@ int orc_load_met_grid(const char* prefix, const char* loc0, const char* loc1, co
  * `limits_from_atmo` != 0 applies GeoAc_SetPropRegion to a copy of *p first. Returns total RK4 steps (<0 on error). */
 int64_t orc_trace(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_rays,
                   const double* theta, const double* phi, double* rec, int32_t* status, int32_t* n_steps);
+/* orc_trace plus the raypath rows of WriteRays=True (one row of GEOAC_PATH_NF doubles every path_stride steps, at most
+ * path_cap rows kept per ray, path_rows[ray] = rows produced); needs accum_per_segment semantics. */
+int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_rays,
+                        const double* theta, const double* phi, double* rec, int32_t* status, int32_t* n_steps,
+                        int path_stride, int64_t path_cap, double* path, int32_t* path_rows);
 
 /* GeoAc_SetPropRegion for this atmosphere: fills vert_limit / range_limit / box limits of *p. */
 void orc_set_prop_region(int variant, const orc_atmo* atmo, geoac_params* p);

@@ -105,6 +105,26 @@ def default_params(variant, atmo=None):
     return p
 
 
+def trace_paths(variant, atmo, params, theta, phi, stride, cap):
+    """As trace(), plus the raypath rows (accum_per_segment semantics): path [n][cap][PATH_NF], path_rows [n]."""
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    n = len(theta)
+    n_rec = params.bounces + 1
+    rec = np.zeros((abi.NFIELDS, n, n_rec))
+    status = np.zeros((n, n_rec), dtype=np.int32)
+    n_steps = np.zeros((n, n_rec), dtype=np.int32)
+    path = np.zeros((n, cap, abi.PATH_NF)); rows = np.zeros(n, dtype=np.int32)
+    L = lib()
+    L.orc_trace_paths.restype = C.c_int64
+    L.orc_trace_paths.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams), C.c_int64, dp, dp, dp, ip, ip, C.c_int, C.c_int64, dp, ip]
+    total = L.orc_trace_paths(variant, atmo.h, C.byref(params), n, _p(theta), _p(phi), _p(rec), status.ctypes.data_as(ip),
+                              n_steps.ctypes.data_as(ip), stride, cap, _p(path), rows.ctypes.data_as(ip))
+    if total < 0:
+        raise RuntimeError("orc_trace_paths failed")
+    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": int(total), "path": path, "path_rows": rows}
+
+
 def trace(variant, atmo, params, theta, phi):
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     phi = np.ascontiguousarray(phi, dtype=np.float64)
@@ -134,7 +154,10 @@ def run_ref(variant, profile_args, out_path, **kv):
     cmd = [ref_binary(variant), out_path] + list(profile_args) + [f"{k}={v}" for k, v in kv.items()]
     out = subprocess.run(cmd, check=True, capture_output=True, text=True).stdout
     info = json.loads(out.strip().splitlines()[-1])
-    return read_ref_bin(out_path), info
+    ref = read_ref_bin(out_path)
+    if int(kv.get("path_stride", 0)) > 0:
+        ref["path"] = np.fromfile(out_path + ".path", dtype=np.float64).reshape(-1, 9)     # ray, state[0..2], amp, att, tt, bounce, step
+    return ref, info
 
 
 def read_ref_bin(path):

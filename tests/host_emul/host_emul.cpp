@@ -18,21 +18,26 @@
 
 using namespace geoac;
 
-template <class EQ>
-static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const double* th, const double* ph, RecOut o) {
+template <class EQ, bool PATHS>
+static long run_mode(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const double* th, const double* ph, RecOut o) {
     long steps = 0;
     std::vector<double> prev(EQ::NEQ, 0.0), work(2 * EQ::NEQ, 0.0);
     for (long i = 0; i < n; i++) {
         LaneD<EQ> ld; LaneI<EQ> li;
         lane_start<EQ>(ld, li, L, T, i, th[i], ph[i]);
-        while (lane_advance<EQ>(ld, li, L, T, prev.data(), 1, o, work.data())) steps++;
+        while (lane_advance<EQ, PATHS>(ld, li, L, T, prev.data(), 1, o, work.data())) steps++;
         steps++;
     }
     return steps;
 }
+template <class EQ>
+static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const double* th, const double* ph, RecOut o) {
+    return o.path_stride > 0 ? run_mode<EQ, true>(L, T, n, th, ph, o) : run_mode<EQ, false>(L, T, n, th, ph, o);
+}
 
 extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const double* table, long n_rays,
-                              const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps) {
+                              const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps,
+                              int path_stride, long path_cap, double* path, int32_t* path_rows) {
     Table1D T; T.base = table; T.n = n; T.xmin = table[TAB_X]; T.xmax = table[(size_t)(n - 1) * TAB_NARR + TAB_X]; T.jump_scale = 0.0;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
     L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
@@ -46,6 +51,7 @@ extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const d
     L.per_bounce_zmax = 0;
     fill_launch_consts_1d(L, T, variant);
     RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
+    o.path = path; o.path_rows = path_rows; o.path_stride = path_stride; o.path_cap = path_cap;
     std::fill(rec, rec + (size_t)GEOAC_NFIELDS * o.n_slots, 0.0);
     std::fill(status, status + o.n_slots, 0); std::fill(n_steps, n_steps + o.n_slots, 0);
     const bool amp = p->calc_amp != 0;
@@ -62,7 +68,8 @@ extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const d
 // range-dependent variants: fields dense [n0][n1][nz] exactly as geoac_set_atmosphere_3d receives them
 extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1, int nz, const double* ax0, const double* ax1, const double* axz,
                               const double* Tf, const double* uf, const double* vf, const double* rhof, long n_rays,
-                              const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps) {
+                              const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps,
+                              int path_stride, long path_cap, double* path, int32_t* path_rows) {
     const bool glob = variant == GEOAC_GLOBAL_RNGDEP;
     std::vector<double> z, tuv, rh;
     build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, Tf, uf, vf, rhof, z, tuv, rh);
@@ -83,6 +90,7 @@ extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1
     L.per_bounce_zmax = 1;
     fill_launch_consts_3d(L, g, variant);
     RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
+    o.path = path; o.path_rows = path_rows; o.path_stride = path_stride; o.path_cap = path_cap;
     std::fill(rec, rec + (size_t)GEOAC_NFIELDS * o.n_slots, 0.0);
     std::fill(status, status + o.n_slots, 0); std::fill(n_steps, n_steps + o.n_slots, 0);
     const bool amp = p->calc_amp != 0;

@@ -45,6 +45,26 @@ def test_cuda_matches_reference_golden(name, capsys):
     assert not problems, "\n".join(problems)
 
 
+@pytest.mark.parametrize("name", util.path_cases())
+def test_cuda_raypath_rows_match_reference(name):
+    """WriteRays=True rows through geoac_trace_paths: row counts / bounce / step indices exact, positions and sums to 1e-9,
+    the amplitude along the path (singular at caustics) to 1e-6."""
+    d, kv = util.load_case(name)
+    variant = int(d["variant"])
+    tr = _tracer_for(variant, kv, d)
+    th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
+    cap = 2000
+    out = tr.trace_paths(th, ph, int(kv["path_stride"]), cap)
+    want_path, want_rows = util.golden_paths(d, cap)
+    problems = util.compare_paths(out["path"], out["path_rows"], want_path, want_rows, util.RTOL, 1e-6, name)
+    want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
+    rp, _ = util.compare_records(out, want, variant, tr.params.calc_amp, util.RTOL, name, amp_rtol=AMP_RTOL)
+    assert not (problems + rp), "\n".join((problems + rp)[:10])
+    # a row capacity that is too small drops the surplus rows but still reports how many were produced
+    small = tr.trace_paths(th, ph, int(kv["path_stride"]), 5)
+    assert np.array_equal(small["path_rows"], want_rows) and np.array_equal(small["path"][:, :5], out["path"][:, :5])
+
+
 def test_cuda_matches_oracle_seeded(oracle):
     rng = np.random.default_rng(20251018)
     n = 96

@@ -37,6 +37,47 @@ def test_oracle_bit_exact_vs_reference(oracle, name):
         assert np.allclose(out["rec"][f], d["rec"][f], rtol=1e-13, atol=1e-12)
 
 
+@pytest.mark.parametrize("name", util.path_cases())
+def test_oracle_raypath_rows_bit_exact_vs_reference(oracle, name):
+    """WriteRays=True rows (one every 25 steps: position, amplitude at that point, absorption and travel-time sums)."""
+    d, kv = util.load_case(name)
+    variant = int(d["variant"])
+    if util.is_rngdep(variant):
+        at = oracle.atmo3d(util.is_global(variant), *util.load_grid(d))
+    else:
+        at = oracle.atmo1d(util.is_global(variant), *oracle.load_met_1d(util.profile_path(d), global_taper=util.is_global(variant)))
+    p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
+    th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
+    cap = 2000
+    out = oracle.trace_paths(variant, at, p, th, ph, int(kv["path_stride"]), cap)
+    want_path, want_rows = util.golden_paths(d, cap)
+    assert np.array_equal(out["path_rows"], want_rows)
+    assert np.array_equal(out["path"], want_path)
+    assert np.array_equal(out["status"], d["status"]) and np.array_equal(out["n_steps"], d["n_steps"])
+
+
+@pytest.mark.parametrize("name", util.path_cases())
+def test_device_math_host_emulation_raypaths(oracle, name):
+    from tests import emul
+    d, kv = util.load_case(name)
+    variant = int(d["variant"])
+    th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
+    cap = 2000
+    if util.is_rngdep(variant):
+        arrs = util.load_grid(d)
+        at = oracle.atmo3d(util.is_global(variant), *arrs)
+        p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
+        out = emul.trace_grid(variant, p, arrs, th, ph, int(kv["path_stride"]), cap)
+    else:
+        arrs = oracle.load_met_1d(util.profile_path(d), global_taper=util.is_global(variant))
+        at = oracle.atmo1d(util.is_global(variant), *arrs)
+        p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
+        out = emul.trace(variant, p, arrs, th, ph, int(kv["path_stride"]), cap)
+    want_path, want_rows = util.golden_paths(d, cap)
+    problems = util.compare_paths(out["path"], out["path_rows"], want_path, want_rows, util.RTOL, 1e-6, name)
+    assert not problems, "\n".join(problems[:10])
+
+
 def test_golden_has_reference_invariants():
     """Sanity of the fixtures themselves: stratified reciprocity (2-D bounce ranges r_n ~ (n+1) r_0)."""
     d, _ = util.load_case("2d_config1")

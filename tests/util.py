@@ -124,3 +124,39 @@ def compare_records(got, want, variant, calc_amp, rtol, label="", exact_discrete
             problems.append(f"{label}: field {f} max rel diff {rel.max():.3e} > {tol:g} (got {a[i]!r}, want {b[i]!r}; "
                             f"{int((rel > tol).sum())} of {rel.size} records)")
     return problems, stats
+
+
+def path_cases():
+    return [n for n in golden_cases() if n.endswith("_path")]
+
+
+def golden_paths(d, cap):
+    """Raypath rows of a golden case (rows x {ray, state[0..2], amp, att, tt, bounce, step}) -> path [n][cap][PATH_NF], rows [n]."""
+    n = len(d["theta_deg"])
+    path = np.zeros((n, cap, abi.PATH_NF)); rows = np.zeros(n, dtype=np.int32)
+    for r in d["path"]:
+        i = int(r[0])
+        assert rows[i] < cap
+        path[i, rows[i]] = r[1:]
+        rows[i] += 1
+    return path, rows
+
+
+def compare_paths(got_path, got_rows, want_path, want_rows, rtol, amp_rtol, label=""):
+    """Row counts, bounce and step indices exact; positions / sums to rtol (positions relative to the path extent);
+    the amplitude along the path to amp_rtol (it passes through caustics, where it is singular)."""
+    problems = []
+    if not np.array_equal(got_rows, want_rows):
+        return [f"{label}: raypath row counts differ: {got_rows.tolist()} vs {want_rows.tolist()}"]
+    for i, nr in enumerate(want_rows):
+        g, w = got_path[i, :nr], want_path[i, :nr]
+        if not (np.array_equal(g[:, 6], w[:, 6]) and np.array_equal(g[:, 7], w[:, 7])):
+            problems.append(f"{label}: ray {i}: bounce/step indices differ")
+            continue
+        for f, tol in ((0, rtol), (1, rtol), (2, rtol), (4, rtol), (5, rtol), (3, amp_rtol)):
+            scale = np.maximum(np.abs(w[:, f]), max(1.0 if f < 3 else 1e-300, 1e-9 * float(np.abs(w[:, f]).max()))) if f != 3 else np.abs(w[:, f]) + 1e-300
+            rel = np.abs(g[:, f] - w[:, f]) / scale
+            if not np.all(rel <= tol):
+                j = int(np.argmax(rel))
+                problems.append(f"{label}: ray {i} path field {f}: max rel diff {rel.max():.3e} > {tol:g} at row {j} (got {g[j, f]!r}, want {w[j, f]!r})")
+    return problems
