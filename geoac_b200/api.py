@@ -47,7 +47,7 @@ def lib():
         L.geoac_get_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
         L.geoac_set_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
         L.geoac_trace.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip]
-        L.geoac_trace_paths.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int64, _dp, _ip]
+        L.geoac_trace_paths.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int64, _dp, _ip, C.c_int64, _dp, _ip]
         L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.geoac_reserve.argtypes = [C.c_void_p, C.c_int64]
         L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -178,18 +178,21 @@ class Tracer:
                                       out["n_steps"].ctypes.data_as(_ip)), "geoac_trace")
         return out
 
-    def trace_paths(self, theta, phi, stride=25, cap=2400):
-        """trace() plus the raypath rows of WriteRays=True: adds path [n][cap][PATH_NF] and path_rows [n] to the result."""
+    def trace_paths(self, theta, phi, stride=25, cap=2400, caustic_cap=0):
+        """trace() plus the raypath rows of WriteRays=True (path [n][cap][PATH_NF], path_rows [n]) and, with caustic_cap > 0,
+        the WriteCaustics=True events (caustic [n][caustic_cap][CAUSTIC_NF], caustic_rows [n])."""
         theta = np.ascontiguousarray(theta, dtype=np.float64)
         phi = np.ascontiguousarray(phi, dtype=np.float64)
         n = len(theta)
         n_rec = self.params.bounces + 1
         out = {"rec": np.empty((abi.NFIELDS, n, n_rec)), "status": np.empty((n, n_rec), dtype=np.int32),
-               "n_steps": np.empty((n, n_rec), dtype=np.int32), "path": np.zeros((n, cap, abi.PATH_NF)),
-               "path_rows": np.zeros(n, dtype=np.int32)}
+               "n_steps": np.empty((n, n_rec), dtype=np.int32), "path": np.zeros((n, max(cap, 1), abi.PATH_NF)),
+               "path_rows": np.zeros(n, dtype=np.int32), "caustic": np.zeros((n, max(caustic_cap, 1), abi.CAUSTIC_NF)),
+               "caustic_rows": np.zeros(n, dtype=np.int32)}
         self._check(lib().geoac_trace_paths(self._h, n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip),
                                             out["n_steps"].ctypes.data_as(_ip), stride, cap, _p(out["path"]),
-                                            out["path_rows"].ctypes.data_as(_ip)), "geoac_trace_paths")
+                                            out["path_rows"].ctypes.data_as(_ip), caustic_cap, _p(out["caustic"]),
+                                            out["caustic_rows"].ctypes.data_as(_ip)), "geoac_trace_paths")
         return out
 
     def reserve(self, n_rays):

@@ -44,7 +44,8 @@ struct geoac_ctx {
     LaunchConsts* d_consts = nullptr;
     unsigned long long* d_counters = nullptr;     // [0] ray counter, [1] total steps
     double* d_prev = nullptr; size_t cap_prev = 0; // y_{k-1} scratch of the trace kernel
-    double* d_path = nullptr; size_t cap_path = 0; int32_t* d_path_rows = nullptr; int64_t cap_path_rows = 0;   // raypath capture staging
+    double* d_path = nullptr; size_t cap_path = 0; int32_t* d_path_rows = nullptr; size_t cap_path_rows = 0;   // raypath capture staging
+    double* d_caus = nullptr; size_t cap_caus = 0; int32_t* d_caus_rows = nullptr; size_t cap_caus_rows = 0;   // caustic event staging
     uint32_t *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr; int64_t cap_order = 0;   // longest-ray-first scheduling
     int last_launches = 0;
     // staging for the host-buffer entry point
@@ -112,7 +113,7 @@ extern "C" void geoac_destroy(geoac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters); cudaFree(ctx->d_prev);
-    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows);
+    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows); cudaFree(ctx->d_caus); cudaFree(ctx->d_caus_rows);
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -357,7 +358,8 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     return GEOAC_OK;
 }
 
-struct PathArgs { double* path = nullptr; int32_t* rows = nullptr; int stride = 0; int64_t cap = 0; };
+struct PathArgs { double* path = nullptr; int32_t* rows = nullptr; int stride = 0; int64_t cap = 0;
+                  double* caus = nullptr; int32_t* caus_rows = nullptr; int64_t caus_cap = 0; };
 
 static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, const double* d_phi,
                          double* d_rec, int32_t* d_status, int32_t* d_n_steps, cudaStream_t st, const PathArgs& pa = PathArgs()) {
@@ -381,8 +383,9 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
     a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1; a.warp_trips = ctx->d_counters + 2;
     a.path = pa.path; a.path_rows = pa.rows; a.path_stride = pa.stride; a.path_cap = pa.cap;
+    a.caus = pa.caus; a.caus_rows = pa.caus_rows; a.caus_cap = pa.caus_cap;
     const bool amp = ctx->prm.calc_amp != 0;
-    if (pa.stride > 0) {          // raypath capture: the PATHS instantiations (same lanes per SM as the plain ones)
+    if (pa.stride > 0 || pa.caus_cap > 0) {          // raypath / caustic capture: the PATHS instantiations (same lanes per SM as the plain ones)
         switch (ctx->variant) {
             case GEOAC_2D:     return amp ? launch_trace<Eq2D<true>, 512, true>(ctx, a, st)     : launch_trace<Eq2D<false>, 512, true>(ctx, a, st);
             case GEOAC_3D:     return amp ? launch_trace<Eq3D<true>, 384, true>(ctx, a, st)     : launch_trace<Eq3D<false>, 512, true>(ctx, a, st);
@@ -443,12 +446,23 @@ extern "C" int geoac_reserve(geoac_ctx* ctx, int64_t n_rays) {
     return reserve_staging(ctx, n_rays);
 }
 
+static int grow(geoac_ctx* ctx, void** buf, size_t* cap, size_t need) {
+    if (need <= *cap) return GEOAC_OK;
+    cudaFree(*buf); *buf = nullptr; *cap = 0;
+    CK(cudaMalloc(buf, need));
+    *cap = need;
+    return GEOAC_OK;
+}
+
 static int trace_host(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
-                      double* rec, int32_t* status, int32_t* n_steps, int path_stride, int64_t path_cap, double* path, int32_t* path_rows) {
+                      double* rec, int32_t* status, int32_t* n_steps, int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
+                      int64_t caus_cap, double* caus, int32_t* caus_rows) {
     if (!ctx || n_rays < 0 || (n_rays > 0 && (!theta || !phi || !rec || !status || !n_steps))) return GEOAC_ERR_BAD_ARG;
     if (path_stride > 0 && (path_cap <= 0 || !path || !path_rows)) return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath capture needs path buffers and a positive row capacity");
-    if (path_stride > 0 && ctx->variant != GEOAC_2D && !ctx->prm.accum_per_segment)
-        return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath rows need accum_per_segment = 1 (the mains' WriteRays accumulation, SURVEY App. A-2)");
+    if (caus_cap > 0 && (!caus || !caus_rows)) return fail(ctx, GEOAC_ERR_BAD_ARG, "caustic capture needs its buffers");
+    if (caus_cap > 0 && !ctx->prm.calc_amp) return fail(ctx, GEOAC_ERR_BAD_ARG, "caustic capture needs calc_amp = 1 (the Jacobian uses the auxiliary equations)");
+    if ((path_stride > 0 || caus_cap > 0) && ctx->variant != GEOAC_2D && !ctx->prm.accum_per_segment)
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath / caustic rows need accum_per_segment = 1 (the mains' WriteRays accumulation, SURVEY App. A-2)");
     if (n_rays == 0) return GEOAC_OK;
     if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");
     cudaSetDevice(ctx->device);
@@ -460,19 +474,19 @@ static int trace_host(geoac_ctx* ctx, int64_t n_rays, const double* theta, const
     cudaStream_t st = ctx->stream;
     if (path_stride > 0) {
         const size_t need = (size_t)n_rays * path_cap * GEOAC_PATH_NF * sizeof(double);
-        if (need > ctx->cap_path) {
-            cudaFree(ctx->d_path); ctx->d_path = nullptr; ctx->cap_path = 0;
-            CK(cudaMalloc(&ctx->d_path, need));
-            ctx->cap_path = need;
-        }
-        if (n_rays > ctx->cap_path_rows) {
-            cudaFree(ctx->d_path_rows); ctx->d_path_rows = nullptr; ctx->cap_path_rows = 0;
-            CK(cudaMalloc(&ctx->d_path_rows, sizeof(int32_t) * n_rays));
-            ctx->cap_path_rows = n_rays;
-        }
+        int g1 = grow(ctx, (void**)&ctx->d_path, &ctx->cap_path, need); if (g1) return g1;
+        int g2 = grow(ctx, (void**)&ctx->d_path_rows, &ctx->cap_path_rows, sizeof(int32_t) * n_rays); if (g2) return g2;
         CK(cudaMemsetAsync(ctx->d_path, 0, need, st));
         CK(cudaMemsetAsync(ctx->d_path_rows, 0, sizeof(int32_t) * n_rays, st));
         pa.path = ctx->d_path; pa.rows = ctx->d_path_rows; pa.stride = path_stride; pa.cap = path_cap;
+    }
+    if (caus_cap > 0) {
+        const size_t need = (size_t)n_rays * caus_cap * GEOAC_CAUSTIC_NF * sizeof(double);
+        int g1 = grow(ctx, (void**)&ctx->d_caus, &ctx->cap_caus, need); if (g1) return g1;
+        int g2 = grow(ctx, (void**)&ctx->d_caus_rows, &ctx->cap_caus_rows, sizeof(int32_t) * n_rays); if (g2) return g2;
+        CK(cudaMemsetAsync(ctx->d_caus, 0, need, st));
+        CK(cudaMemsetAsync(ctx->d_caus_rows, 0, sizeof(int32_t) * n_rays, st));
+        pa.caus = ctx->d_caus; pa.caus_rows = ctx->d_caus_rows; pa.caus_cap = caus_cap;
     }
     CK(cudaMemcpyAsync(ctx->d_theta, theta, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ctx->d_phi, phi, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
@@ -489,6 +503,10 @@ static int trace_host(geoac_ctx* ctx, int64_t n_rays, const double* theta, const
         CK(cudaMemcpyAsync(path, ctx->d_path, (size_t)n_rays * path_cap * GEOAC_PATH_NF * sizeof(double), cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(path_rows, ctx->d_path_rows, sizeof(int32_t) * n_rays, cudaMemcpyDeviceToHost, st));
     }
+    if (caus_cap > 0) {
+        CK(cudaMemcpyAsync(caus, ctx->d_caus, (size_t)n_rays * caus_cap * GEOAC_CAUSTIC_NF * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(caus_rows, ctx->d_caus_rows, sizeof(int32_t) * n_rays, cudaMemcpyDeviceToHost, st));
+    }
     unsigned long long cnt[2] = { 0, 0 };
     CK(cudaMemcpyAsync(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -499,14 +517,16 @@ static int trace_host(geoac_ctx* ctx, int64_t n_rays, const double* theta, const
 
 extern "C" int geoac_trace(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
                            double* rec, int32_t* status, int32_t* n_steps) {
-    return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, 0, 0, nullptr, nullptr);
+    return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, 0, 0, nullptr, nullptr, 0, nullptr, nullptr);
 }
 
 extern "C" int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
                                  double* rec, int32_t* status, int32_t* n_steps,
-                                 int path_stride, int64_t path_cap, double* path, int32_t* path_rows) {
-    if (path_stride <= 0) return ctx ? fail(ctx, GEOAC_ERR_BAD_ARG, "path_stride must be positive") : GEOAC_ERR_BAD_ARG;
-    return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, path_stride, path_cap, path, path_rows);
+                                 int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
+                                 int64_t caustic_cap, double* caustic, int32_t* caustic_rows) {
+    if (path_stride < 0 || caustic_cap < 0 || (path_stride == 0 && caustic_cap == 0))
+        return ctx ? fail(ctx, GEOAC_ERR_BAD_ARG, "ask for raypath rows (path_stride > 0) and / or caustic events (caustic_cap > 0)") : GEOAC_ERR_BAD_ARG;
+    return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, path_stride, path_cap, path, path_rows, caustic_cap, caustic, caustic_rows);
 }
 
 extern "C" int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_ms) {

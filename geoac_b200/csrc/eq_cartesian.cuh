@@ -152,6 +152,19 @@ struct Eq3D {
         }
     }
 
+    // GeoAc_Jacobian, 3DStratified.cpp:410-428: determinant of (dx/ds, dx/dtheta, dx/dphi); its sign changes mark caustics
+    GEOAC_HD static double jacobian(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
+        if (!AMP) return 0.0;
+        const SegPos sp = seg_locate(T, yk[2], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
+        const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
+        const double nu_mag = (L.c_src - rc.nx * u - rc.ny * v) / c;
+        const double cp[3] = { c * rc.nx / nu_mag + u, c * rc.ny / nu_mag + v, c * yk[3] / nu_mag };
+        const double cpm = sqrt(cp[0] * cp[0] + cp[1] * cp[1] + cp[2] * cp[2]);
+        const double xs = cp[0] / cpm, ys = cp[1] / cpm, zs = cp[2] / cpm;
+        return xs * (yk[5] * yk[10] - yk[9] * yk[6]) - yk[4] * (ys * yk[10] - zs * yk[9]) + yk[8] * (ys * yk[6] - zs * yk[5]);
+    }
+
     // GeoAc_Amplitude at an arbitrary state (also evaluated along the path for the raypath rows)
     GEOAC_HD static double amplitude(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
         if (!AMP) return 0.0;
@@ -287,6 +300,15 @@ struct Eq2D {
             y0[3] = pv[3]; y0[4] = -pv[4];
             y0[5] = -pv[5] + 2.0 * dnuz_ds * pv[4] / (L.c_gnd / rc.ceff0 * pv[2]);
         }
+    }
+
+    // GeoAc_Jacobian, 2DStratified.cpp:291-300
+    GEOAC_HD static double jacobian(const LaunchConsts&, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
+        if (!AMP) return 0.0;
+        const SegPos sp = seg_locate(T, yk[1], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
+        const double drds = c / rc.ceff0 * rc.costh, dzds = c / rc.ceff0 * yk[2];
+        return yk[0] * (drds * yk[4] - dzds * yk[3]);
     }
 
     // GeoAc_Amplitude at an arbitrary state (also evaluated along the path for the raypath rows)

@@ -191,6 +191,22 @@ struct EqGlobal {
         }
     }
 
+    // GeoAc_Jacobian, Global.cpp:594-608 (dp/ds carries 1/(r sin lat), the volume factor r^2 cos lat: App. A-6)
+    GEOAC_HD static double jacobian(const LaunchConsts&, const Table1D& T, const RayC&, const double* yk, int& cur) {
+        if (!AMP) return 0.0;
+        const SegPos sp = seg_locate(T, yk[0], cur);
+        const double c = sound_speed0(spl_f(T, TAB_T, sp));
+        const double u = spl_f(T, TAB_U, sp), v = spl_f(T, TAB_V, sp);
+        const double r = yk[0], nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
+        double sl, cl; sincos(yk[1], &sl, &cl);
+        const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
+        const double q0 = c * nu0 / nm, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm + u;
+        const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double dr_ds = q0 / qm, dt_ds = 1.0 / r * q1 / qm, dp_ds = 1.0 / (r * sl) * q2 / qm;
+        return r * r * cl * (dr_ds * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (dt_ds * yk[14] - dp_ds * yk[13])
+                             + yk[12] * (dt_ds * yk[8] - dp_ds * yk[7]));
+    }
+
     // GeoAc_Amplitude at an arbitrary state (Global.cpp:594-629; also evaluated along the path for the raypath rows)
     GEOAC_HD static double amplitude(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* yk, int& cur) {
         if (!AMP) return 0.0;

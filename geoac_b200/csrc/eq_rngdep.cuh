@@ -160,6 +160,20 @@ struct Eq3DRD {
         }
     }
 
+    // GeoAc_Jacobian, 3DRngDep.cpp:547-565
+    GEOAC_HD static double jacobian(const LaunchConsts&, const Grid3D& G, const RayC&, const double* yk, Cur3& cur) {
+        if (!AMP) return 0.0;
+        double w[4], dzs[3];
+        ms_wrappers<false, false, false>(G, yk[0], yk[1], yk[2], cur, w, dzs);
+        const double c = sqrt(kGamR * w[0]), u = w[1], v = w[2];
+        const double nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
+        const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
+        const double q0 = c * nu0 / nm + u, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm;
+        const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double xs = q0 / qm, ys = q1 / qm, zs = q2 / qm;
+        return xs * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (ys * yk[14] - zs * yk[13]) + yk[12] * (ys * yk[8] - zs * yk[7]);
+    }
+
     // GeoAc_Amplitude at an arbitrary state (3DRngDep.cpp:547-592; also evaluated along the path for the raypath rows)
     GEOAC_HD static double amplitude(const LaunchConsts& L, const Grid3D& G, const RayC& rc, const double* yk, Cur3& cur) {
         if (!AMP) return 0.0;
@@ -364,6 +378,22 @@ struct EqGlobalRD {
             y0[9]  = -pv[9]  + 2.0 * dnu_r_ds * pv[6] * den;
             y0[15] = -pv[15] + 2.0 * dnu_r_ds * pv[12] * den;
         }
+    }
+
+    // GeoAc_Jacobian (as Global.cpp:594-608)
+    GEOAC_HD static double jacobian(const LaunchConsts&, const Grid3D& G, const RayC&, const double* yk, Cur3& cur) {
+        if (!AMP) return 0.0;
+        double w[4], dzs[3];
+        ms_wrappers<true, false, false>(G, yk[1], yk[2], yk[0], cur, w, dzs);
+        const double c = sqrt(kGamR * w[0]), u = w[1], v = w[2];
+        const double r = yk[0], nu0 = yk[3], nu1 = yk[4], nu2 = yk[5];
+        double sl, cl; sincos(yk[1], &sl, &cl);
+        const double nm = sqrt(nu0 * nu0 + nu1 * nu1 + nu2 * nu2);
+        const double q0 = c * nu0 / nm, q1 = c * nu1 / nm + v, q2 = c * nu2 / nm + u;
+        const double qm = sqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double dr_ds = q0 / qm, dt_ds = 1.0 / r * q1 / qm, dp_ds = 1.0 / (r * sl) * q2 / qm;
+        return r * r * cl * (dr_ds * (yk[7] * yk[14] - yk[13] * yk[8]) - yk[6] * (dt_ds * yk[14] - dp_ds * yk[13])
+                             + yk[12] * (dt_ds * yk[8] - dp_ds * yk[7]));
     }
 
     // GeoAc_Amplitude at an arbitrary state (as Global.cpp:594-629; also evaluated along the path for the raypath rows)

@@ -45,6 +45,7 @@ struct TraceArgs {
     unsigned long long* counter_long; // next unclaimed entry of that leading region (claimed 8 rays at a time)
     int packet_refill;                // experiment knob: refill a warp only when all of its lanes are idle (always on for PacketMode sets)
     double* path; int32_t* path_rows; int path_stride; int64_t path_cap;   // raypath capture (PATHS kernels), else unused
+    double* caus; int32_t* caus_rows; int64_t caus_cap;                    // caustic events (PATHS kernels), else unused
     double* prev;                     // y_{k-1} scratch: [NEQ][grid * block] doubles (variants with a quadratic intercept)
 };
 
@@ -81,6 +82,8 @@ struct RecOut {
     double* rec; int32_t* status; int32_t* n_steps; int64_t n_slots; int n_rec;
     // raypath capture (PATHS kernels only): rows of GEOAC_PATH_NF doubles, `path_cap` rows reserved per ray
     double* path; int32_t* path_rows; int path_stride; int64_t path_cap;
+    // caustic events (PATHS kernels only): rows of GEOAC_CAUSTIC_NF doubles where the Jacobian changes sign
+    double* caus; int32_t* caus_rows; int64_t caus_cap;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -97,12 +100,13 @@ struct LaneD {
     double y[EQ::NEQ];
     typename EQ::RayC rc;
     double tt_total, att_total, tt_b, att_b, zmax;
+    double D_prev;          // Jacobian at the previous step (caustic capture)
 };
 template <class EQ>
 struct LaneI {
     typename EQ::Cursor cur;
     int bounce, ksteps;
-    int path_n;             // raypath rows emitted so far (PATHS kernels)
+    int path_n, caus_n;     // raypath rows / caustic events emitted so far (PATHS kernels)
     int64_t ray;
 };
 
@@ -114,8 +118,8 @@ template <class EQ> struct NeedsPrev { static constexpr bool value = !(EQ::VARIA
 
 template <class EQ>
 GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, int64_t idx, double theta, double phi) {
-    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.path_n = 0; n.cur = typename EQ::Cursor{};
-    d.tt_total = d.att_total = d.tt_b = d.att_b = d.zmax = 0.0;
+    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.path_n = 0; n.caus_n = 0; n.cur = typename EQ::Cursor{};
+    d.tt_total = d.att_total = d.tt_b = d.att_b = d.zmax = 0.0; d.D_prev = 0.0;
     EQ::init(L, T, theta, phi, d.rc, d.y, n.cur);
 }
 
@@ -161,7 +165,21 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
 
     if (!(brk || gnd || lim)) {
         if (PATHS) {
-            if (n.ksteps % o.path_stride == 0) {                  // row for state m = ksteps (m < k: never the sub-ground point)
+            if (o.caus_cap > 0) {
+                // WriteCaustics=True (Code/GeoAc3D_main.cpp:241-268): D_prev starts as the Jacobian of step 1 of each bounce; a
+                // row { position, travel time } wherever D * D_prev < 0
+                const double D = EQ::jacobian(L, T, d.rc, acc, n.cur);
+                if (n.ksteps > 1 && D * d.D_prev < 0.0) {
+                    if (n.caus_n < o.caus_cap) {
+                        double* row = o.caus + ((int64_t)n.ray * o.caus_cap + n.caus_n) * GEOAC_CAUSTIC_NF;
+                        row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = d.tt_total;
+                        row[4] = (double)n.bounce; row[5] = (double)n.ksteps;
+                    }
+                    n.caus_n++;
+                }
+                d.D_prev = D;
+            }
+            if (o.path_stride > 0 && n.ksteps % o.path_stride == 0) {   // row for state m = ksteps (m < k: never the sub-ground point)
                 if (n.path_n < o.path_cap) {
                     double* row = o.path + ((int64_t)n.ray * o.path_cap + n.path_n) * GEOAC_PATH_NF;
                     row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2];
@@ -184,7 +202,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     if (!gnd) {
         o.status[slot] = brk ? GEOAC_ST_BREAK : GEOAC_ST_LIMIT;
         o.n_steps[slot] = brk ? n.ksteps : L.step_limit;
-        if (PATHS) o.path_rows[n.ray] = n.path_n;
+        if (PATHS) { if (o.path_rows) o.path_rows[n.ray] = n.path_n; if (o.caus_rows) o.caus_rows[n.ray] = n.caus_n; }
         return false;
     }
     if (!L.seg_mode) { d.tt_total += d.tt_b; d.att_total += d.att_b; d.tt_b = 0.0; d.att_b = 0.0; }
@@ -202,7 +220,10 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     o.rec[(int64_t)GEOAC_F_MARGIN * o.n_slots + slot] = margin;
     o.status[slot] = GEOAC_ST_ARRIVAL;
     o.n_steps[slot] = n.ksteps;
-    if (n.bounce >= L.bounces) { if (PATHS) o.path_rows[n.ray] = n.path_n; return false; }
+    if (n.bounce >= L.bounces) {
+        if (PATHS) { if (o.path_rows) o.path_rows[n.ray] = n.path_n; if (o.caus_rows) o.caus_rows[n.ray] = n.caus_n; }
+        return false;
+    }
     double ym2[NEQ], y0[NEQ];
 #pragma unroll
     for (int i = 0; i < NEQ; i++) ym2[i] = NeedsPrev<EQ>::value ? prev[i * pstride] : 0.0;
@@ -284,6 +305,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
     const unsigned lane = threadIdx.x & 31;
     RecOut o; o.rec = a.rec; o.status = a.status; o.n_steps = a.n_steps; o.n_rec = a.n_rec; o.n_slots = a.n_rays * a.n_rec;
     o.path = a.path; o.path_rows = a.path_rows; o.path_stride = a.path_stride; o.path_cap = a.path_cap;
+    o.caus = a.caus; o.caus_rows = a.caus_rows; o.caus_cap = a.caus_cap;
     LaneD<EQ>& ld = *reinterpret_cast<LaneD<EQ>*>(lanes + (size_t)threadIdx.x * LaneLayout<EQ>::STRIDE);
     LaneI<EQ> li;
     // y_{k-1} history (quadratic intercept only): [eq][global thread] in an L2-resident global scratch, written once per step
@@ -356,7 +378,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             gi.cur.kz = __shfl_sync(0xffffffffu, li.cur.kz, owner);
             gi.bounce = __shfl_sync(0xffffffffu, li.bounce, owner); gi.ksteps = __shfl_sync(0xffffffffu, li.ksteps, owner);
             gi.ray = __shfl_sync(0xffffffffu, (long long)li.ray, owner);
-            gi.path_n = __shfl_sync(0xffffffffu, li.path_n, owner);
+            gi.path_n = __shfl_sync(0xffffffffu, li.path_n, owner); gi.caus_n = __shfl_sync(0xffffffffu, li.caus_n, owner);
             const int othread = (int)(threadIdx.x & ~31u) + owner;
             double* const rec = lanes + (size_t)othread * LaneLayout<EQ>::STRIDE;
             double* const gwork = rec + LaneLayout<EQ>::WORK;
@@ -371,9 +393,9 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             const int bkz = __shfl_sync(0xffffffffu, gi.cur.kz, src);
             const int bbo = __shfl_sync(0xffffffffu, gi.bounce, src), bks = __shfl_sync(0xffffffffu, gi.ksteps, src);
             const int bal = __shfl_sync(0xffffffffu, (int)alive, src);
-            const int bpn = __shfl_sync(0xffffffffu, gi.path_n, src);
+            const int bpn = __shfl_sync(0xffffffffu, gi.path_n, src), bcn = __shfl_sync(0xffffffffu, gi.caus_n, src);
             if (have_ray) {
-                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks; li.path_n = bpn;
+                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks; li.path_n = bpn; li.caus_n = bcn;
                 have_ray = bal != 0;
                 my_steps++;
             }

@@ -58,7 +58,9 @@ enum {
                                   was crossed; values within ~1e-9 of 0 or -1 flag near-threshold rays */
     GEOAC_NFIELDS      = 26,
     /* one raypath row (geoac_trace_paths): state[0..2], amplitude (linear), absorption sum, travel-time sum, bounce, step */
-    GEOAC_PATH_NF      = 8
+    GEOAC_PATH_NF      = 8,
+    /* one caustic event: state[0..2] at the step where the Jacobian changed sign, travel-time sum, bounce, step */
+    GEOAC_CAUSTIC_NF   = 6
 };
 
 /* per-slot status */
@@ -140,10 +142,15 @@ int geoac_trace_device(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, co
  *   path      : n_rays * path_cap * GEOAC_PATH_NF doubles, row r of ray i at path[(i*path_cap + r)*GEOAC_PATH_NF]
  *   path_rows : n_rays int32, rows PRODUCED for the ray (if > path_cap the surplus was dropped)
  * The front end prints lat/lon in degrees, max(z, 0), 20 log10(amplitude) and -absorption exactly as it does today.
- * Requires params.accum_per_segment = 1 (the accumulation convention of that mode; always so for 2D). */
+ * With caustic_cap > 0 the call also returns the WriteCaustics=True rows (:241-268): wherever the Jacobian determinant
+ * (GeoAc_Jacobian) changes sign between consecutive steps, one row of GEOAC_CAUSTIC_NF doubles { state[0], state[1],
+ * state[2], travel-time sum, bounce index, step index }, at most caustic_cap per ray (caustic / caustic_rows laid out like
+ * path / path_rows; needs calc_amp = 1).  Either capture may be switched off (path_stride = 0 or caustic_cap = 0), not both.
+ * Requires params.accum_per_segment = 1 (the accumulation convention of those modes; always so for 2D). */
 int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
                       double* rec, int32_t* status, int32_t* n_steps,
-                      int path_stride, int64_t path_cap, double* path, int32_t* path_rows);
+                      int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
+                      int64_t caustic_cap, double* caustic, int32_t* caustic_rows);
 
 /* Optional: allocate the device staging geoac_trace() needs for batches of up to n_rays rays (with the current
  * `bounces`) ahead of time, so that the first trace call does not pay for it.  geoac_trace() grows it on demand anyway. */

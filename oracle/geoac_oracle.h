@@ -81,7 +81,8 @@ int64_t orc_trace(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_
  * path_cap rows kept per ray, path_rows[ray] = rows produced); needs accum_per_segment semantics. */
 int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_rays,
                         const double* theta, const double* phi, double* rec, int32_t* status, int32_t* n_steps,
-                        int path_stride, int64_t path_cap, double* path, int32_t* path_rows);
+                        int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
+                        int64_t caus_cap, double* caus, int32_t* caus_rows);
 
 /* GeoAc_SetPropRegion for this atmosphere: fills vert_limit / range_limit / box limits of *p. */
 void orc_set_prop_region(int variant, const orc_atmo* atmo, geoac_params* p);

@@ -108,6 +108,16 @@ static double amp2d(orc_ray* r, const double* yk) {
     return 1.0 / (4.0 * ORC_PI) * sqrt(fabs(Amp_Num / Amp_Den));
 }
 
+/* GeoAc_Jacobian :291-300 on its own (WriteCaustics) */
+static double jac2d(orc_ray* r, const double* yk) {
+    src2d* s = SRC(r); orc_atmo* a = ATM(r);
+    double rr = yk[0], z = yk[1];
+    double cz = a->c(a, 0.0, 0.0, z);
+    double drds = cz / s->c_eff_0 * cos(r->theta);
+    double dzds = cz / s->c_eff_0 * yk[2];
+    return rr * (drds * yk[4] - dzds * yk[3]);
+}
+
 static double alt2d(orc_ray* r, const double* y) { (void)r; return y[1]; }
 
 /* results row of Code/GeoAc2D_main.cpp:216-226: inclination is printed as -theta [deg] */
@@ -117,4 +127,4 @@ static void fin2d(orc_ray* r, const double* ym1, const double* yk, double tt, do
     *margin = (yk[1] - ATM(r)->z_grnd) / fabs(yk[1] - ym1[1]);
 }
 
-const orc_eqset orc_eq_2d = { 6, 3, init2d, update2d, rhs2d, setds2d, brk2d, gnd2d, tt2d, sb2d, amp2d, reflect2d, alt2d, fin2d };
+const orc_eqset orc_eq_2d = { 6, 3, init2d, update2d, rhs2d, setds2d, brk2d, gnd2d, tt2d, sb2d, amp2d, jac2d, reflect2d, alt2d, fin2d };

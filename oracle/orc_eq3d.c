@@ -243,4 +243,4 @@ static void fin3d(orc_ray* r, const double* ym1, const double* yk, double tt, do
     *margin = (yk[2] - a->z_grnd) / fabs(yk[2] - ym1[2]);
 }
 
-const orc_eqset orc_eq_3d = { 12, 4, init3d, update3d, rhs3d, setds3d, brk3d, gnd3d, tt3d, sb3d, amp3d, reflect3d, alt3d, fin3d };
+const orc_eqset orc_eq_3d = { 12, 4, init3d, update3d, rhs3d, setds3d, brk3d, gnd3d, tt3d, sb3d, amp3d, jac3d, reflect3d, alt3d, fin3d };

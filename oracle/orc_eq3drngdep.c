@@ -246,4 +246,4 @@ static void fin3r(orc_ray* r, const double* ym1, const double* yk, double tt, do
     *margin = (yk[2] - a->z_grnd) / fabs(yk[2] - ym1[2]);
 }
 
-const orc_eqset orc_eq_3drngdep = { 18, 6, init3r, update3r, rhs3r, setds3r, brk3r, gnd3r, tt3r, sb3r, amp3r, reflect3r, alt3r, fin3r };
+const orc_eqset orc_eq_3drngdep = { 18, 6, init3r, update3r, rhs3r, setds3r, brk3r, gnd3r, tt3r, sb3r, amp3r, jac3r, reflect3r, alt3r, fin3r };

@@ -335,5 +335,5 @@ static void fin_common(orc_ray* r, const double* ym1, const double* yk, double t
 static void fing(orc_ray* r, const double* ym1, const double* yk, double tt, double* i, double* b, double* x, double* m) { fin_common(r, ym1, yk, tt, -1.0, i, b, x, m); }
 static void fingr(orc_ray* r, const double* ym1, const double* yk, double tt, double* i, double* b, double* x, double* m) { fin_common(r, ym1, yk, tt, 1.0, i, b, x, m); }
 
-const orc_eqset orc_eq_global       = { 18, 6, initg, updateg,  rhsg, setdsg, brkg,  gndg, ttg, sbg, ampg, reflectg, altg, fing };
-const orc_eqset orc_eq_globalrngdep = { 18, 6, initg, updategr, rhsg, setdsg, brkgr, gndg, ttg, sbg, ampg, reflectg, altg, fingr };
+const orc_eqset orc_eq_global       = { 18, 6, initg, updateg,  rhsg, setdsg, brkg,  gndg, ttg, sbg, ampg, jacg, reflectg, altg, fing };
+const orc_eqset orc_eq_globalrngdep = { 18, 6, initg, updategr, rhsg, setdsg, brkgr, gndg, ttg, sbg, ampg, jacg, reflectg, altg, fingr };

@@ -23,6 +23,7 @@ typedef struct orc_eqset {
     void   (*tt_seg)(orc_ray*, const double* ya, const double* yb, double* acc);
     void   (*sb_seg)(orc_ray*, const double* ya, const double* yb, double* acc);
     double (*amplitude)(orc_ray*, const double* yk);
+    double (*jacobian)(orc_ray*, const double* yk);      /* GeoAc_Jacobian: sign changes mark caustics */
     void   (*reflect)(orc_ray*, const double* ykm2, const double* ykm1, const double* yk, double* y0);
     double (*altitude)(orc_ray*, const double* y);
     /* fills inclination / back azimuth / aux / margin of the record (theta_deg-free: uses ray->theta/phi) */

@@ -47,10 +47,12 @@ static int propagate_rk4(const orc_eqset* e, orc_ray* r, double (*sol)[ORC_MAXEQ
 
 /* orc_trace + the raypath rows of WriteRays=True (Code/GeoAc3D_main.cpp:249-262 and the sibling mains): with
  * path_stride > 0 one row { state[0..2], amplitude, attenuation, travel time, bounce, step } is appended per ray every
- * path_stride steps of the per-segment post pass (requires accum_per_segment semantics, which the mains use then). */
+ * path_stride steps of the per-segment post pass (requires accum_per_segment semantics, which the mains use then); with
+ * caus_cap > 0 also the WriteCaustics=True rows { state[0..2], travel time, bounce, step } where the Jacobian changes sign. */
 int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_rays,
                         const double* theta, const double* phi, double* rec, int32_t* status, int32_t* n_steps,
-                        int path_stride, int64_t path_cap, double* path, int32_t* path_rows) {
+                        int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
+                        int64_t caus_cap, double* caus, int32_t* caus_rows) {
     const orc_eqset* e = eqset_for(variant);
     if (!e || !atmo || !p) return -1;
     const int n_rec = p->bounces + 1;
@@ -63,7 +65,7 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
     atmo->z_grnd = p->z_grnd; atmo->tweak_abs = p->tweak_abs;
     const int per_bounce_zmax = (variant == GEOAC_3D_RNGDEP || variant == GEOAC_GLOBAL_RNGDEP);  /* App. A-3 */
     const int seg_mode = (variant == GEOAC_2D) ? 1 : p->accum_per_segment;                      /* App. A-2 */
-    if (path_stride > 0 && !seg_mode) return -1;
+    if ((path_stride > 0 || caus_cap > 0) && !seg_mode) return -1;
 
     orc_ray ray; memset(&ray, 0, sizeof ray);
     ray.atmo = atmo; ray.prm = p; ray.calc_amp = p->calc_amp;
@@ -73,13 +75,16 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
         ray.theta = theta[iray]; ray.phi = phi[iray];
         e->init(&ray, sol[0]);
         double tt = 0.0, att = 0.0, zmax = 0.0;
-        int32_t prow = 0;
+        int32_t prow = 0, crow = 0;
         for (int b = 0; b < n_rec; b++) {
             int64_t slot = iray * n_rec + b;
             int left; int k = propagate_rk4(e, &ray, sol, step_limit, &left);
             total += k;
             if (seg_mode) {
+                double D = 0.0, D_prev = 0.0;
+                if (caus_cap > 0) D_prev = e->jacobian(&ray, sol[1]);              /* Code/GeoAc3D_main.cpp:245 */
                 for (int m = 1; m < k; m++) {
+                    if (caus_cap > 0) D = e->jacobian(&ray, sol[m]);
                     e->tt_seg(&ray, sol[m - 1], sol[m], &tt); e->sb_seg(&ray, sol[m - 1], sol[m], &att);
                     if (path_stride > 0 && m % path_stride == 0) {
                         if (prow < path_cap) {
@@ -90,6 +95,14 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
                         }
                         prow++;
                     }
+                    if (caus_cap > 0 && D * D_prev < 0.0) {                        /* :263-268 */
+                        if (crow < caus_cap) {
+                            double* row = caus + (iray * caus_cap + crow) * GEOAC_CAUSTIC_NF;
+                            row[0] = sol[m][0]; row[1] = sol[m][1]; row[2] = sol[m][2]; row[3] = tt; row[4] = (double)b; row[5] = (double)m;
+                        }
+                        crow++;
+                    }
+                    if (caus_cap > 0) D_prev = D;
                 }
             } else {
                 double t = 0.0, a = 0.0;
@@ -99,6 +112,7 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
             }
             n_steps[slot] = k;
             if (path_stride > 0) path_rows[iray] = prow;
+            if (caus_cap > 0) caus_rows[iray] = crow;
             if (left) { status[slot] = GEOAC_ST_BREAK; break; }
             if (k >= step_limit) { status[slot] = GEOAC_ST_LIMIT; break; }
             status[slot] = GEOAC_ST_ARRIVAL;
@@ -128,7 +142,7 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
 
 int64_t orc_trace(int variant, orc_atmo* atmo, const geoac_params* p, int64_t n_rays,
                   const double* theta, const double* phi, double* rec, int32_t* status, int32_t* n_steps) {
-    return orc_trace_paths(variant, atmo, p, n_rays, theta, phi, rec, status, n_steps, 0, 0, 0, 0);
+    return orc_trace_paths(variant, atmo, p, n_rays, theta, phi, rec, status, n_steps, 0, 0, 0, 0, 0, 0, 0);
 }
 
 /* GeoAc_SetPropRegion: G2S_Spline1D.cpp:22-28, G2S_GlobalSpline1D.cpp:22-30; grids: orc_mspline.c */

@@ -105,7 +105,7 @@ def default_params(variant, atmo=None):
     return p
 
 
-def trace_paths(variant, atmo, params, theta, phi, stride, cap):
+def trace_paths(variant, atmo, params, theta, phi, stride, cap, caus_cap=0):
     """As trace(), plus the raypath rows (accum_per_segment semantics): path [n][cap][PATH_NF], path_rows [n]."""
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     phi = np.ascontiguousarray(phi, dtype=np.float64)
@@ -114,15 +114,17 @@ def trace_paths(variant, atmo, params, theta, phi, stride, cap):
     rec = np.zeros((abi.NFIELDS, n, n_rec))
     status = np.zeros((n, n_rec), dtype=np.int32)
     n_steps = np.zeros((n, n_rec), dtype=np.int32)
-    path = np.zeros((n, cap, abi.PATH_NF)); rows = np.zeros(n, dtype=np.int32)
+    path = np.zeros((n, max(cap, 1), abi.PATH_NF)); rows = np.zeros(n, dtype=np.int32)
+    caus = np.zeros((n, max(caus_cap, 1), abi.CAUSTIC_NF)); crow = np.zeros(n, dtype=np.int32)
     L = lib()
     L.orc_trace_paths.restype = C.c_int64
-    L.orc_trace_paths.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams), C.c_int64, dp, dp, dp, ip, ip, C.c_int, C.c_int64, dp, ip]
+    L.orc_trace_paths.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams), C.c_int64, dp, dp, dp, ip, ip, C.c_int, C.c_int64, dp, ip, C.c_int64, dp, ip]
     total = L.orc_trace_paths(variant, atmo.h, C.byref(params), n, _p(theta), _p(phi), _p(rec), status.ctypes.data_as(ip),
-                              n_steps.ctypes.data_as(ip), stride, cap, _p(path), rows.ctypes.data_as(ip))
+                              n_steps.ctypes.data_as(ip), stride, cap, _p(path), rows.ctypes.data_as(ip), caus_cap, _p(caus), crow.ctypes.data_as(ip))
     if total < 0:
         raise RuntimeError("orc_trace_paths failed")
-    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": int(total), "path": path, "path_rows": rows}
+    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": int(total), "path": path, "path_rows": rows,
+            "caustic": caus, "caustic_rows": crow}
 
 
 def trace(variant, atmo, params, theta, phi):
@@ -157,6 +159,8 @@ def run_ref(variant, profile_args, out_path, **kv):
     ref = read_ref_bin(out_path)
     if int(kv.get("path_stride", 0)) > 0:
         ref["path"] = np.fromfile(out_path + ".path", dtype=np.float64).reshape(-1, 9)     # ray, state[0..2], amp, att, tt, bounce, step
+    if int(kv.get("caustics", 0)) > 0:
+        ref["caustic"] = np.fromfile(out_path + ".caus", dtype=np.float64).reshape(-1, 7)  # ray, state[0..2], tt, bounce, step
     return ref, info
 
 

@@ -62,7 +62,7 @@ int main(int argc, char** argv) {
     const char* out_path = argv[1];
     double theta_min = 0.5, theta_max = 45.0, theta_step = 0.5;
     double phi_min = -90.0, phi_max = -90.0, phi_step = 1.0;
-    int bounces = 2, accum_mode = 0, stride = 1, offset = 0, quiet = 1, path_stride = 0;
+    int bounces = 2, accum_mode = 0, stride = 1, offset = 0, quiet = 1, path_stride = 0, caustics = 0;
     double x_src = 0.0, y_src = 0.0, z_src = 0.0, lat_src = 30.0, lon_src = 0.0;
     bool have_src = false;
     bool CalcAmp = true;
@@ -99,6 +99,7 @@ int main(int argc, char** argv) {
         else if (!strncmp(a, "rng_max=", 8))     GeoAc_range_limit = atof(a + 8);
 #endif
         else if (!strncmp(a, "accum_mode=", 11)) accum_mode = atoi(a + 11);
+        else if (!strncmp(a, "caustics=", 9))    caustics = atoi(a + 9);           // WriteCaustics=True: rows where the Jacobian changes sign
         else if (!strncmp(a, "path_stride=", 12)) path_stride = atoi(a + 12);   // WriteRays=True: one raypath row every N steps (the mains use 25)
         else if (!strncmp(a, "stride=", 7))      stride = atoi(a + 7);
         else if (!strncmp(a, "offset=", 7))      offset = atoi(a + 7);
@@ -133,6 +134,7 @@ int main(int argc, char** argv) {
 
     std::vector<double> angles;                 // theta_deg, phi_deg per traced ray
     std::vector<double> recs;
+    std::vector<double> caus;                   // caustic rows: ray, state[0..2], travel time, bounce, step
     std::vector<double> paths;                  // raypath rows: ray, state[0..2], amplitude, attenuation, travel time, bounce, step
     long total_steps = 0; double t_rk4 = 0.0, t_post = 0.0, t_all0 = now_s();
     long ray_index = 0, n_traced = 0;
@@ -164,7 +166,10 @@ int main(int argc, char** argv) {
             k = GeoAc_Propagate_RK4(solution, BreakCheck);
             double t1 = now_s();
             if (accum_mode) {
+                double D = 0.0, D_prev = 0.0;
+                if (caustics) D_prev = GeoAc_Jacobian(solution, 1);                 // Code/GeoAc3D_main.cpp:245
                 for (int m = 1; m < k; m++) {
+                    if (caustics) D = GeoAc_Jacobian(solution, m);
                     GeoAc_TravelTimeSegment(travel_time_sum, solution, m - 1, m);
                     GeoAc_SB_AttenSegment(attenuation, solution, m - 1, m, freq);
                     if (path_stride > 0 && m % path_stride == 0) {            // Code/GeoAc3D_main.cpp:254-262 (and the sibling mains)
@@ -172,6 +177,11 @@ int main(int argc, char** argv) {
                                                 CalcAmp ? GeoAc_Amplitude(solution, m) : 0.0, attenuation, travel_time_sum, (double)bnc, (double)m };
                         paths.insert(paths.end(), row, row + 9);
                     }
+                    if (caustics && D * D_prev < 0.0) {                              // :263-268
+                        const double row[7] = { (double)(n_traced - 1), solution[m][0], solution[m][1], solution[m][2], travel_time_sum, (double)bnc, (double)m };
+                        caus.insert(caus.end(), row, row + 7);
+                    }
+                    if (caustics) D_prev = D;
                 }
             } else {
                 travel_time_sum += GeoAc_TravelTime(solution, k);
@@ -248,6 +258,13 @@ int main(int argc, char** argv) {
     fwrite(angles.data(), sizeof(double), angles.size(), f);
     fwrite(recs.data(), sizeof(double), recs.size(), f);
     fclose(f);
+    if (caustics) {
+        std::string cp = std::string(out_path) + ".caus";
+        FILE* g = fopen(cp.c_str(), "wb");
+        if (!g) { perror("open caustics out"); return 1; }
+        fwrite(caus.data(), sizeof(double), caus.size(), g);
+        fclose(g);
+    }
     if (path_stride > 0) {
         std::string pp = std::string(out_path) + ".path";
         FILE* g = fopen(pp.c_str(), "wb");

@@ -62,33 +62,39 @@ def _paths(nr, stride, cap):
     return path, rows
 
 
-def trace(variant, params, atmo_arrays, theta, phi, path_stride=0, path_cap=0):
+def _caus(nr, cap):
+    return np.zeros((nr, max(cap, 1), abi.CAUSTIC_NF)), np.zeros(nr, dtype=np.int32)
+
+
+def trace(variant, params, atmo_arrays, theta, phi, path_stride=0, path_cap=0, caus_cap=0):
     L = C.CDLL(build())
     L.emul_trace_1d.restype = C.c_long
-    L.emul_trace_1d.argtypes = [C.c_int, C.POINTER(abi.GeoacParams), C.c_int, dp, C.c_long, dp, dp, dp, ip, ip, C.c_int, C.c_long, dp, ip]
+    L.emul_trace_1d.argtypes = [C.c_int, C.POINTER(abi.GeoacParams), C.c_int, dp, C.c_long, dp, dp, dp, ip, ip, C.c_int, C.c_long, dp, ip, C.c_long, dp, ip]
     tab, n = make_table(variant == abi.GEOAC_GLOBAL, *atmo_arrays)
     theta = np.ascontiguousarray(theta, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
     nr = len(theta); n_rec = params.bounces + 1
     rec = np.zeros((abi.NFIELDS, nr, n_rec)); status = np.zeros((nr, n_rec), dtype=np.int32); n_steps = np.zeros((nr, n_rec), dtype=np.int32)
     path, rows = _paths(nr, path_stride, path_cap)
+    caus, crow = _caus(nr, caus_cap)
     total = L.emul_trace_1d(variant, C.byref(params), n, tab.ctypes.data_as(dp), nr, theta.ctypes.data_as(dp), phi.ctypes.data_as(dp),
                             rec.ctypes.data_as(dp), status.ctypes.data_as(ip), n_steps.ctypes.data_as(ip),
-                            path_stride, path_cap, path.ctypes.data_as(dp), rows.ctypes.data_as(ip))
-    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total, "path": path, "path_rows": rows}
+                            path_stride, path_cap, path.ctypes.data_as(dp), rows.ctypes.data_as(ip), caus_cap, caus.ctypes.data_as(dp), crow.ctypes.data_as(ip))
+    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total, "path": path, "path_rows": rows, "caustic": caus, "caustic_rows": crow}
 
 
-def trace_grid(variant, params, grid_arrays, theta, phi, path_stride=0, path_cap=0):
+def trace_grid(variant, params, grid_arrays, theta, phi, path_stride=0, path_cap=0, caus_cap=0):
     """Range-dependent variants: grid_arrays = ax0, ax1, axz, T, u, v, rho as geoac_set_atmosphere_3d takes them."""
     L = C.CDLL(build())
     L.emul_trace_3d.restype = C.c_long
     L.emul_trace_3d.argtypes = [C.c_int, C.POINTER(abi.GeoacParams), C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp, C.c_long, dp, dp, dp, ip, ip,
-                                C.c_int, C.c_long, dp, ip]
+                                C.c_int, C.c_long, dp, ip, C.c_long, dp, ip]
     arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in grid_arrays]
     theta = np.ascontiguousarray(theta, dtype=np.float64); phi = np.ascontiguousarray(phi, dtype=np.float64)
     nr = len(theta); n_rec = params.bounces + 1
     rec = np.zeros((abi.NFIELDS, nr, n_rec)); status = np.zeros((nr, n_rec), dtype=np.int32); n_steps = np.zeros((nr, n_rec), dtype=np.int32)
     path, rows = _paths(nr, path_stride, path_cap)
+    caus, crow = _caus(nr, caus_cap)
     total = L.emul_trace_3d(variant, C.byref(params), len(arrs[0]), len(arrs[1]), len(arrs[2]), *[a.ctypes.data_as(dp) for a in arrs], nr,
                             theta.ctypes.data_as(dp), phi.ctypes.data_as(dp), rec.ctypes.data_as(dp), status.ctypes.data_as(ip), n_steps.ctypes.data_as(ip),
-                            path_stride, path_cap, path.ctypes.data_as(dp), rows.ctypes.data_as(ip))
-    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total, "path": path, "path_rows": rows}
+                            path_stride, path_cap, path.ctypes.data_as(dp), rows.ctypes.data_as(ip), caus_cap, caus.ctypes.data_as(dp), crow.ctypes.data_as(ip))
+    return {"rec": rec, "status": status, "n_steps": n_steps, "total_steps": total, "path": path, "path_rows": rows, "caustic": caus, "caustic_rows": crow}

@@ -43,7 +43,7 @@ static void run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const
     std::vector<Cnt> rec((size_t)GEOAC_NFIELDS * n * n_rec), prev(EQ::NEQ), work(2 * EQ::NEQ);
     std::vector<int32_t> status(n * n_rec), nsteps(n * n_rec);
     RecOut o; o.rec = rec.data(); o.status = status.data(); o.n_steps = nsteps.data(); o.n_rec = n_rec; o.n_slots = n * n_rec;
-    o.path = nullptr; o.path_rows = nullptr; o.path_stride = 0; o.path_cap = 0;
+    o.path = nullptr; o.path_rows = nullptr; o.path_stride = 0; o.path_cap = 0; o.caus = nullptr; o.caus_rows = nullptr; o.caus_cap = 0;
     cnt::tally() = cnt::Tally();
     long steps = 0;
     for (long i = 0; i < n; i++) {

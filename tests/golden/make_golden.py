@@ -70,13 +70,13 @@ CASES = {
     "globalrngdep_c5": (abi.GEOAC_GLOBAL_RNGDEP, "grid_c5", dict(theta_min=6, theta_max=46, theta_step=20, phi_min=20, phi_max=200, phi_step=140, bounces=2,
                                                                  lat_src=35, lon_src=0)),
     # raypath rows (WriteRays=True: one row every 25 steps with the amplitude at that point), all five variants
-    "2d_path": (abi.GEOAC_2D, [TOY], dict(theta_min=5, theta_max=36, theta_step=15, bounces=1, path_stride=25)),
-    "3d_path": (abi.GEOAC_3D, [TOY], dict(theta_min=5, theta_max=46, theta_step=20, phi_min=30, phi_max=210, phi_step=170, bounces=1, accum_mode=1, path_stride=25)),
-    "global_path": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=10, theta_max=31, theta_step=20, phi_min=60, phi_max=60, phi_step=1, bounces=1, accum_mode=1, path_stride=25)),
+    "2d_path": (abi.GEOAC_2D, [TOY], dict(theta_min=5, theta_max=36, theta_step=15, bounces=1, path_stride=25, caustics=1)),
+    "3d_path": (abi.GEOAC_3D, [TOY], dict(theta_min=5, theta_max=46, theta_step=20, phi_min=30, phi_max=210, phi_step=170, bounces=1, accum_mode=1, path_stride=25, caustics=1)),
+    "global_path": (abi.GEOAC_GLOBAL, [TOY], dict(theta_min=10, theta_max=31, theta_step=20, phi_min=60, phi_max=60, phi_step=1, bounces=1, accum_mode=1, path_stride=25, caustics=1)),
     "3drngdep_path": (abi.GEOAC_3D_RNGDEP, "grid_cart", dict(theta_min=12, theta_max=33, theta_step=20, phi_min=70, phi_max=70, phi_step=1, bounces=1,
-                                                             x_src=13.7, y_src=-21.3, accum_mode=1, path_stride=25)),
+                                                             x_src=13.7, y_src=-21.3, accum_mode=1, path_stride=25, caustics=1)),
     "globalrngdep_path": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(theta_min=12, theta_max=33, theta_step=20, phi_min=70, phi_max=70, phi_step=1, bounces=1,
-                                                                     lat_src=33.3, lon_src=1.7, accum_mode=1, path_stride=25)),
+                                                                     lat_src=33.3, lon_src=1.7, accum_mode=1, path_stride=25, caustics=1)),
     "3d_elevated": (abi.GEOAC_3D, [TOY], dict(theta_min=-10, theta_max=40, theta_step=10, azimuth=-60, bounces=2, z_src=12.5, z_grnd=1.2, freq=0.5, rng_max=600, alt_max=120)),
 }
 
@@ -101,6 +101,8 @@ def main(names):
         out = os.path.join(GOLD, name + ".npz")
         if "path" in ref:
             extra["path"] = ref["path"]
+        if "caustic" in ref:
+            extra["caustic"] = ref["caustic"]
         np.savez_compressed(out, variant=variant, **extra, keys=np.array(sorted(f"{k}={v}" for k, v in kv.items())),
                             theta_deg=ref["theta_deg"], phi_deg=ref["phi_deg"], rec=ref["rec"], status=ref["status"],
                             n_steps=ref["n_steps"], eq_cnt=ref["eq_cnt"], vert_limit=info["vert_limit"])

@@ -32,12 +32,12 @@ static long run_mode(const LaunchConsts& L, const typename EQ::Atmo& T, long n, 
 }
 template <class EQ>
 static long run(const LaunchConsts& L, const typename EQ::Atmo& T, long n, const double* th, const double* ph, RecOut o) {
-    return o.path_stride > 0 ? run_mode<EQ, true>(L, T, n, th, ph, o) : run_mode<EQ, false>(L, T, n, th, ph, o);
+    return (o.path_stride > 0 || o.caus_cap > 0) ? run_mode<EQ, true>(L, T, n, th, ph, o) : run_mode<EQ, false>(L, T, n, th, ph, o);
 }
 
 extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const double* table, long n_rays,
                               const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps,
-                              int path_stride, long path_cap, double* path, int32_t* path_rows) {
+                              int path_stride, long path_cap, double* path, int32_t* path_rows, long caus_cap, double* caus, int32_t* caus_rows) {
     Table1D T; T.base = table; T.n = n; T.xmin = table[TAB_X]; T.xmax = table[(size_t)(n - 1) * TAB_NARR + TAB_X]; T.jump_scale = 0.0;
     LaunchConsts L; std::memset(&L, 0, sizeof L);
     L.ds_min = p->ds_min; L.ds_max = p->ds_max; L.vert_limit = p->vert_limit; L.range_limit = p->range_limit;
@@ -52,6 +52,7 @@ extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const d
     fill_launch_consts_1d(L, T, variant);
     RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
     o.path = path; o.path_rows = path_rows; o.path_stride = path_stride; o.path_cap = path_cap;
+    o.caus = caus; o.caus_rows = caus_rows; o.caus_cap = caus_cap;
     std::fill(rec, rec + (size_t)GEOAC_NFIELDS * o.n_slots, 0.0);
     std::fill(status, status + o.n_slots, 0); std::fill(n_steps, n_steps + o.n_slots, 0);
     const bool amp = p->calc_amp != 0;
@@ -69,7 +70,7 @@ extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const d
 extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1, int nz, const double* ax0, const double* ax1, const double* axz,
                               const double* Tf, const double* uf, const double* vf, const double* rhof, long n_rays,
                               const double* th, const double* ph, double* rec, int32_t* status, int32_t* n_steps,
-                              int path_stride, long path_cap, double* path, int32_t* path_rows) {
+                              int path_stride, long path_cap, double* path, int32_t* path_rows, long caus_cap, double* caus, int32_t* caus_rows) {
     const bool glob = variant == GEOAC_GLOBAL_RNGDEP;
     std::vector<double> z, tuv, rh;
     build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, Tf, uf, vf, rhof, z, tuv, rh);
@@ -91,6 +92,7 @@ extern "C" long emul_trace_3d(int variant, const geoac_params* p, int n0, int n1
     fill_launch_consts_3d(L, g, variant);
     RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
     o.path = path; o.path_rows = path_rows; o.path_stride = path_stride; o.path_cap = path_cap;
+    o.caus = caus; o.caus_rows = caus_rows; o.caus_cap = caus_cap;
     std::fill(rec, rec + (size_t)GEOAC_NFIELDS * o.n_slots, 0.0);
     std::fill(status, status + o.n_slots, 0); std::fill(n_steps, n_steps + o.n_slots, 0);
     const bool amp = p->calc_amp != 0;

@@ -54,9 +54,13 @@ def test_cuda_raypath_rows_match_reference(name):
     tr = _tracer_for(variant, kv, d)
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
     cap = 2000
-    out = tr.trace_paths(th, ph, int(kv["path_stride"]), cap)
+    out = tr.trace_paths(th, ph, int(kv["path_stride"]), cap, caustic_cap=32)
     want_path, want_rows = util.golden_paths(d, cap)
     problems = util.compare_paths(out["path"], out["path_rows"], want_path, want_rows, util.RTOL, 1e-6, name)
+    want_c, want_crows = util.golden_caustics(d, 32)                     # WriteCaustics=True events
+    problems += util.compare_caustics(out["caustic"], out["caustic_rows"], want_c, want_crows, util.RTOL, name)
+    only_c = tr.trace_paths(th, ph, 0, 0, caustic_cap=32)               # events without raypath rows
+    assert np.array_equal(only_c["caustic"], out["caustic"]) and np.array_equal(only_c["caustic_rows"], out["caustic_rows"])
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
     rp, _ = util.compare_records(out, want, variant, tr.params.calc_amp, util.RTOL, name, amp_rtol=AMP_RTOL)
     assert not (problems + rp), "\n".join((problems + rp)[:10])

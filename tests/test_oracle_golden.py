@@ -49,10 +49,13 @@ def test_oracle_raypath_rows_bit_exact_vs_reference(oracle, name):
     p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
     cap = 2000
-    out = oracle.trace_paths(variant, at, p, th, ph, int(kv["path_stride"]), cap)
+    out = oracle.trace_paths(variant, at, p, th, ph, int(kv["path_stride"]), cap, caus_cap=32)
     want_path, want_rows = util.golden_paths(d, cap)
     assert np.array_equal(out["path_rows"], want_rows)
     assert np.array_equal(out["path"], want_path)
+    want_c, want_crows = util.golden_caustics(d, 32)                     # WriteCaustics=True rows
+    assert want_crows.sum() > 0
+    assert np.array_equal(out["caustic_rows"], want_crows) and np.array_equal(out["caustic"], want_c)
     assert np.array_equal(out["status"], d["status"]) and np.array_equal(out["n_steps"], d["n_steps"])
 
 
@@ -67,14 +70,16 @@ def test_device_math_host_emulation_raypaths(oracle, name):
         arrs = util.load_grid(d)
         at = oracle.atmo3d(util.is_global(variant), *arrs)
         p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
-        out = emul.trace_grid(variant, p, arrs, th, ph, int(kv["path_stride"]), cap)
+        out = emul.trace_grid(variant, p, arrs, th, ph, int(kv["path_stride"]), cap, 32)
     else:
         arrs = oracle.load_met_1d(util.profile_path(d), global_taper=util.is_global(variant))
         at = oracle.atmo1d(util.is_global(variant), *arrs)
         p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
-        out = emul.trace(variant, p, arrs, th, ph, int(kv["path_stride"]), cap)
+        out = emul.trace(variant, p, arrs, th, ph, int(kv["path_stride"]), cap, 32)
     want_path, want_rows = util.golden_paths(d, cap)
     problems = util.compare_paths(out["path"], out["path_rows"], want_path, want_rows, util.RTOL, 1e-6, name)
+    want_c, want_crows = util.golden_caustics(d, 32)
+    problems += util.compare_caustics(out["caustic"], out["caustic_rows"], want_c, want_crows, util.RTOL, name)
     assert not problems, "\n".join(problems[:10])
 
 

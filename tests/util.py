@@ -160,3 +160,32 @@ def compare_paths(got_path, got_rows, want_path, want_rows, rtol, amp_rtol, labe
                 j = int(np.argmax(rel))
                 problems.append(f"{label}: ray {i} path field {f}: max rel diff {rel.max():.3e} > {tol:g} at row {j} (got {g[j, f]!r}, want {w[j, f]!r})")
     return problems
+
+
+def golden_caustics(d, cap):
+    """Caustic rows of a golden case (rows x {ray, state[0..2], tt, bounce, step}) -> caustic [n][cap][CAUSTIC_NF], rows [n]."""
+    n = len(d["theta_deg"])
+    caus = np.zeros((n, cap, abi.CAUSTIC_NF)); rows = np.zeros(n, dtype=np.int32)
+    for r in d["caustic"]:
+        i = int(r[0])
+        assert rows[i] < cap
+        caus[i, rows[i]] = r[1:]
+        rows[i] += 1
+    return caus, rows
+
+
+def compare_caustics(got, got_rows, want, want_rows, rtol, label=""):
+    """Event counts, bounce and step indices exact (the step at which the Jacobian changes sign is a discrete output);
+    positions relative to the path extent and travel time to rtol."""
+    if not np.array_equal(got_rows, want_rows):
+        return [f"{label}: caustic counts differ: {got_rows.tolist()} vs {want_rows.tolist()}"]
+    problems = []
+    for i, nr in enumerate(want_rows):
+        g, w = got[i, :nr], want[i, :nr]
+        if not np.array_equal(g[:, 4:], w[:, 4:]):
+            problems.append(f"{label}: ray {i}: caustic bounce/step indices differ: {g[:, 4:].tolist()} vs {w[:, 4:].tolist()}")
+            continue
+        rel = np.abs(g[:, :4] - w[:, :4]) / np.maximum(np.abs(w[:, :4]), 1.0)
+        if nr and rel.max() > rtol:
+            problems.append(f"{label}: ray {i}: caustic rows differ by {rel.max():.3e}")
+    return problems
