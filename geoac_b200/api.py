@@ -57,6 +57,7 @@ def lib():
         L.geoac_eq_count.argtypes = [C.c_int, C.c_int]
         L.geoac_last_trace_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.geoac_selftest_math.argtypes = [C.c_void_p, C.c_int, _dp]
+        L.geoac_get_grid_tables.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_int64, _dp]
         L.geoac_measure_fp64_peak.restype = C.c_double
         L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _LIB = L
@@ -67,6 +68,7 @@ EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
+    "geoac_get_grid_tables",
 ]
 
 
@@ -154,6 +156,12 @@ class Tracer:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, axz, T, u, v, rho)]
         self._check(lib().geoac_set_atmosphere_3d(self._h, len(arrs[0]), len(arrs[1]), len(arrs[2]), *[_p(a) for a in arrs]),
                     "geoac_set_atmosphere_3d")
+
+    def grid_tables(self, n0, n1, nz):
+        """Test hook: the device-built node tables (tuv [n0][n1][nz][18], rho [n0][n1][nz][2])."""
+        tuv = np.empty((n0, n1, nz, 18)); rho = np.empty((n0, n1, nz, 2))
+        self._check(lib().geoac_get_grid_tables(self._h, tuv.size, _p(tuv), rho.size, _p(rho)), "geoac_get_grid_tables")
+        return tuv, rho
 
     @property
     def params(self):

@@ -12,6 +12,8 @@
 #include <vector>
 #include <algorithm>
 #include <type_traits>
+#include <thread>
+#include <atomic>
 
 #include "core.cuh"
 #include "eq_cartesian.cuh"
@@ -190,6 +192,80 @@ extern "C" int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, c
     return GEOAC_OK;
 }
 
+// ---- device-side Set_Slopes_Multi (G2S_MultiDimSpline3D.cpp:306-425, G2S_GlobalMultiDimSpline3D.cpp:313-431) ----
+// One thread per (horizontal node, quantity): the ten Thomas solves of a column (f and its two node differences for T, u,
+// v; f for rho) are independent, and everything that depends on the vertical axis only (sub-diagonal, pivots, squared
+// spacings, the c' sweep) is precomputed once on the host.  Explicit round-to-nearest intrinsics keep every operation
+// separate (no FMA contraction), so the tables are bit-identical to host_tables.hpp::build_grid_tables, which follows the
+// reference's recurrences operation by operation (checked bitwise by tests/test_gpu_scale.py).
+struct ZAux { const double *A, *DEN, *NC, *P2LO, *P2HI; };      // each nz doubles
+
+__global__ void grid_tables_kernel(int glob, int n0, int n1, int nz, const double* ax0, const double* ax1, ZAux za,
+                                   const double* T, const double* u, const double* v, const double* rho, double* tuv, double* rh) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ncol = (long long)n0 * n1;
+    if (tid >= ncol * 10) return;
+    const long long col = tid / 10; const int q = (int)(tid % 10);
+    const int i = (int)(col / n1), j = (int)(col % n1);
+    const int F = (q < 9) ? q / 3 : 3, kind = (q < 9) ? q % 3 : 0;
+    const double* f = (F == 0) ? T : ((F == 1) ? u : ((F == 2) ? v : rho));
+    const int iu = min(i + 1, n0 - 1), id = max(i - 1, 0), ju = min(j + 1, n1 - 1), jd = max(j - 1, 0);
+    const double* fc = f + col * nz;
+    const double* fu = (kind == 1) ? f + ((long long)iu * n1 + j) * nz : f + ((long long)i * n1 + ju) * nz;
+    const double* fd = (kind == 1) ? f + ((long long)id * n1 + j) * nz : f + ((long long)i * n1 + jd) * nz;
+    const double span = (kind == 1) ? __dsub_rn(ax0[iu], ax0[id]) : __dsub_rn(ax1[ju], ax1[jd]);
+    auto val = [&](int k) { return (kind == 0) ? fc[k] : __ddiv_rn(__dsub_rn(fu[k], fd[k]), span); };
+    const bool shifted = glob && kind != 0;                       // the Global file's dfdt[i] - dfdt[i+1] slip (App. A-9)
+    double* o; int os, slope_at, value_at;
+    if (F < 3) { o = tuv + col * nz * MS_STRIDE + MS_FIELD * F; os = MS_STRIDE; slope_at = 1 + kind; value_at = (kind == 0) ? 0 : 3 + kind; }
+    else       { o = rh + col * nz * 2; os = 2; slope_at = 1; value_at = 0; }
+    // forward sweep: d' parked in the slope slot
+    double vm = val(0), vc = val(1), vp;
+    o[value_at] = vm;
+    double nd = __ddiv_rn(__ddiv_rn(__dmul_rn(3.0, __dsub_rn(vc, vm)), za.P2HI[0]), za.DEN[0]);       // di / bi
+    o[slope_at] = nd;
+    for (int k = 1; k < nz - 1; k++) {
+        vp = val(k + 1);
+        o[(size_t)k * os + value_at] = vc;
+        const double lo = shifted ? __dsub_rn(vc, vp) : __dsub_rn(vc, vm);
+        const double di = __dmul_rn(3.0, __dadd_rn(__ddiv_rn(lo, za.P2LO[k]), __ddiv_rn(__dsub_rn(vp, vc), za.P2HI[k])));
+        nd = __ddiv_rn(__dsub_rn(di, __dmul_rn(nd, za.A[k])), za.DEN[k]);
+        o[(size_t)k * os + slope_at] = nd;
+        vm = vc; vc = vp;
+    }
+    {
+        const int k = nz - 1;
+        o[(size_t)k * os + value_at] = vc;
+        const double di = __ddiv_rn(__dmul_rn(3.0, __dsub_rn(vc, vm)), za.P2LO[k]);
+        nd = __ddiv_rn(__dsub_rn(di, __dmul_rn(nd, za.A[k])), za.DEN[k]);
+        o[(size_t)k * os + slope_at] = nd;
+    }
+    // back substitution in place
+    double sn = nd;
+    for (int k = nz - 2; k >= 0; k--) {
+        sn = __dsub_rn(o[(size_t)k * os + slope_at], __dmul_rn(za.NC[k], sn));
+        o[(size_t)k * os + slope_at] = sn;
+    }
+}
+
+static void build_zaux(const std::vector<double>& z, std::vector<double>& aux) {     // [A | DEN | NC | P2LO | P2HI], nz each
+    const int n = (int)z.size();
+    aux.assign((size_t)5 * n, 0.0);
+    double *A = aux.data(), *DEN = A + n, *NC = DEN + n, *P2LO = NC + n, *P2HI = P2LO + n;
+    double ai, bi, ci;
+    bi = 2.0 / (z[1] - z[0]); ci = 1.0 / (z[1] - z[0]);
+    DEN[0] = bi; NC[0] = ci / bi; P2HI[0] = std::pow(z[1] - z[0], 2);
+    for (int i = 1; i < n - 1; i++) {
+        ai = 1.0 / (z[i] - z[i - 1]);
+        bi = 2.0 * (1.0 / (z[i] - z[i - 1]) + 1.0 / (z[i + 1] - z[i]));
+        ci = 1.0 / (z[i + 1] - z[i]);
+        A[i] = ai; DEN[i] = bi - NC[i - 1] * ai; NC[i] = ci / DEN[i];
+        P2LO[i] = std::pow(z[i] - z[i - 1], 2); P2HI[i] = std::pow(z[i + 1] - z[i], 2);
+    }
+    ai = 1.0 / (z[n - 1] - z[n - 2]); bi = 2.0 / (z[n - 1] - z[n - 2]);
+    A[n - 1] = ai; DEN[n - 1] = bi - NC[n - 2] * ai; P2LO[n - 1] = std::pow(z[n - 1] - z[n - 2], 2);
+}
+
 extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, const double* ax0, const double* ax1, const double* axz,
                                        const double* T, const double* u, const double* v, const double* rho) {
     if (!ctx) return GEOAC_ERR_BAD_ARG;
@@ -204,16 +280,43 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     if (nodes * MS_STRIDE >= (size_t)1 << 32) return fail(ctx, GEOAC_ERR_TOO_LARGE, "grid exceeds 2^32/18 nodes (32-bit element offsets in the kernel)");
     cudaSetDevice(ctx->device);
     const bool glob = ctx->variant == GEOAC_GLOBAL_RNGDEP;
-    std::vector<double> z, tuv, rh;
-    build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, T, u, v, rho, z, tuv, rh);
+    std::vector<double> z(nz);
+    for (int k = 0; k < nz; k++) z[k] = axz[k] + (glob ? kREarth : 0.0);                     // r_vals[nr] += r_earth
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax); ctx->d_tuv = ctx->d_rho = ctx->d_ax = nullptr;
-    CK(cudaMalloc(&ctx->d_tuv, tuv.size() * sizeof(double)));
-    CK(cudaMalloc(&ctx->d_rho, rh.size() * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_tuv, nodes * MS_STRIDE * sizeof(double)));
+    CK(cudaMalloc(&ctx->d_rho, nodes * 2 * sizeof(double)));
     std::vector<double> r0, r1, rz;
     build_axis_records(ax0, n0, r0); build_axis_records(ax1, n1, r1); build_axis_records(z.data(), nz, rz);
     CK(cudaMalloc(&ctx->d_ax, (size_t)(n0 + n1 + nz) * AX * sizeof(double)));
-    CK(cudaMemcpy(ctx->d_tuv, tuv.data(), tuv.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_rho, rh.data(), rh.size() * sizeof(double), cudaMemcpyHostToDevice));
+    const char* host_env = std::getenv("GEOAC_B200_HOST_TABLES");          // tests: build the tables on the host instead
+    if (host_env && std::atoi(host_env) != 0) {
+        std::vector<double> zz, tuv, rh;
+        build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, T, u, v, rho, zz, tuv, rh);
+        CK(cudaMemcpy(ctx->d_tuv, tuv.data(), tuv.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_rho, rh.data(), rh.size() * sizeof(double), cudaMemcpyHostToDevice));
+    } else {
+        // raw fields + axis-only coefficients up, slopes and node differences built in HBM
+        std::vector<double> aux; build_zaux(z, aux);
+        double *d_f = nullptr, *d_aux = nullptr;
+        CK(cudaMalloc(&d_f, nodes * 4 * sizeof(double)));
+        if (cudaMalloc(&d_aux, (aux.size() + n0 + n1) * sizeof(double)) != cudaSuccess) { cudaFree(d_f); return fail(ctx, GEOAC_ERR_CUDA, "table build: out of device memory"); }
+        const double* src[4] = { T, u, v, rho };
+        cudaError_t e = cudaSuccess;
+        for (int F = 0; F < 4 && e == cudaSuccess; F++) e = cudaMemcpy(d_f + (size_t)F * nodes, src[F], nodes * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_aux, aux.data(), aux.size() * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_aux + aux.size(), ax0, n0 * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_aux + aux.size() + n0, ax1, n1 * sizeof(double), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) {
+            ZAux za; za.A = d_aux; za.DEN = d_aux + nz; za.NC = d_aux + 2 * (size_t)nz; za.P2LO = d_aux + 3 * (size_t)nz; za.P2HI = d_aux + 4 * (size_t)nz;
+            const long long nthreads = (long long)n0 * n1 * 10;
+            grid_tables_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(glob ? 1 : 0, n0, n1, nz, d_aux + aux.size(), d_aux + aux.size() + n0, za,
+                                                                                           d_f, d_f + nodes, d_f + 2 * nodes, d_f + 3 * nodes, ctx->d_tuv, ctx->d_rho);
+            e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        }
+        cudaFree(d_f); cudaFree(d_aux);
+        if (e != cudaSuccess) { ctx->err = std::string("table build: ") + cudaGetErrorString(e); return GEOAC_ERR_CUDA; }
+    }
     CK(cudaMemcpy(ctx->d_ax, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_ax + (size_t)n0 * AX, r1.data(), r1.size() * sizeof(double), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_ax + (size_t)(n0 + n1) * AX, rz.data(), rz.size() * sizeof(double), cudaMemcpyHostToDevice));
@@ -228,6 +331,18 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
         ctx->prm.src[1] = (g.amin + g.amax) / 2.0; ctx->prm.src[2] = (g.bmin + g.bmax) / 2.0;
     }
     ctx->is_grid = true; ctx->have_atmo = true; ctx->consts_dirty = true;
+    return GEOAC_OK;
+}
+
+// Test hook: the node tables as the kernels read them (tuv[n0][n1][nz][18], rho[n0][n1][nz][2]; mspline.cuh).
+extern "C" int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t cap_rho, double* rho) {
+    if (!ctx) return GEOAC_ERR_BAD_ARG;
+    if (!ctx->is_grid || !ctx->d_tuv) return fail(ctx, GEOAC_ERR_NO_ATMO, "no range-dependent atmosphere set");
+    const size_t nodes = (size_t)ctx->grid.n0 * ctx->grid.n1 * ctx->grid.nz;
+    if (!tuv || !rho || (size_t)cap_tuv < nodes * MS_STRIDE || (size_t)cap_rho < nodes * 2) return fail(ctx, GEOAC_ERR_BAD_ARG, "get_grid_tables: buffers too small");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpy(tuv, ctx->d_tuv, nodes * MS_STRIDE * sizeof(double), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rho, ctx->d_rho, nodes * 2 * sizeof(double), cudaMemcpyDeviceToHost));
     return GEOAC_OK;
 }
 
@@ -579,6 +694,37 @@ extern "C" int geoac_load_met_1d(const char* path, const char* format, double z_
 }
 
 // ---- Load_G2S_Multi: Code/Atmo/G2S_MultiDimSpline3D.cpp:139-189 (Cartesian), G2S_GlobalMultiDimSpline3D.cpp:142-199 (Global) ----
+// The reference reads its 40 000 - 65 000 node files one after another with operator>>.  Node files are independent: the
+// first one fixes the level count, the rest are read whole and parsed with strtod (the conversion operator>> / fscanf use,
+// so every value has the same bits) by a pool of host threads, each writing its own columns of the dense arrays.
+static int parse_met_column(const std::string& path, int fmt, int global, int max_rows, double* axz, double* T, double* u, double* v, double* rho) {
+    FILE* f = std::fopen(path.c_str(), "rb"); if (!f) return -1;
+    std::string buf;
+    char chunk[1 << 16]; size_t got;
+    while ((got = std::fread(chunk, 1, sizeof chunk, f)) > 0) buf.append(chunk, got);
+    std::fclose(f);
+    const char* p = buf.c_str();
+    const int ncol = fmt == 0 ? 6 : 7;
+    int k = 0;
+    while (k < max_rows) {
+        double c[7]; int got_cols = 0;
+        for (; got_cols < ncol; got_cols++) { char* e; c[got_cols] = std::strtod(p, &e); if (e == p) break; p = e; }
+        if (got_cols < ncol) break;
+        const double zz = c[0];
+        double tt, uu, vv, rr;
+        if (fmt == 0) { tt = c[1]; uu = c[2]; vv = c[3]; rr = c[4]; } else { uu = c[1]; vv = c[2]; tt = c[4]; rr = c[5]; }
+        double arg;                                                             // ground taper: width 0.05 Cartesian, 0.2 Global; z_grnd = 0 at load
+        if (global) { const double r = zz + kREarth; arg = -(r - kREarth - 0.0) / 0.2; }
+        else        arg = -(zz - 0.0) / 0.05;
+        uu *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
+        vv *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
+        if (axz) axz[k] = zz;
+        T[k] = tt; u[k] = uu; v[k] = vv; rho[k] = rr;
+        k++;
+    }
+    return k;
+}
+
 extern "C" int geoac_load_met_grid(const char* prefix, const char* loc0, const char* loc1, const char* format, int global,
                                    int cap0, int cap1, int capz, int* n0, int* n1, int* nz,
                                    double* ax0, double* ax1, double* axz, double* T, double* u, double* v, double* rho) {
@@ -593,30 +739,33 @@ extern "C" int geoac_load_met_grid(const char* prefix, const char* loc0, const c
     const int c0 = read_axis(loc0, ax0, cap0), c1 = read_axis(loc1, ax1, cap1);
     if (c0 < 2 || c1 < 2) return GEOAC_ERR_IO;
     if (global) { for (int i = 0; i < c0; i++) ax0[i] *= kPi / 180.0; for (int i = 0; i < c1; i++) ax1[i] *= kPi / 180.0; }   // degrees -> radians
-    int cz = -1;
-    std::string path;
-    for (int i = 0; i < c0; i++) for (int j = 0; j < c1; j++) {
-        path = std::string(prefix) + std::to_string(i * c1 + j) + ".met";          // <prefix><i0*n1+i1>.met
-        FILE* f = std::fopen(path.c_str(), "r"); if (!f) return GEOAC_ERR_IO;
-        int k = 0; double zz, tt, uu, vv, rr, t1, t2;
+    auto node_path = [&](long long idx) { return std::string(prefix) + std::to_string(idx) + ".met"; };   // <prefix><i0*n1+i1>.met
+    const int cz = parse_met_column(node_path(0), fmt, global, capz, axz, T, u, v, rho);   // the first profile fixes the level count
+    if (cz < 3) return GEOAC_ERR_IO;
+    const long long ncol = (long long)c0 * c1;
+    unsigned nthr = std::thread::hardware_concurrency(); if (nthr == 0) nthr = 1;
+    if (const char* e = std::getenv("GEOAC_B200_LOAD_THREADS")) nthr = (unsigned)std::max(1, std::atoi(e));
+    nthr = (unsigned)std::min<long long>(std::min(nthr, 64u), std::max(1LL, ncol - 1));
+    std::atomic<long long> next{1};
+    std::atomic<int> bad{0};
+    auto work = [&]() {
+        std::vector<double> zcol((size_t)cz);
         for (;;) {
-            const bool ok = fmt == 0 ? std::fscanf(f, "%lf %lf %lf %lf %lf %lf", &zz, &tt, &uu, &vv, &rr, &t1) == 6
-                                     : std::fscanf(f, "%lf %lf %lf %lf %lf %lf %lf", &zz, &uu, &vv, &t1, &tt, &rr, &t2) == 7;
-            if (!ok || k >= capz || (cz >= 0 && k >= cz)) break;
-            double arg;                                                             // ground taper: width 0.05 Cartesian, 0.2 Global; z_grnd = 0 at load
-            if (global) { const double r = zz + kREarth; arg = -(r - kREarth - 0.0) / 0.2; }
-            else        arg = -(zz - 0.0) / 0.05;
-            uu *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
-            vv *= (2.0 / (1.0 + std::exp(arg)) - 1.0) / 1000.0;
-            const size_t id = ((size_t)i * c1 + j) * (size_t)(cz >= 0 ? cz : capz) + k;
-            axz[k] = zz; T[id] = tt; u[id] = uu; v[id] = vv; rho[id] = rr;
-            k++;
+            const long long c = next.fetch_add(1);
+            if (c >= ncol || bad.load()) return;
+            const size_t o = (size_t)c * cz;
+            const int k = parse_met_column(node_path(c), fmt, global, cz, zcol.data(), T + o, u + o, v + o, rho + o);
+            if (k != cz) { bad.store(1); return; }
+            if (c == ncol - 1) std::copy(zcol.begin(), zcol.end(), axz);   // the reference overwrites z with every file; the last one stays
         }
-        std::fclose(f);
-        if (cz < 0) cz = k; else if (k != cz) return GEOAC_ERR_IO;
-    }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nthr; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (bad.load()) return GEOAC_ERR_IO;
     *n0 = c0; *n1 = c1; *nz = cz;
-    return cz >= 3 ? GEOAC_OK : GEOAC_ERR_IO;
+    return GEOAC_OK;
 }
 
 // ---- accuracy self-test of the branch-free FP64 primitives (core.cuh) against libdevice, on the device ----

@@ -189,6 +189,13 @@ int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kern
  * and maximum absolute error of sin, cos (arguments within a few turns), in that order. */
 int geoac_selftest_math(geoac_ctx* ctx, int n_per_thread, double* max_rel_err);
 
+/* Test hook: copy the range-dependent node tables out of device memory exactly as the kernels read them --
+ * tuv[n0][n1][nz][18] (per field T,u,v: f, z-slope, z-slope of df/dax0, z-slope of df/dax1, df/dax0, df/dax1) and
+ * rho[n0][n1][nz][2] (f, z-slope).  These are what Set_Slopes_Multi builds (Code/Atmo/G2S_MultiDimSpline3D.cpp:306-425,
+ * G2S_GlobalMultiDimSpline3D.cpp:313-431); geoac_set_atmosphere_3d builds them ON THE DEVICE (one thread per column and
+ * quantity), and the parity tests compare them bit for bit with the reference's recurrences. cap_* in doubles. */
+int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t cap_rho, double* rho);
+
 /* FP64 DFMA micro-benchmark on ctx's device: returns measured TFLOP/s (2 flops per DFMA) -- the roofline denominator. */
 double geoac_measure_fp64_peak(geoac_ctx* ctx, double* out_ms);
 

@@ -467,6 +467,18 @@ orc_atmo* orc_atmo3d_create(int global, int n0, int n1, int nz, const double* ax
     return at;
 }
 
+/* Checker access to what Set_Slopes_Multi produced: which = 0 values, 1 vertical slopes, 2 slopes of d/d(ax0), 3 slopes of
+ * d/d(ax1) of field 0 T / 1 u / 2 v / 3 rho, dense [n0][n1][nz] into out.  Returns the node count (0 on bad arguments). */
+int64_t orc_atmo3d_slopes(const orc_atmo* at, int field, int which, double* out) {
+    if (!at || !at->grid || field < 0 || field > 3 || which < 0 || which > 3) return 0;
+    const ms_grid* g = (const ms_grid*)at->grid;
+    const size_t N = (size_t)g->n0 * g->n1 * g->nz;
+    const ms_field* F = &g->F[field];
+    const double* src = which == 0 ? F->f : (which == 1 ? F->s : (which == 2 ? F->sa : F->sb));
+    memcpy(out, src, N * sizeof(double));
+    return (int64_t)N;
+}
+
 /* Load_G2S_Multi: read `prefix<idx>.met` for every node (Cartesian idx = i0*n1 + i1, :154; Global idx = it*np + ip, :165)
  * plus the two node-coordinate files; winds m/s -> km/s with the ground taper (width 0.05 Cartesian, 0.2 Global; the
  * reference's z_grnd is 0 at load time).  Global lat/lon files are degrees -> radians.  Outputs as orc_atmo3d_create wants. */

@@ -32,6 +32,8 @@ def lib():
         L.orc_atmo3d_create.restype = C.c_void_p
         L.orc_atmo3d_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp]
         L.orc_atmo_destroy.argtypes = [C.c_void_p]
+        L.orc_atmo3d_slopes.restype = C.c_int64
+        L.orc_atmo3d_slopes.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
         L.orc_trace.restype = C.c_int64
         L.orc_trace.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams), C.c_int64, dp, dp, dp, ip, ip]
         L.orc_set_prop_region.argtypes = [C.c_int, C.c_void_p, C.POINTER(abi.GeoacParams)]
@@ -95,6 +97,15 @@ def atmo3d(is_global, ax0, ax1, axz, T, u, v, rho):
     if not h:
         raise RuntimeError("orc_atmo3d_create failed")
     return Atmo(h)
+
+
+def atmo3d_slopes(atmo, shape):
+    """Set_Slopes_Multi output of the oracle: array [field T,u,v,rho][values, z-slopes, d/dax0 slopes, d/dax1 slopes][n0][n1][nz]."""
+    out = np.empty((4, 4) + tuple(shape))
+    for f in range(4):
+        for w in range(4):
+            assert lib().orc_atmo3d_slopes(atmo.h, f, w, _p(out[f, w])) == out[f, w].size
+    return out
 
 
 def default_params(variant, atmo=None):

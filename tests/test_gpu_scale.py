@@ -130,3 +130,33 @@ def test_table_too_large_for_shared_memory_still_traces():
     m = a["status"] == abi.ST_ARRIVAL
     # the natural spline's end condition moves to the new top, which perturbs the slopes of the last original levels a little
     assert np.allclose(a["rec"][abi.F_TRAVELTIME][m], b["rec"][abi.F_TRAVELTIME][m], rtol=1e-6)
+
+
+@pytest.mark.parametrize("glob", [False, True])
+def test_device_built_node_tables_match_set_slopes_multi(glob, monkeypatch):
+    """geoac_set_atmosphere_3d builds the node tables on the device (one thread per column and quantity).  They must be
+    bit for bit what Set_Slopes_Multi yields (G2S_MultiDimSpline3D.cpp:306-425 / G2S_GlobalMultiDimSpline3D.cpp:313-431,
+    restated by the oracle, incl. the Global file's dfdt[i]-dfdt[i+1] slip) and what the host builder of the same library
+    yields (GEOAC_B200_HOST_TABLES=1), on a non-uniform vertical axis so that every spacing-dependent term differs."""
+    from oracle import pyoracle as po          # checker only
+    from geoac_b200 import synth
+    n0, n1, nz = 9, 11, 57
+    ax0, ax1, axz, T, u, v, rho = (synth.config5_grid(n0, n1, nz) if glob else synth.config4_grid(n0, n1, nz))
+    rng = np.random.default_rng(7)
+    axz = np.cumsum(0.3 + rng.random(nz))                    # irregular levels
+    T = T * (1.0 + 0.01 * rng.standard_normal(T.shape)); u = u + 1e-3 * rng.standard_normal(u.shape)
+    variant = abi.GEOAC_GLOBAL_RNGDEP if glob else abi.GEOAC_3D_RNGDEP
+    tr = g.Tracer(variant, 0)
+    tr.set_atmosphere_3d(ax0, ax1, axz, T, u, v, rho)
+    tuv, rh = tr.grid_tables(n0, n1, nz)
+    ref = po.atmo3d_slopes(po.atmo3d(glob, ax0, ax1, axz, T, u, v, rho), (n0, n1, nz))
+    for F in range(3):
+        for w in range(4):
+            assert np.array_equal(tuv[..., 6 * F + w].view(np.uint64), ref[F, w].view(np.uint64)), (F, w)
+    assert np.array_equal(rh[..., 0].view(np.uint64), ref[3, 0].view(np.uint64))
+    assert np.array_equal(rh[..., 1].view(np.uint64), ref[3, 1].view(np.uint64))
+    monkeypatch.setenv("GEOAC_B200_HOST_TABLES", "1")
+    th = g.Tracer(variant, 0)
+    th.set_atmosphere_3d(ax0, ax1, axz, T, u, v, rho)
+    tuv_h, rh_h = th.grid_tables(n0, n1, nz)
+    assert np.array_equal(tuv.view(np.uint64), tuv_h.view(np.uint64)) and np.array_equal(rh.view(np.uint64), rh_h.view(np.uint64))
