@@ -31,6 +31,17 @@ class GeoacParams(C.Structure):
         return q
 
 
+EIG_NF = 18            # doubles per eigenray-search row (geoac_eigenray_search)
+
+
+class GeoacEigOpts(C.Structure):
+    _fields_ = [
+        ("theta_min", C.c_double), ("theta_max", C.c_double), ("azimuth_err_lim", C.c_double),
+        ("d_theta_big", C.c_double), ("d_theta_small", C.c_double), ("tolerance", C.c_double),
+        ("bnc_min", C.c_int32), ("bnc_max", C.c_int32), ("iterations", C.c_int32), ("max_rounds", C.c_int32),
+    ]
+
+
 def eq_count(variant, calc_amp):
     """GeoAc_SetEqCnt (reference Code/GeoAc/GeoAc.Interface.cpp:21-41)."""
     if variant == GEOAC_2D:

@@ -58,6 +58,11 @@ def lib():
         L.geoac_last_trace_counters.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.geoac_selftest_math.argtypes = [C.c_void_p, C.c_int, _dp]
         L.geoac_get_grid_tables.argtypes = [C.c_void_p, C.c_int64, _dp, C.c_int64, _dp]
+        L.geoac_default_eig_opts.argtypes = [C.POINTER(abi.GeoacEigOpts)]
+        L.geoac_eigenray_search.argtypes = [C.c_void_p, C.POINTER(abi.GeoacEigOpts), C.c_int, _dp, C.c_int64, _dp,
+                                            C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.geoac_get_variant.argtypes = [C.c_void_p]
+        L.geoac_source_state.argtypes = [C.c_void_p, _dp]
         L.geoac_measure_fp64_peak.restype = C.c_double
         L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _LIB = L
@@ -68,7 +73,7 @@ EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
-    "geoac_get_grid_tables",
+    "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_get_variant", "geoac_source_state",
 ]
 
 
@@ -156,6 +161,30 @@ class Tracer:
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, axz, T, u, v, rho)]
         self._check(lib().geoac_set_atmosphere_3d(self._h, len(arrs[0]), len(arrs[1]), len(arrs[2]), *[_p(a) for a in arrs]),
                     "geoac_set_atmosphere_3d")
+
+    def eigenray_search(self, receivers, cap_rows=4096, **opts):
+        """GeoAc3D[.RngDep] -eig_search for one source (params.src) and many receivers [(x, y) km]: rows [n][EIG_NF] (one per
+        GeoAc_EstimateEigenray call of the reference, include/geoac_b200.h) and stats {rounds, rays, found}.
+        opts: theta_min, theta_max, bnc_min, bnc_max, iterations, azimuth_err_lim, d_theta_big, d_theta_small, tolerance."""
+        o = abi.GeoacEigOpts()
+        lib().geoac_default_eig_opts(C.byref(o))
+        for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown eigenray option {k}")
+            setattr(o, k, v)
+        rc = np.ascontiguousarray(receivers, dtype=np.float64).reshape(-1, 2)
+        rows = np.zeros((cap_rows, abi.EIG_NF))
+        n = C.c_int64(0)
+        stats = (C.c_int64 * 3)()
+        self._check(lib().geoac_eigenray_search(self._h, C.byref(o), len(rc), _p(rc), cap_rows, _p(rows), C.byref(n), stats),
+                    "geoac_eigenray_search")
+        return rows[:n.value].copy(), {"rounds": stats[0], "rays": stats[1], "found": stats[2]}
+
+    def source_state(self):
+        """c, u, v, rho at the source point as the kernels sample them."""
+        out = np.zeros(4)
+        self._check(lib().geoac_source_state(self._h, _p(out)), "geoac_source_state")
+        return out
 
     def grid_tables(self, n0, n1, nz):
         """Test hook: the device-built node tables (tuv [n0][n1][nz][18], rho [n0][n1][nz][2])."""

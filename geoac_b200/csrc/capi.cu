@@ -644,6 +644,20 @@ extern "C" int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* t
     return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, path_stride, path_cap, path, path_rows, caustic_cap, caustic, caustic_rows);
 }
 
+extern "C" int geoac_get_variant(const geoac_ctx* ctx) { return ctx ? ctx->variant : -1; }
+
+// Atmosphere at the source point, sampled on the device by the same spline code the kernels use (the per-launch invariants).
+extern "C" int geoac_source_state(geoac_ctx* ctx, double* out4) {
+    if (!ctx || !out4) return GEOAC_ERR_BAD_ARG;
+    cudaSetDevice(ctx->device);
+    int rc = refresh_consts(ctx); if (rc != GEOAC_OK) return rc;
+    LaunchConsts L;
+    CK(cudaMemcpyAsync(&L, ctx->d_consts, sizeof L, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out4[0] = L.c_src; out4[1] = L.u_src; out4[2] = L.v_src; out4[3] = L.rho_src;
+    return GEOAC_OK;
+}
+
 extern "C" int geoac_last_trace_stats(geoac_ctx* ctx, int64_t* total_steps, double* kernel_ms) {
     if (!ctx) return GEOAC_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);

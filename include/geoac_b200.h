@@ -175,6 +175,42 @@ int geoac_load_met_grid(const char* prefix, const char* loc0, const char* loc1, 
                         int cap0, int cap1, int capz, int* n0, int* n1, int* nz,
                         double* ax0, double* ax1, double* axz, double* T, double* u, double* v, double* rho);
 
+/* ---- eigenray search: GeoAc3D / GeoAc3D.RngDep -eig_search ----
+ * Replaces the loop of GeoAc3D_RunEigSearch (Code/GeoAc3D_main.cpp:531-541; GeoAc3D.RngDep_main.cpp likewise) including
+ * GeoAc_EstimateEigenray (Code/GeoAc/GeoAc.Eigenray.cpp:30-121) and GeoAc_3DEigenray_LM (:123-335), for one source (ctx
+ * params `src`) and n_rcvr receivers at once.  Same decisions as the reference's one-ray-at-a-time search; the rays of all
+ * receivers, bounce counts and brackets are traced in batches on the GPU (geoac_b200/csrc/eigenray.cu). */
+typedef struct geoac_eig_opts {
+    double theta_min, theta_max;   /* inclination limits [deg], 0.5 / 45 (GeoAc3D_main.cpp:461)                        */
+    double azimuth_err_lim;        /* [deg] 2.0                                                                         */
+    double d_theta_big;            /* 0.25  (Eigenray.cpp:20)                                                           */
+    double d_theta_small;          /* 0.002 (Eigenray.cpp:21)                                                           */
+    double tolerance;              /* [km] arrival-to-receiver distance that ends the LM search, 0.1 (Eigenray.cpp:139) */
+    int32_t bnc_min, bnc_max;      /* bounce counts searched, 0 / 0                                                     */
+    int32_t iterations;            /* LM iteration limit, 25                                                            */
+    int32_t max_rounds;            /* safety limit on trace batches, 4096                                               */
+} geoac_eig_opts;
+int geoac_default_eig_opts(geoac_eig_opts* o);
+
+/* One row per GeoAc_EstimateEigenray call, in the reference's order (receiver, bounce count, theta_start ascending):
+ *  0 receiver index   1 bounce count   2 estimate succeeded   3 theta_estimate [deg]   4 phi_estimate [deg from the x axis]
+ *  5 theta_next       6 eigenray found 7 theta [deg]          8 phi [deg from the x axis; azimuth = 90 - phi]
+ *  9 travel time [s] 10 celerity [km/s] 11 amplitude (linear; the reference prints 20 log10)   12 absorption [dB], positive
+ * 13 arrival inclination [deg]  14 back azimuth [deg]  15 azimuth deviation [deg]  16 LM iterations used  17 status of the
+ *    final trace.  7, 8, 16 are set whenever the estimate succeeded (angles where the LM search stopped); 9-15, 17 only for
+ *    eigenrays found.  A ray that ends on the step limit counts as having left the region (the reference would go on with
+ *    the state at the limit). */
+enum { GEOAC_EIG_NF = 18 };
+/* rcvr_xy: n_rcvr pairs (x, y) [km].  rows: cap_rows * GEOAC_EIG_NF doubles; *n_rows = rows produced (GEOAC_ERR_TOO_LARGE
+ * if more than cap_rows).  stats (may be NULL): [0] trace batches, [1] rays traced, [2] eigenrays found.  The raypath file
+ * of an eigenray (<title>_Eigenray-N.dat) is geoac_trace_paths at (theta, phi) with accum_per_segment = 1, stride 25. */
+int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy,
+                          int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats);
+
+/* Variant the context was created for; c, u, v, rho at the source point (device-sampled), 4 doubles. */
+int geoac_get_variant(const geoac_ctx* ctx);
+int geoac_source_state(geoac_ctx* ctx, double* out4);
+
 /* Number of state equations for (variant, calc_amp): GeoAc_SetEqCnt, Code/GeoAc/GeoAc.Interface.cpp:21-41. */
 int geoac_eq_count(int variant, int calc_amp);
 

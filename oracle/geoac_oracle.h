@@ -61,6 +61,7 @@ orc_atmo* orc_atmo1d_create(int global, int n, const double* z, const double* T,
 orc_atmo* orc_atmo3d_create(int global, int n0, int n1, int nz, const double* ax0, const double* ax1,
                             const double* axz, const double* T, const double* u, const double* v, const double* rho);
 void      orc_atmo_destroy(orc_atmo* a);
+void      orc_atmo_sample(orc_atmo* a, double p0, double p1, double p2, double* out4);   /* c, u, v, rho */
 int64_t   orc_atmo3d_slopes(const orc_atmo* at, int field, int which, double* out);   /* Set_Slopes_Multi output, see orc_mspline.c */
 
 double orc_suthbass_alpha(orc_atmo* a, double x0, double x1, double x2, double freq);

@@ -223,3 +223,8 @@ double orc_suthbass_alpha(orc_atmo* a, double q0, double q1, double q2, double f
     }
     return (a_cl + a_rot + a_diff + a_vib) * a->tweak_abs * 8.685889;
 }
+
+/* c, u, v, rho at a point (the wrappers the reference's callers use, e.g. M_Comps in GeoAc.Eigenray.cpp:131-135). */
+void orc_atmo_sample(orc_atmo* a, double p0, double p1, double p2, double* out4) {
+    out4[0] = a->c(a, p0, p1, p2); out4[1] = a->u(a, p0, p1, p2); out4[2] = a->v(a, p0, p1, p2); out4[3] = a->rho(a, p0, p1, p2);
+}

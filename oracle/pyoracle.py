@@ -32,6 +32,7 @@ def lib():
         L.orc_atmo3d_create.restype = C.c_void_p
         L.orc_atmo3d_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp, dp]
         L.orc_atmo_destroy.argtypes = [C.c_void_p]
+        L.orc_atmo_sample.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, dp]
         L.orc_atmo3d_slopes.restype = C.c_int64
         L.orc_atmo3d_slopes.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
         L.orc_trace.restype = C.c_int64
@@ -97,6 +98,13 @@ def atmo3d(is_global, ax0, ax1, axz, T, u, v, rho):
     if not h:
         raise RuntimeError("orc_atmo3d_create failed")
     return Atmo(h)
+
+
+def atmo_sample(atmo, p0, p1, p2):
+    """c, u, v, rho at a point."""
+    out = np.zeros(4)
+    lib().orc_atmo_sample(atmo.h, p0, p1, p2, _p(out))
+    return out
 
 
 def atmo3d_slopes(atmo, shape):

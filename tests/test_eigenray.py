@@ -1,0 +1,163 @@
+"""Eigenray search (Code/GeoAc/GeoAc.Eigenray.cpp, Code/GeoAc3D_main.cpp:531-541) against golden vectors dumped
+from the UNMODIFIED reference (tests/golden/eig/*.npz, tests/golden/make_golden_eig.py).
+CPU: the one-ray-at-a-time oracle restatement (oracle/pyeig.py) reproduces the reference's decisions and angles.
+GPU: geoac_eigenray_search (batched, geoac_b200/csrc/eigenray.cu) through the C ABI does too, for one and for many receivers."""
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+import geoac_b200 as g
+from geoac_b200 import abi
+from tests import util
+
+EIG = os.path.join(util.GOLD, "eig")
+ANGLE_ATOL = 1e-7          # degrees: LM iterates depend on the Jacobian states, which agree to ~1e-9 relative (tests/util.py)
+TEXT_RTOL = 3e-7           # the reference prints its eigenray attributes with 8 significant digits
+
+
+def eig_cases():
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(EIG, "*.npz")))
+
+
+def load(name):
+    d = np.load(os.path.join(EIG, name + ".npz"))
+    kv = dict(s.split("=", 1) for s in d["keys"].tolist())
+    return d, kv
+
+
+def parse_results(text):
+    """<title>_results.dat -> list of dicts (one per eigenray, in file order)."""
+    out = []
+    for blk in re.split(r"Eigenray-\d+\.", text)[1:]:
+        num = r"([-+0-9.eE]+|nan|inf|-inf)"
+        f = lambda pat: float(re.search(pat, blk).group(1))
+        m = re.search(r"theta, phi = " + num + ", " + num, blk)
+        out.append(dict(bounces=int(re.search(r"(\d+) bounce", blk).group(1)), theta=float(m.group(1)), az=float(m.group(2)),
+                        tt=f(r"Travel Time = " + num), cel=f(r"Celerity = " + num), amp_db=f(r"Amplitude \(geometric\) = " + num),
+                        att_db=f(r"Atmospheric attenuation = " + num), incl=f(r"Arrival inclination = " + num),
+                        back_az=f(r"Back azimuth of arrival = " + num), dev=f(r"Azimuth deviation = " + num)))
+    return out
+
+
+def opts_from(kv):
+    o = {}
+    for k in ("theta_min", "theta_max", "azimuth_err_lim"):
+        if k in kv:
+            o[k] = float(kv[k])
+    for k in ("bnc_min", "bnc_max", "iterations"):
+        if k in kv:
+            o[k] = int(kv[k])
+    return o
+
+
+def receiver(kv):
+    return float(kv.get("x_rcvr", -250.0)), float(kv.get("y_rcvr", 0.0))
+
+
+def set_source(p, kv):
+    p.src[0], p.src[1], p.src[2] = float(kv.get("x_src", 0.0)), float(kv.get("y_src", 0.0)), float(kv.get("z_src", 0.0))
+    return p
+
+
+def check_rows(rows, gold, label):
+    """rows [n][EIG_NF] (product or oracle) vs the reference's [n][8]."""
+    assert len(rows) == len(gold), (label, len(rows), len(gold))
+    assert np.array_equal(rows[:, [1, 2, 6]], gold[:, [0, 1, 5]]), label            # bounce count, estimate ok, eigenray found
+    assert np.array_equal(rows[:, 3], gold[:, 2]) and np.array_equal(rows[:, 5], gold[:, 4]), label     # theta_est / theta_next lie on the fan
+    ok = gold[:, 1] == 1
+    assert np.allclose(rows[ok, 4], gold[ok, 3], rtol=0, atol=ANGLE_ATOL), label                       # phi_est
+    assert np.allclose(rows[ok][:, [7, 8]], gold[ok][:, [6, 7]], rtol=0, atol=ANGLE_ATOL), (label, rows[ok][:, [7, 8]] - gold[ok][:, [6, 7]])
+
+
+def check_attributes(rows, text, label):
+    ref = parse_results(text)
+    got = rows[rows[:, 6] == 1]
+    assert len(got) == len(ref), label
+    for r, t in zip(got, ref):
+        assert int(r[1]) == t["bounces"]
+        near = lambda a, b, atol=0.0: abs(a - b) <= TEXT_RTOL * abs(b) + atol
+        assert near(r[7], t["theta"]) and near(90.0 - r[8], t["az"], 1e-6), (label, r[7], t)
+        assert near(r[9], t["tt"]) and near(r[10], t["cel"]), (label, r[9], r[10], t)
+        assert near(20.0 * np.log10(r[11]), t["amp_db"], 2e-5), (label, 20.0 * np.log10(r[11]), t)      # amplitude: 1e-6 relative through caustics
+        assert near(-r[12], t["att_db"]) and near(r[13], t["incl"], 1e-6), (label, r[12], r[13], t)
+        assert near(r[14], t["back_az"], 1e-6) and abs(r[15] - t["dev"]) < 1e-6, (label, r[14], r[15], t)
+
+
+@pytest.mark.parametrize("name", ["eig3d_axis", "eig3d_far"])
+def test_oracle_eigenray_search_matches_reference(name, oracle):
+    from oracle import pyoracle as po, pyeig
+    d, kv = load(name)
+    at = po.atmo1d(False, *po.load_met_1d(util.TOY))
+    p = set_source(po.default_params(abi.GEOAC_3D, at), kv)
+    rows, _ = pyeig.run_eig_search(abi.GEOAC_3D, at, p, receiver(kv), **opts_from(kv))
+    check_rows(rows, d["rows"], name)
+    ok = d["rows"][:, 1] == 1
+    assert np.array_equal(rows[ok][:, [4, 7, 8]], d["rows"][ok][:, [3, 6, 7]]), "oracle is bit-exact on the search angles"
+    check_attributes(rows, str(d["text"]), name)
+
+
+def _tracer(d, kv):
+    variant = int(d["variant"])
+    tr = g.Tracer(variant, 0)
+    if variant == abi.GEOAC_3D:
+        tr.set_atmosphere_1d(*g.load_met_1d(util.TOY))
+    else:
+        tr.set_atmosphere_3d(*util.load_grid(d))
+    tr.params = set_source(tr.params, kv)
+    return tr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", eig_cases())
+def test_cuda_eigenray_search_matches_reference(name):
+    d, kv = load(name)
+    tr = _tracer(d, kv)
+    before = bytes(tr.params)
+    rows, stats = tr.eigenray_search([receiver(kv)], **opts_from(kv))
+    assert bytes(tr.params) == before, "the search must leave the context's parameters as it found them"
+    check_rows(rows, d["rows"], name)
+    check_attributes(rows, str(d["text"]), name)
+    assert stats["found"] == int(d["rows"][:, 5].sum()) and stats["rounds"] < 80
+    print(f"\n[{name}] reference {float(d['ref_seconds']):.1f} s one ray at a time; here {stats['rays']} rays in {stats['rounds']} batches")
+
+
+@pytest.mark.gpu
+def test_cuda_eigenray_search_many_receivers_equals_one_by_one():
+    """Receivers are searched concurrently (their fans and LM rays share the batches); every receiver's rows must be
+    bit for bit what a search for that receiver alone returns."""
+    names = ["eig3d_axis", "eig3d_cross", "eig3d_far"]
+    rcv = [(-250.0, 0.0), (-280.0, 130.0), (-520.0, 60.0), (-400.0, -90.0), (150.0, 200.0)]
+    tr = g.Tracer(abi.GEOAC_3D, 0)
+    tr.set_atmosphere_1d(*g.load_met_1d(util.TOY))
+    rows, stats = tr.eigenray_search(rcv, bnc_min=0, bnc_max=2)
+    one_rounds = 0
+    for i, r in enumerate(rcv):
+        single, st = tr.eigenray_search([r], bnc_min=0, bnc_max=2)
+        one_rounds += st["rounds"]
+        mine = rows[rows[:, 0] == i].copy()
+        mine[:, 0] = 0
+        assert np.array_equal(mine.view(np.uint64), single.view(np.uint64)), i
+    assert stats["rounds"] < one_rounds                    # batching across receivers shares the rounds
+    for name in names[:1]:                                 # and the default case is among them, with the reference's answer
+        d, kv = load(name)
+        sel = rows[(rows[:, 0] == 0) & (rows[:, 1] <= 1)]
+        check_rows(sel, d["rows"], name)
+
+
+@pytest.mark.gpu
+def test_eigenray_search_error_paths():
+    tr = g.Tracer(abi.GEOAC_2D, 0)
+    tr.set_atmosphere_1d(*g.load_met_1d(util.TOY))
+    with pytest.raises(g.GeoAcError):
+        tr.eigenray_search([(-250.0, 0.0)])                 # only the Cartesian 3-D variants have an eigenray search
+    tr3 = g.Tracer(abi.GEOAC_3D, 0)
+    with pytest.raises(g.GeoAcError):
+        tr3.eigenray_search([(-250.0, 0.0)])                # no atmosphere yet
+    tr3.set_atmosphere_1d(*g.load_met_1d(util.TOY))
+    with pytest.raises(g.GeoAcError):
+        tr3.eigenray_search([(-250.0, 0.0)], bnc_min=2, bnc_max=1)
+    rows, _ = tr3.eigenray_search(np.zeros((0, 2)))
+    assert len(rows) == 0
