@@ -38,6 +38,7 @@ class GeoacEigOpts(C.Structure):
     _fields_ = [
         ("theta_min", C.c_double), ("theta_max", C.c_double), ("azimuth_err_lim", C.c_double),
         ("d_theta_big", C.c_double), ("d_theta_small", C.c_double), ("tolerance", C.c_double),
+        ("src_lat_deg", C.c_double), ("src_lon_deg", C.c_double),
         ("bnc_min", C.c_int32), ("bnc_max", C.c_int32), ("iterations", C.c_int32), ("max_rounds", C.c_int32),
     ]
 

@@ -1,7 +1,8 @@
 // eigenray.cu -- batched eigenray search above the C ABI (host code only; every ray goes through geoac_trace on the GPU).
 //
-// Replaces, for the Cartesian variants (GeoAc3D, GeoAc3D.RngDep), the body of GeoAc3D_RunEigSearch
-// (Code/GeoAc3D_main.cpp:531-541, Code/GeoAc3D.RngDep_main.cpp likewise):
+// Replaces the body of GeoAc3D_RunEigSearch (Code/GeoAc3D_main.cpp:531-541, Code/GeoAc3D.RngDep_main.cpp likewise) and of
+// GeoAcGlobal_RunEigSearch (Code/GeoAcGlobal_main.cpp:573-583, GeoAcGlobal.RngDep_main.cpp likewise; the Global routines
+// are Code/GeoAc/GeoAc.Eigenray.Global.cpp:46-136 and :139-320 -- same algorithm on great-circle range and bearing):
 //     for every bounce count:  theta_start = theta_min;
 //         while theta_start < theta_max:  GeoAc_EstimateEigenray (Code/GeoAc/GeoAc.Eigenray.cpp:30-121)
 //                                         on success GeoAc_3DEigenray_LM (:123-335);  theta_start = theta_next
@@ -48,16 +49,18 @@ struct Request { double theta, phi; int amp, nb; };
 struct Search {
     geoac_ctx* ctx;
     int variant;
-    bool strat;
+    bool strat, glob = false;
     geoac_eig_opts o;
-    double src[3];
+    double src[3];                            // Source_Loc: (x, y, z) [km], or (lat, lon) [deg] and z for the Global variants
+    double z_grnd = 0.0;
     double Mx = 0, My = 0;                    // u/c, v/c at the source (stratified LM, Eigenray.cpp:131-135; w = 0)
     std::map<RayKey, RayVal> cache;
     std::map<RayKey, Request> want;           // this round's misses
     int64_t rays_traced = 0; int rounds = 0;
 
-    // state of ray (theta, phi) [degrees, phi from the x axis] after n_bnc reflections, or nullptr + a recorded request.
-    // *brk receives the reference's BreakCheck (any segment left the region; a step-limit end counts as one, see INTEGRATION).
+    // state of the ray launched at (GeoAc_theta, GeoAc_phi) [radians, exactly the values the reference assigns] after n_bnc
+    // reflections, or nullptr + a recorded request.  *brk receives the reference's BreakCheck (any segment left the region;
+    // a step-limit end counts as one, see include/geoac_b200.h).
     const double* lookup(double theta, double phi, int amp, int n_bnc, bool* brk, bool record = true) {
         RayKey k{ bits(theta), bits(phi), amp };
         auto it = cache.find(k);
@@ -78,47 +81,65 @@ struct Search {
 
     // ---- GeoAc_EstimateEigenray, Eigenray.cpp:30-121 ----
     struct Est { bool complete = false, ok = false, next_known = false; double theta_est = 0, phi_est = 0, theta_next = 0; };
-    static double modify_d_theta(double dr, double dr_dtheta, double big, double small_) {       // :23-27
-        const double width = 2.0 * std::pow(dr_dtheta, 2);
+    static double modify_d_theta(double dr, double dr_dtheta, double big, double small_, double wf) {   // :23-27; Global :39-43 (width factor 1/2)
+        const double width = wf * std::pow(dr_dtheta, 2);
         return big - (big - small_) * std::exp(-dr * dr / width);
+    }
+    static double bearing(double lat1, double long1, double lat2, double long2) {                 // Calc_Bearing, Eigenray.Global.cpp:25-30
+        const double term1 = std::sin((long2 - long1) * Pi / 180.0);
+        const double term2 = std::cos(lat1 * Pi / 180.0) * std::tan(lat2 * Pi / 180.0) - std::sin(lat1 * Pi / 180.0) * std::cos((long2 - long1) * Pi / 180.0);
+        return std::atan2(term1, term2) * 180.0 / Pi;
+    }
+    static double gc_distance(double lat1, double long1, double lat2, double long2) {             // Calc_GC_Distance, :32-37
+        const double term1 = std::pow(std::sin((lat2 - lat1) * Pi / 180.0 / 2.0), 2);
+        const double term2 = std::cos(lat1 * Pi / 180.0) * std::cos(lat2 * Pi / 180.0) * std::pow(std::sin((long2 - long1) * Pi / 180.0 / 2.0), 2);
+        return 2.0 * 6370.0 * std::asin(std::sqrt(term1 + term2));
     }
     Est estimate(const double rcv[2], double theta_min, double theta_max, int bounces) {
         Est e;
-        const double r_rcvr = std::sqrt(std::pow(rcv[0] - src[0], 2) + std::pow(rcv[1] - src[1], 2));
-        double phi = 180.0 / 3.14159 * std::atan2(rcv[1] - src[1], rcv[0] - src[0]);
+        const double r_rcvr = glob ? gc_distance(src[0], src[1], rcv[0], rcv[1])
+                                   : std::sqrt(std::pow(rcv[0] - src[0], 2) + std::pow(rcv[1] - src[1], 2));
+        double phi = glob ? bearing(src[0], src[1], rcv[0], rcv[1])                       // Global: an azimuth; Cartesian: from the x axis
+                          : 180.0 / 3.14159 * std::atan2(rcv[1] - src[1], rcv[0] - src[0]);
         int iterations = 0;
         e.theta_est = theta_max;
         double r, r_prev, d_theta = o.d_theta_big, d_phi = 10.0;
         bool theta_max_reached = false;
         while (std::fabs(d_phi) > o.azimuth_err_lim && iterations < 5) {
             r = r_rcvr; r_prev = r_rcvr;
-            for (double theta = theta_min; theta <= theta_max; theta += d_theta) {
+            const double phi_rad = glob ? (90.0 - phi) * Pi / 180.0 : phi * Pi / 180.0;      // GeoAc_phi
+            // Cartesian: theta <= theta_max (Eigenray.cpp:58); Global: theta < theta_max (Eigenray.Global.cpp:74)
+            for (double theta = theta_min; glob ? theta < theta_max : theta <= theta_max; theta += d_theta) {
                 if (theta + d_theta >= theta_max) theta_max_reached = true;
                 bool brk;
-                const double* s = lookup(theta, phi, 0, bounces, &brk);
+                const double* s = lookup(theta * Pi / 180.0, phi_rad, 0, bounces, &brk);
                 if (!s) {
                     if (iterations < 3) {          // fixed step: the rest of this fan is known now
                         int guard = 0;
-                        for (double t = theta + d_theta; t <= theta_max && guard < 100000; t += d_theta, guard++) { bool b2; lookup(t, phi, 0, bounces, &b2); }
+                        for (double t = theta + d_theta; (glob ? t < theta_max : t <= theta_max) && guard < 100000; t += d_theta, guard++) { bool b2; lookup(t * Pi / 180.0, phi_rad, 0, bounces, &b2); }
                     }
                     return e;                      // incomplete
                 }
                 if (brk) { r = r_rcvr; r_prev = r_rcvr; }
+                else if (glob) r = gc_distance(src[0], src[1], s[1] * 180.0 / Pi, s[2] * 180.0 / Pi);
                 else r = std::sqrt(std::pow(s[0] - src[0], 2) + std::pow(s[1] - src[1], 2));
                 if ((r - r_rcvr) * (r_prev - r_rcvr) < 0.0) {
                     if (iterations == 0) { e.theta_next = theta; e.next_known = true; }
-                    d_phi = (std::atan2(rcv[1] - src[1], rcv[0] - src[0]) - std::atan2(s[1] - src[1], s[0] - src[0])) * 180.0 / Pi;
+                    if (glob) {
+                        d_phi = bearing(src[0], src[1], rcv[0], rcv[1]);
+                        d_phi -= bearing(src[0], src[1], s[1] * 180.0 / Pi, s[2] * 180.0 / Pi);
+                    } else d_phi = (std::atan2(rcv[1] - src[1], rcv[0] - src[0]) - std::atan2(s[1] - src[1], s[0] - src[0])) * 180.0 / Pi;
                     while (d_phi > 180.0) d_phi -= 360.0;
                     while (d_phi < -180.0) d_phi += 360.0;
                     if (std::fabs(d_phi) < o.azimuth_err_lim) {
-                        e.theta_est = theta - d_theta; e.phi_est = phi; e.ok = true; e.complete = true;
+                        e.theta_est = theta - d_theta; e.phi_est = glob ? 90.0 - phi : phi; e.ok = true; e.complete = true;
                         return e;
                     }
                     phi += d_phi * 0.9;
                     theta_min = std::max(theta - 7.5, theta_min);
                     break;
                 }
-                if (iterations >= 3) d_theta = modify_d_theta(r - r_rcvr, (r - r_prev) / (2.0 * d_theta), o.d_theta_big, o.d_theta_small);
+                if (iterations >= 3) d_theta = modify_d_theta(r - r_rcvr, (r - r_prev) / (2.0 * d_theta), o.d_theta_big, o.d_theta_small, glob ? 0.5 : 2.0);
                 r_prev = r;
             }
             if (theta_max_reached) { e.theta_next = theta_max; e.next_known = true; break; }
@@ -142,18 +163,23 @@ struct Search {
             out.iters = n;
             if (n == o.iterations) break;
             const double th = theta * Pi / 180.0, ph = phi * Pi / 180.0;
-            if (strat) {
+            if (strat && !glob) {
                 const double nu0[3] = { std::cos(th) * std::cos(ph), std::cos(th) * std::sin(ph), std::sin(th) };
                 const double M = 1.0 + (nu0[0] * Mx + nu0[1] * My + nu0[2] * 0.0);
                 nu0_xy[0] = nu0[0] / M; nu0_xy[1] = nu0[1] / M;
             }
             bool brk;
-            const double* s = lookup(theta, phi, 1, bnc_cnt, &brk);
+            const double* s = lookup(th, ph, 1, bnc_cnt, &brk);
             if (!s) { out.theta = theta; out.phi = phi; return out; }          // incomplete
             if (brk) break;
-            x = s[0]; dx = rcv[0] - x;
-            y = s[1]; dy = rcv[1] - y;
-            dr = (double)std::sqrt(dx * dx + dy * dy);
+            if (glob) {                                                        // Eigenray.Global.cpp:183-184 (x = lat, y = lon)
+                x = s[1]; y = s[2];
+                dr = gc_distance((double)(x * 180.0 / Pi), (double)(y * 180.0 / Pi), rcv[0], rcv[1]);
+            } else {
+                x = s[0]; dx = rcv[0] - x;
+                y = s[1]; dy = rcv[1] - y;
+                dr = (double)std::sqrt(dx * dx + dy * dy);
+            }
             if (dr < tolerance) { out.found = true; break; }
             else if (n > 0 && dr > dr_prev) {
                 theta -= dt * step_scalar;
@@ -162,7 +188,18 @@ struct Search {
                 if (std::sqrt(dt * dt + dp * dp) * step_scalar < 1.0e-12) break;
             } else {
                 step_scalar = std::min(1.0, step_scalar * 1.25);
-                if (strat) {
+                if (glob) {                                                    // Eigenray.Global.cpp:283-294; dx, dy = d_lat, d_lon
+                    const double rg = 6370.0 + z_grnd;
+                    dx = rcv[0] * Pi / 180.0 - x;
+                    dy = rcv[1] * Pi / 180.0 - y;
+                    dx_dt = s[7] - 1.0 / rg * s[4] / s[3] * s[6];
+                    dx_dp = s[13] - 1.0 / rg * s[4] / s[3] * s[12];
+                    dy_dt = s[8] - 1.0 / (rg * std::cos(x)) * s[5] / s[3] * s[6];
+                    dy_dp = s[14] - 1.0 / (rg * std::cos(x)) * s[5] / s[3] * s[12];
+                    det = dx_dt * dy_dp - dx_dp * dy_dt;
+                    dt = (dy_dp * dx - dx_dp * dy) / det * 180.0 / Pi;
+                    dp = (-dy_dt * dx + dx_dt * dy) / det * 180.0 / Pi;
+                } else if (strat) {
                     dx_dt = s[4] - nu0_xy[0] / s[3] * s[6];
                     dy_dt = s[5] - nu0_xy[1] / s[3] * s[6];
                     dx_dp = s[8] - nu0_xy[0] / s[3] * s[10];
@@ -173,9 +210,11 @@ struct Search {
                     dx_dp = s[12] - s[3] / s[5] * s[14];
                     dy_dp = s[13] - s[4] / s[5] * s[14];
                 }
-                det = dx_dt * dy_dp - dx_dp * dy_dt;
-                dt = 1.0 / det * (dy_dp * dx - dx_dp * dy) * 180.0 / Pi;
-                dp = 1.0 / det * (dx_dt * dy - dy_dt * dx) * 180.0 / Pi;
+                if (!glob) {
+                    det = dx_dt * dy_dp - dx_dp * dy_dt;
+                    dt = 1.0 / det * (dy_dp * dx - dx_dp * dy) * 180.0 / Pi;
+                    dp = 1.0 / det * (dx_dt * dy - dy_dt * dx) * 180.0 / Pi;
+                }
                 if (dt > theta_lim_step) dt = theta_lim_step;
                 if (dp > phi_lim_step) dp = phi_lim_step;
                 if (dt < -theta_lim_step) dt = -theta_lim_step;
@@ -220,7 +259,7 @@ struct Search {
         for (int amp = 0; amp < 2; amp++) {
             std::vector<double> th, ph; std::vector<RayKey> keys; int nb = 0;
             for (auto& kv : want) if (kv.first.amp == amp) {
-                th.push_back(kv.second.theta * Pi / 180.0); ph.push_back(kv.second.phi * Pi / 180.0);
+                th.push_back(kv.second.theta); ph.push_back(kv.second.phi);
                 keys.push_back(kv.first); nb = std::max(nb, kv.second.nb);
             }
             if (th.empty()) continue;
@@ -252,7 +291,7 @@ extern "C" int geoac_default_eig_opts(geoac_eig_opts* o) {
     std::memset(o, 0, sizeof *o);
     o->theta_min = 0.5; o->theta_max = 45.0; o->bnc_min = 0; o->bnc_max = 0; o->iterations = 25;      // GeoAc3D_main.cpp:461-464
     o->azimuth_err_lim = 2.0; o->d_theta_big = 0.25; o->d_theta_small = 0.002; o->tolerance = 0.1;   // Eigenray.cpp:20-21,139
-    o->max_rounds = 4096;
+    o->max_rounds = 4096; o->src_lat_deg = 30.0; o->src_lon_deg = 0.0;                              // GeoAcGlobal_main.cpp:497
     return GEOAC_OK;
 }
 
@@ -260,11 +299,18 @@ extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts,
                                      int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats) {
     if (!ctx || !opts || !rcvr_xy || !n_rows || n_rcvr < 0 || (cap_rows > 0 && !rows)) return GEOAC_ERR_BAD_ARG;
     const int variant = geoac_get_variant(ctx);
-    if (variant != GEOAC_3D && variant != GEOAC_3D_RNGDEP) return GEOAC_ERR_BAD_ARG;      // the Global search (Eigenray.Global.cpp) is not covered yet
+    if (variant == GEOAC_2D) return GEOAC_ERR_BAD_ARG;                                    // GeoAc2D has no eigenray search
     if (opts->bnc_min < 0 || opts->bnc_max < opts->bnc_min || opts->iterations < 0 || !(opts->d_theta_big > 0.0)) return GEOAC_ERR_BAD_ARG;
     geoac_params user; int rc = geoac_get_params(ctx, &user); if (rc) return rc;
     Search S; S.ctx = ctx; S.variant = variant; S.strat = variant == GEOAC_3D; S.o = *opts;
-    S.src[0] = user.src[0]; S.src[1] = user.src[1]; S.src[2] = std::max(user.z_grnd, user.src[2]);
+    S.glob = variant == GEOAC_GLOBAL || variant == GEOAC_GLOBAL_RNGDEP; S.z_grnd = user.z_grnd;
+    if (S.glob) {
+        // Source_Loc = (lat, lon) in degrees as the Global mains hold it (GeoAcGlobal_main.cpp:497); the rays start from
+        // lat*Pi/180, lon*Pi/180 (Eigenray.Global.cpp:78), which is written into the context for the duration of the search
+        S.src[0] = opts->src_lat_deg; S.src[1] = opts->src_lon_deg; S.src[2] = std::max(user.z_grnd, user.src[0]);
+        geoac_params p = user; p.src[0] = S.src[2]; p.src[1] = S.src[0] * Pi / 180.0; p.src[2] = S.src[1] * Pi / 180.0;
+        rc = geoac_set_params(ctx, &p); if (rc) return rc;
+    } else { S.src[0] = user.src[0]; S.src[1] = user.src[1]; S.src[2] = std::max(user.z_grnd, user.src[2]); }
     if (S.strat) {
         double a[4]; rc = geoac_source_state(ctx, a); if (rc) return rc;
         S.Mx = a[1] / a[0]; S.My = a[2] / a[0];
@@ -287,7 +333,8 @@ extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts,
     if (!found.empty()) {
         std::vector<double> th, ph;
         for (int i : found) { th.push_back(calls[i].l.theta * Pi / 180.0); ph.push_back(calls[i].l.phi * Pi / 180.0); nbmax = std::max(nbmax, calls[i].n_bnc); }
-        geoac_params p = user; p.bounces = nbmax; p.calc_amp = 1; p.accum_per_segment = 1;
+        geoac_params p; rc = geoac_get_params(ctx, &p); if (rc) { geoac_set_params(ctx, &user); return rc; }      // keeps the search's source
+        p.bounces = nbmax; p.calc_amp = 1; p.accum_per_segment = 1;
         rc = geoac_set_params(ctx, &p);
         slots = (int64_t)found.size() * (nbmax + 1);
         rec.resize((size_t)GEOAC_NFIELDS * slots); st.resize((size_t)slots); std::vector<int32_t> ns((size_t)slots);
@@ -313,15 +360,25 @@ extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts,
                 const double rx = rcvr_xy[2 * c.rcvr], ry = rcvr_xy[2 * c.rcvr + 1];
                 const double tt = F(GEOAC_F_TRAVELTIME);
                 r[9] = tt;
-                r[10] = std::sqrt(std::pow(F(0) - S.src[0], 2) + std::pow(F(1) - S.src[1], 2)) / tt;           // celerity, :260
                 r[11] = F(GEOAC_F_AMPLITUDE); r[12] = F(GEOAC_F_ATTEN); r[13] = F(GEOAC_F_INCLINATION);
-                double back_az = S.strat ? (90.0 - (c.l.phi * Pi / 180.0) * 180.0 / Pi) + 180.0                    // :239-244
-                                         : 90.0 - std::atan2(-F(4), -F(3)) * 180.0 / Pi;
-                double dev = back_az - (90.0 - std::atan2(S.src[1] - ry, S.src[0] - rx) * 180.0 / Pi);
-                while (back_az > 180.0) back_az -= 360.0;
-                while (back_az < -180.0) back_az += 360.0;
-                while (dev > 180.0) dev -= 360.0;
-                while (dev < -180.0) dev += 360.0;
+                double back_az, dev;
+                if (S.glob) {                                                                                      // Eigenray.Global.cpp:238-241,266-273
+                    r[10] = Search::gc_distance(S.src[0], S.src[1], rx, ry) / tt;
+                    if (variant == GEOAC_GLOBAL_RNGDEP) r[13] = -r[13];          // the record follows that main's +asin (App. A-16); the search prints -asin
+                    back_az = 90.0 - std::atan2(-F(4), -F(5)) * 180.0 / Pi;
+                    dev = back_az - Search::bearing(rx, ry, S.src[0], S.src[1]);
+                    if (dev > 180.0) dev -= 360.0;
+                    if (dev < -180.0) dev += 360.0;
+                } else {
+                    r[10] = std::sqrt(std::pow(F(0) - S.src[0], 2) + std::pow(F(1) - S.src[1], 2)) / tt;           // celerity, Eigenray.cpp:260
+                    back_az = S.strat ? (90.0 - (c.l.phi * Pi / 180.0) * 180.0 / Pi) + 180.0                        // :239-244
+                                      : 90.0 - std::atan2(-F(4), -F(3)) * 180.0 / Pi;
+                    dev = back_az - (90.0 - std::atan2(S.src[1] - ry, S.src[0] - rx) * 180.0 / Pi);
+                    while (back_az > 180.0) back_az -= 360.0;
+                    while (back_az < -180.0) back_az += 360.0;
+                    while (dev > 180.0) dev -= 360.0;
+                    while (dev < -180.0) dev += 360.0;
+                }
                 r[14] = back_az; r[15] = dev;
                 r[17] = st[(size_t)slot];
             }

@@ -175,10 +175,11 @@ int geoac_load_met_grid(const char* prefix, const char* loc0, const char* loc1, 
                         int cap0, int cap1, int capz, int* n0, int* n1, int* nz,
                         double* ax0, double* ax1, double* axz, double* T, double* u, double* v, double* rho);
 
-/* ---- eigenray search: GeoAc3D / GeoAc3D.RngDep -eig_search ----
+/* ---- eigenray search: -eig_search of GeoAc3D, GeoAc3D.RngDep, GeoAcGlobal, GeoAcGlobal.RngDep ----
  * Replaces the loop of GeoAc3D_RunEigSearch (Code/GeoAc3D_main.cpp:531-541; GeoAc3D.RngDep_main.cpp likewise) including
- * GeoAc_EstimateEigenray (Code/GeoAc/GeoAc.Eigenray.cpp:30-121) and GeoAc_3DEigenray_LM (:123-335), for one source (ctx
- * params `src`) and n_rcvr receivers at once.  Same decisions as the reference's one-ray-at-a-time search; the rays of all
+ * GeoAc_EstimateEigenray (Code/GeoAc/GeoAc.Eigenray.cpp:30-121) and GeoAc_3DEigenray_LM (:123-335), and the Global
+ * counterparts (Code/GeoAcGlobal_main.cpp:573-583, Code/GeoAc/GeoAc.Eigenray.Global.cpp:46-136, :139-320), for one source
+ * and n_rcvr receivers at once.  Same decisions as the reference's one-ray-at-a-time search; the rays of all
  * receivers, bounce counts and brackets are traced in batches on the GPU (geoac_b200/csrc/eigenray.cu). */
 typedef struct geoac_eig_opts {
     double theta_min, theta_max;   /* inclination limits [deg], 0.5 / 45 (GeoAc3D_main.cpp:461)                        */
@@ -186,6 +187,9 @@ typedef struct geoac_eig_opts {
     double d_theta_big;            /* 0.25  (Eigenray.cpp:20)                                                           */
     double d_theta_small;          /* 0.002 (Eigenray.cpp:21)                                                           */
     double tolerance;              /* [km] arrival-to-receiver distance that ends the LM search, 0.1 (Eigenray.cpp:139) */
+    double src_lat_deg, src_lon_deg; /* Global variants only: the source as the Global mains hold it, in DEGREES (30, 0;
+                                      GeoAcGlobal_main.cpp:497); the search launches from lat*Pi/180, lon*Pi/180 and
+                                      params.src[0] (altitude).  Receivers are (lat, lon) in degrees there            */
     int32_t bnc_min, bnc_max;      /* bounce counts searched, 0 / 0                                                     */
     int32_t iterations;            /* LM iteration limit, 25                                                            */
     int32_t max_rounds;            /* safety limit on trace batches, 4096                                               */
@@ -201,7 +205,8 @@ int geoac_default_eig_opts(geoac_eig_opts* o);
  *    eigenrays found.  A ray that ends on the step limit counts as having left the region (the reference would go on with
  *    the state at the limit). */
 enum { GEOAC_EIG_NF = 18 };
-/* rcvr_xy: n_rcvr pairs (x, y) [km].  rows: cap_rows * GEOAC_EIG_NF doubles; *n_rows = rows produced (GEOAC_ERR_TOO_LARGE
+/* rcvr_xy: n_rcvr pairs (x, y) [km], or (lat, lon) [deg] for the Global variants (phi columns 4, 8 are then 90 - azimuth, as
+ * inside the reference).  rows: cap_rows * GEOAC_EIG_NF doubles; *n_rows = rows produced (GEOAC_ERR_TOO_LARGE
  * if more than cap_rows).  stats (may be NULL): [0] trace batches, [1] rays traced, [2] eigenrays found.  The raypath file
  * of an eigenray (<title>_Eigenray-N.dat) is geoac_trace_paths at (theta, phi) with accum_per_segment = 1, stride 25. */
 int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy,

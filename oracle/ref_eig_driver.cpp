@@ -9,10 +9,11 @@
 //   phi measured from the x axis as inside the reference).  The reference's own text outputs (<title>_results.dat,
 //   <title>_Eigenray-N.dat) are written into `workdir`.
 //
-// Usage: ref_eig3d <out.bin> <workdir> <profile>  [key=value ...]            (stratified)
-//        ref_eig3drngdep <out.bin> <workdir> <prefix> <loc_x> <loc_y> [key=value ...]
-//   keys: theta_min theta_max bnc_min bnc_max bounces x_src y_src z_src x_rcvr y_rcvr azimuth_err_lim iterations freq abs_coeff
-//         z_grnd alt_max rng_max profile_format verbose
+// Usage: ref_eig3d | ref_eigglobal <out.bin> <workdir> <profile>  [key=value ...]            (stratified)
+//        ref_eig3drngdep | ref_eigglobalrngdep <out.bin> <workdir> <prefix> <loc_1> <loc_2> [key=value ...]
+//   keys: theta_min theta_max bnc_min bnc_max bounces x_src y_src z_src x_rcvr y_rcvr (Global: lat_src lon_src lat_rcvr lon_rcvr,
+//         degrees; GeoAcGlobal_main.cpp:522-526) azimuth_err_lim iterations freq abs_coeff z_grnd alt_max rng_max profile_format verbose
+// The Global variants link Code/GeoAc/GeoAc.Eigenray.Global.cpp instead; phi columns are then 90 - azimuth as that file holds them.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,10 +32,14 @@
 #include "GeoAc/GeoAc.Interface.h"
 #include "GeoAc/GeoAc.Eigenray.h"
 
-#ifdef REF_3DRNGDEP
+#if defined(REF_3DRNGDEP) || defined(REF_GLOBALRNGDEP)
+#define REF_RNGDEP 1
 void Spline_Multi_G2S(char*, char*, char*, char*);
 #else
 void Spline_Single_G2S(char*, char*);
+#endif
+#if defined(REF_GLOBAL) || defined(REF_GLOBALRNGDEP)
+#define REF_GLOB 1
 #endif
 
 int main(int argc, char** argv) {
@@ -43,7 +48,7 @@ int main(int argc, char** argv) {
         rl.rlim_cur = rl.rlim_max; setrlimit(RLIMIT_STACK, &rl);
         if (!getenv("REF_DRIVER_REEXEC")) { setenv("REF_DRIVER_REEXEC", "1", 1); execv("/proc/self/exe", argv); }
     }
-#ifdef REF_3DRNGDEP
+#ifdef REF_RNGDEP
     const int nprof = 3;
 #else
     const int nprof = 1;
@@ -59,14 +64,18 @@ int main(int argc, char** argv) {
     }
     if (chdir(argv[2]) != 0) { perror("chdir"); return 2; }
 
+#ifdef REF_GLOB
+    double Source_Loc[3] = { 30.0, 0.0, 0.0 }, Receiver_Loc[2] = { 30.0, -2.5 };      // (lat, lon) [deg], z: GeoAcGlobal_main.cpp:497-498
+#else
     double Source_Loc[3] = { 0.0, 0.0, 0.0 }, Receiver_Loc[2] = { -250.0, 0.0 };
+#endif
     double theta_min = 0.5, theta_max = 45.0, azimuth_err_lim = 2.0, freq = 0.1;
     int bnc_min = 0, bnc_max = 0, iterations = 25;
     char* fmt = (char*)"zTuvdp";
     verbose_output = false; z_grnd = 0.0; tweak_abs = 0.3;
     const int first_kv = 3 + nprof;
     for (int i = first_kv; i < argc; i++) if (!strncmp(argv[i], "profile_format=", 15)) fmt = argv[i] + 15;
-#ifndef REF_3DRNGDEP
+#ifndef REF_RNGDEP
     Spline_Single_G2S((char*)prof[0].c_str(), fmt);               // as in the main: load before parsing
 #endif
     for (int i = first_kv; i < argc; i++) {
@@ -76,11 +85,18 @@ int main(int argc, char** argv) {
         else if (!strncmp(a, "bnc_min=", 8))           bnc_min = atoi(a + 8);
         else if (!strncmp(a, "bnc_max=", 8))           bnc_max = atoi(a + 8);
         else if (!strncmp(a, "bounces=", 8))           bnc_min = bnc_max = atoi(a + 8);
+#ifdef REF_GLOB
+        else if (!strncmp(a, "lat_src=", 8))           Source_Loc[0] = atof(a + 8);
+        else if (!strncmp(a, "lon_src=", 8))           Source_Loc[1] = atof(a + 8);
+        else if (!strncmp(a, "lat_rcvr=", 9))          Receiver_Loc[0] = atof(a + 9);
+        else if (!strncmp(a, "lon_rcvr=", 9))          Receiver_Loc[1] = atof(a + 9);
+#else
         else if (!strncmp(a, "x_src=", 6))             Source_Loc[0] = atof(a + 6);
         else if (!strncmp(a, "y_src=", 6))             Source_Loc[1] = atof(a + 6);
-        else if (!strncmp(a, "z_src=", 6))             Source_Loc[2] = atof(a + 6);
         else if (!strncmp(a, "x_rcvr=", 7))            Receiver_Loc[0] = atof(a + 7);
         else if (!strncmp(a, "y_rcvr=", 7))            Receiver_Loc[1] = atof(a + 7);
+#endif
+        else if (!strncmp(a, "z_src=", 6))             Source_Loc[2] = atof(a + 6);
         else if (!strncmp(a, "verbose=", 8))           verbose_output = atoi(a + 8) != 0;
         else if (!strncmp(a, "azimuth_err_lim=", 16))  azimuth_err_lim = atof(a + 16);
         else if (!strncmp(a, "iterations=", 11))       iterations = atof(a + 11);
@@ -88,16 +104,18 @@ int main(int argc, char** argv) {
         else if (!strncmp(a, "abs_coeff=", 10))        tweak_abs = std::max(0.0, atof(a + 10));
         else if (!strncmp(a, "z_grnd=", 7))            z_grnd = atof(a + 7);
         else if (!strncmp(a, "alt_max=", 8))           GeoAc_vert_limit = atof(a + 8);
-#ifndef REF_3DRNGDEP
+#ifndef REF_RNGDEP
         else if (!strncmp(a, "rng_max=", 8))           GeoAc_range_limit = atof(a + 8);
 #endif
         else if (!strncmp(a, "profile_format=", 15)) {}
         else { fprintf(stderr, "unknown key %s\n", a); return 2; }
     }
     Source_Loc[2] = std::max(z_grnd, Source_Loc[2]);
-#ifdef REF_3DRNGDEP
+#ifdef REF_RNGDEP
     Spline_Multi_G2S((char*)prof[0].c_str(), (char*)prof[1].c_str(), (char*)prof[2].c_str(), fmt);
     GeoAc_SetPropRegion();
+#elif defined(REF_GLOBAL)
+    Spline_Single_G2S((char*)prof[0].c_str(), fmt);               // GeoAcGlobal_main.cpp:547 loads the profile a second time
 #endif
     char title[8] = "e";
     results.open("e_results.dat");

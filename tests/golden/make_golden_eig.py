@@ -28,7 +28,13 @@ CASES = {
     "eig3d_far": (abi.GEOAC_3D, [mg.TOY], dict(x_rcvr=-520, y_rcvr=60, bnc_min=1, bnc_max=2, azimuth_err_lim=0.4)),
     # range-dependent Cartesian variant on the synthetic grid of the parity cases
     "eig3drngdep": (abi.GEOAC_3D_RNGDEP, "grid_cart", dict(x_src=13.7, y_src=-21.3, x_rcvr=-230, y_rcvr=95, bnc_min=0, bnc_max=1)),
+    # spherical variants (Code/GeoAc/GeoAc.Eigenray.Global.cpp): the shipped default (receiver 2.5 deg west) and an oblique one
+    "eigglobal_w": (abi.GEOAC_GLOBAL, [mg.TOY], dict(bnc_min=0, bnc_max=1)),
+    "eigglobal_nw": (abi.GEOAC_GLOBAL, [mg.TOY], dict(lat_src=41.5, lon_src=12.25, lat_rcvr=42.6, lon_rcvr=8.9, bnc_min=0, bnc_max=1, z_src=0.8, azimuth_err_lim=0.3)),
+    "eigglobalrngdep": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(lat_src=33.3, lon_src=1.7, lat_rcvr=34.1, lon_rcvr=-1.2, bnc_min=0, bnc_max=0)),
 }
+
+EXE = {abi.GEOAC_3D: "ref_eig3d", abi.GEOAC_3D_RNGDEP: "ref_eig3drngdep", abi.GEOAC_GLOBAL: "ref_eigglobal", abi.GEOAC_GLOBAL_RNGDEP: "ref_eigglobalrngdep"}
 
 
 def main(names):
@@ -41,7 +47,7 @@ def main(names):
                 files = list(mg.GRIDS[prof]["build"](td))
                 extra["grid"] = prof
                 prof = files
-            exe = os.path.join(ROOT, "oracle", "_ref", "ref_eig3d" if variant == abi.GEOAC_3D else "ref_eig3drngdep")
+            exe = os.path.join(ROOT, "oracle", "_ref", EXE[variant])
             wd = os.path.join(td, "w")
             os.makedirs(wd)
             out = os.path.join(td, "o.bin")

@@ -50,15 +50,27 @@ def opts_from(kv):
     for k in ("bnc_min", "bnc_max", "iterations"):
         if k in kv:
             o[k] = int(kv[k])
+    for k in ("lat_src", "lon_src"):
+        if k in kv:
+            o["src_" + k[:3] + "_deg"] = float(kv[k])
     return o
 
 
-def receiver(kv):
+def is_glob(variant):
+    return int(variant) in (abi.GEOAC_GLOBAL, abi.GEOAC_GLOBAL_RNGDEP)
+
+
+def receiver(kv, variant=abi.GEOAC_3D):
+    if is_glob(variant):
+        return float(kv.get("lat_rcvr", 30.0)), float(kv.get("lon_rcvr", -2.5))
     return float(kv.get("x_rcvr", -250.0)), float(kv.get("y_rcvr", 0.0))
 
 
-def set_source(p, kv):
-    p.src[0], p.src[1], p.src[2] = float(kv.get("x_src", 0.0)), float(kv.get("y_src", 0.0)), float(kv.get("z_src", 0.0))
+def set_source(p, kv, variant=abi.GEOAC_3D):
+    if is_glob(variant):          # altitude only; latitude / longitude go in degrees through the search options, as in the Global mains
+        p.src[0] = float(kv.get("z_src", 0.0))
+    else:
+        p.src[0], p.src[1], p.src[2] = float(kv.get("x_src", 0.0)), float(kv.get("y_src", 0.0)), float(kv.get("z_src", 0.0))
     return p
 
 
@@ -86,13 +98,14 @@ def check_attributes(rows, text, label):
         assert near(r[14], t["back_az"], 1e-6) and abs(r[15] - t["dev"]) < 1e-6, (label, r[14], r[15], t)
 
 
-@pytest.mark.parametrize("name", ["eig3d_axis", "eig3d_far"])
+@pytest.mark.parametrize("name", ["eig3d_axis", "eig3d_far", "eigglobal_w"])
 def test_oracle_eigenray_search_matches_reference(name, oracle):
     from oracle import pyoracle as po, pyeig
     d, kv = load(name)
-    at = po.atmo1d(False, *po.load_met_1d(util.TOY))
-    p = set_source(po.default_params(abi.GEOAC_3D, at), kv)
-    rows, _ = pyeig.run_eig_search(abi.GEOAC_3D, at, p, receiver(kv), **opts_from(kv))
+    variant = int(d["variant"])
+    at = po.atmo1d(is_glob(variant), *po.load_met_1d(util.TOY, global_taper=is_glob(variant)))
+    p = set_source(po.default_params(variant, at), kv, variant)
+    rows, _ = pyeig.run_eig_search(variant, at, p, receiver(kv, variant), **opts_from(kv))
     check_rows(rows, d["rows"], name)
     ok = d["rows"][:, 1] == 1
     assert np.array_equal(rows[ok][:, [4, 7, 8]], d["rows"][ok][:, [3, 6, 7]]), "oracle is bit-exact on the search angles"
@@ -102,11 +115,11 @@ def test_oracle_eigenray_search_matches_reference(name, oracle):
 def _tracer(d, kv):
     variant = int(d["variant"])
     tr = g.Tracer(variant, 0)
-    if variant == abi.GEOAC_3D:
-        tr.set_atmosphere_1d(*g.load_met_1d(util.TOY))
+    if variant in (abi.GEOAC_3D, abi.GEOAC_GLOBAL):
+        tr.set_atmosphere_1d(*g.load_met_1d(util.TOY, global_taper=is_glob(variant)))
     else:
         tr.set_atmosphere_3d(*util.load_grid(d))
-    tr.params = set_source(tr.params, kv)
+    tr.params = set_source(tr.params, kv, variant)
     return tr
 
 
@@ -116,7 +129,7 @@ def test_cuda_eigenray_search_matches_reference(name):
     d, kv = load(name)
     tr = _tracer(d, kv)
     before = bytes(tr.params)
-    rows, stats = tr.eigenray_search([receiver(kv)], **opts_from(kv))
+    rows, stats = tr.eigenray_search([receiver(kv, d["variant"])], **opts_from(kv))
     assert bytes(tr.params) == before, "the search must leave the context's parameters as it found them"
     check_rows(rows, d["rows"], name)
     check_attributes(rows, str(d["text"]), name)
@@ -152,7 +165,7 @@ def test_eigenray_search_error_paths():
     tr = g.Tracer(abi.GEOAC_2D, 0)
     tr.set_atmosphere_1d(*g.load_met_1d(util.TOY))
     with pytest.raises(g.GeoAcError):
-        tr.eigenray_search([(-250.0, 0.0)])                 # only the Cartesian 3-D variants have an eigenray search
+        tr.eigenray_search([(-250.0, 0.0)])                 # GeoAc2D has no eigenray search
     tr3 = g.Tracer(abi.GEOAC_3D, 0)
     with pytest.raises(g.GeoAcError):
         tr3.eigenray_search([(-250.0, 0.0)])                # no atmosphere yet
