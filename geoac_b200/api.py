@@ -61,6 +61,7 @@ def lib():
         L.geoac_default_eig_opts.argtypes = [C.POINTER(abi.GeoacEigOpts)]
         L.geoac_eigenray_search.argtypes = [C.c_void_p, C.POINTER(abi.GeoacEigOpts), C.c_int, _dp, C.c_int64, _dp,
                                             C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.geoac_eigenray_direct.argtypes = [C.c_void_p, C.POINTER(abi.GeoacEigOpts), C.c_int, _dp, _dp, _dp, C.POINTER(C.c_int64)]
         L.geoac_get_variant.argtypes = [C.c_void_p]
         L.geoac_source_state.argtypes = [C.c_void_p, _dp]
         L.geoac_measure_fp64_peak.restype = C.c_double
@@ -73,7 +74,7 @@ EXPORTED_SYMBOLS = [
     "geoac_create", "geoac_destroy", "geoac_last_error", "geoac_default_params", "geoac_set_atmosphere_1d",
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
-    "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_get_variant", "geoac_source_state",
+    "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_eigenray_direct", "geoac_get_variant", "geoac_source_state",
 ]
 
 
@@ -180,6 +181,21 @@ class Tracer:
                     "geoac_eigenray_search")
         return rows[:n.value].copy(), {"rounds": stats[0], "rays": stats[1], "found": stats[2]}
 
+    def eigenray_direct(self, receivers, estimates, **opts):
+        """-eig_direct: LM search from caller-supplied estimates [(theta_est, phi_est (deg from the x axis), bounces)], one per
+        receiver entry; rows as eigenray_search."""
+        o = abi.GeoacEigOpts()
+        lib().geoac_default_eig_opts(C.byref(o))
+        for k, v in opts.items():
+            setattr(o, k, v)
+        rc = np.ascontiguousarray(receivers, dtype=np.float64).reshape(-1, 2)
+        est = np.ascontiguousarray(estimates, dtype=np.float64).reshape(-1, 3)
+        assert len(rc) == len(est)
+        rows = np.zeros((len(rc), abi.EIG_NF))
+        stats = (C.c_int64 * 3)()
+        self._check(lib().geoac_eigenray_direct(self._h, C.byref(o), len(rc), _p(rc), _p(est), _p(rows), stats), "geoac_eigenray_direct")
+        return rows, {"rounds": stats[0], "rays": stats[1], "found": stats[2]}
+
     def source_state(self):
         """c, u, v, rho at the source point as the kernels sample them."""
         out = np.zeros(4)
@@ -254,7 +270,7 @@ class Tracer:
         return steps / (32.0 * t.value) if t.value else 0.0
 
     def last_kernel_launches(self):
-        """Kernels the last trace enqueued (1, or 5 with the longest-ray-first scheduling pass)."""
+        """Kernels the last trace enqueued (1; 5 or 10 with the longest-ray-first scheduling pass)."""
         k = C.c_int64(0)
         self._check(lib().geoac_last_trace_counters(self._h, None, C.byref(k)), "geoac_last_trace_counters")
         return k.value

@@ -39,6 +39,7 @@ struct geoac_ctx {
     double xmin = 0, xmax = 0;
     std::vector<double> h_table;
     double* d_table = nullptr;
+    double* d_sbpoly = nullptr;      // per-interval absorption polynomials of the 1-D table (core.cuh), rebuilt with the invariants
     // range-dependent grid
     bool is_grid = false;
     Grid3D grid{};
@@ -48,7 +49,7 @@ struct geoac_ctx {
     double* d_prev = nullptr; size_t cap_prev = 0; // y_{k-1} scratch of the trace kernel
     double* d_path = nullptr; size_t cap_path = 0; int32_t* d_path_rows = nullptr; size_t cap_path_rows = 0;   // raypath capture staging
     double* d_caus = nullptr; size_t cap_caus = 0; int32_t* d_caus_rows = nullptr; size_t cap_caus_rows = 0;   // caustic event staging
-    uint32_t *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr; int64_t cap_order = 0;   // longest-ray-first scheduling
+    uint32_t *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_blockhist = nullptr, *d_order2 = nullptr; uint8_t* d_keys = nullptr; int64_t cap_order = 0, cap_keys = 0;   // longest-ray-first scheduling
     int last_launches = 0;
     // staging for the host-buffer entry point
     double *d_theta = nullptr, *d_phi = nullptr, *d_rec = nullptr;
@@ -114,8 +115,8 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
 extern "C" void geoac_destroy(geoac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaFree(ctx->d_table); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters); cudaFree(ctx->d_prev);
-    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows); cudaFree(ctx->d_caus); cudaFree(ctx->d_caus_rows);
+    cudaFree(ctx->d_table); cudaFree(ctx->d_sbpoly); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters); cudaFree(ctx->d_prev);
+    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_blockhist); cudaFree(ctx->d_order2); cudaFree(ctx->d_keys); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows); cudaFree(ctx->d_caus); cudaFree(ctx->d_caus_rows);
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -181,6 +182,8 @@ extern "C" int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, c
         for (int i = 0; i < n; i++) { tb[(size_t)i * TAB_NARR + slots[f]] = col[i]; tb[(size_t)i * TAB_NARR + slots[f] + 1] = slo[i]; }
     }
     cudaFree(ctx->d_table); ctx->d_table = nullptr;
+    cudaFree(ctx->d_sbpoly); ctx->d_sbpoly = nullptr;
+    CK(cudaMalloc(&ctx->d_sbpoly, (size_t)(n - 1) * SBP_STRIDE * sizeof(double)));
     CK(cudaMalloc(&ctx->d_table, ctx->h_table.size() * sizeof(double)));
     CK(cudaMemcpy(ctx->d_table, tb, ctx->h_table.size() * sizeof(double), cudaMemcpyHostToDevice));
     ctx->n = n; ctx->xmin = x[0]; ctx->xmax = x[n - 1];
@@ -356,6 +359,16 @@ __global__ void setup_consts_kernel(LaunchConsts* out, const LaunchConsts in, co
     *out = L;
 }
 
+// per-interval absorption polynomials (core.cuh: sbpoly_build_interval), one thread per interval, after the invariants
+__global__ void build_sbpoly_kernel(const LaunchConsts* Lc, const double* table, int n, double xmin, double xmax, int glob, double* out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n - 1) return;
+    Table1D T; T.base = table; T.n = n; T.xmin = xmin; T.xmax = xmax; T.jump_scale = 0.0; T.sbpoly = nullptr;
+    double o[SBP_STRIDE];
+    sbpoly_build_interval(*Lc, T, glob != 0, k, o);
+    for (int i = 0; i < SBP_STRIDE; i++) out[(size_t)k * SBP_STRIDE + i] = o[i];
+}
+
 __global__ void setup_consts_grid_kernel(LaunchConsts* out, const LaunchConsts in, const Grid3D g, int variant) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     LaunchConsts L = in;
@@ -379,7 +392,11 @@ static int refresh_consts(geoac_ctx* ctx) {
     L.step_limit = (int)(p.ray_limit * (int)(1.0 / (p.ds_min * 10)));                                     // Solver.cpp:14
     L.per_bounce_zmax = (ctx->variant == GEOAC_3D_RNGDEP || ctx->variant == GEOAC_GLOBAL_RNGDEP);         // App. A-3
     if (ctx->is_grid) setup_consts_grid_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->grid, ctx->variant);
-    else setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->xmin, ctx->xmax, ctx->variant);
+    else {
+        setup_consts_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_consts, L, ctx->d_table, ctx->n, ctx->xmin, ctx->xmax, ctx->variant);
+        build_sbpoly_kernel<<<(ctx->n - 1 + 63) / 64, 64, 0, ctx->stream>>>(ctx->d_consts, ctx->d_table, ctx->n, ctx->xmin, ctx->xmax,
+                                                                            ctx->variant == GEOAC_GLOBAL, ctx->d_sbpoly);
+    }
     CK(cudaGetLastError());
     ctx->consts_dirty = false;
     return GEOAC_OK;
@@ -457,15 +474,43 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
         }
-        order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long);
-        order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
-        order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
+        // stratified sets: order by (cost bucket, inclination, batch index) + whole-warp refill, so that a warp's lanes read
+        // the same few table records (trace_kernel.cuh); GEOAC_B200_STABLE=0 keeps the plain counting sort (A/B measurements)
+        static const int stable_env = [] { const char* e = std::getenv("GEOAC_B200_STABLE"); return e ? std::atoi(e) : 1; }();
+        if (!PacketMode<EQ>::value && stable_env) {
+            const int nblk = ctx->sm_count;
+            const int64_t n = a.n_rays, chunk = (n + nblk - 1) / nblk;
+            if (!ctx->d_blockhist) CK(cudaMalloc(&ctx->d_blockhist, sizeof(uint32_t) * (size_t)nblk * kCostBuckets + 2 * sizeof(double)));
+            if (n > ctx->cap_keys) {
+                cudaFree(ctx->d_keys); cudaFree(ctx->d_order2); ctx->d_keys = nullptr; ctx->d_order2 = nullptr; ctx->cap_keys = 0;
+                CK(cudaMalloc(&ctx->d_keys, (size_t)2 * n)); CK(cudaMalloc(&ctx->d_order2, sizeof(uint32_t) * n));
+                ctx->cap_keys = n;
+            }
+            double* trange = reinterpret_cast<double*>(ctx->d_blockhist + (size_t)nblk * kCostBuckets);
+            uint8_t *key_t = ctx->d_keys, *key_c = ctx->d_keys + n;
+            order_theta_range_kernel<<<1, 1024, 0, st>>>(a.theta, n, trange);
+            static const int cost_shift = [] { const char* e = std::getenv("GEOAC_B200_COSTSHIFT"); return e ? std::min(7, std::max(0, std::atoi(e))) : 2; }();
+            order_keys_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_c, cost_shift);
+            stable_hist_kernel<<<nblk, 256, 0, st>>>(key_t, nullptr, n, chunk, ctx->d_blockhist);
+            stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
+            stable_scatter_kernel<<<nblk, 32, 0, st>>>(key_t, nullptr, n, chunk, ctx->d_blockhist, ctx->d_order2);
+            stable_hist_kernel<<<nblk, 256, 0, st>>>(key_c, ctx->d_order2, n, chunk, ctx->d_blockhist);
+            stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
+            stable_scatter_kernel<<<nblk, 32, 0, st>>>(key_c, ctx->d_order2, n, chunk, ctx->d_blockhist, ctx->d_order);
+            ctx->last_launches += 8;
+            if (!std::getenv("GEOAC_B200_PACKET")) a.packet_refill = 1;
+        } else {
+            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long);
+            order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
+            order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
+            ctx->last_launches += 3;
+        }
         CK(cudaGetLastError());
         a.n_claims = n_entries;
         static const bool coop_off = [] { const char* e = std::getenv("GEOAC_B200_COOP"); return e && std::atoi(e) == 0; }();
         a.n_long = (PacketMode<EQ>::value && !coop_off) ? n_long : nullptr;
         a.order = ctx->d_order;
-        ctx->last_launches += 4;
+        ctx->last_launches += 1;                                        // the cost scout
     }
     void* args[] = { (void*)&a };
     CK(cudaLaunchKernel(fn, dim3(grid), dim3(BLOCK), args, smem, st));
@@ -494,6 +539,10 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     TraceArgs a;
     a.grid = ctx->grid;
     a.table = ctx->d_table; a.table_n = ctx->n; a.table_xmin = ctx->xmin; a.table_xmax = ctx->xmax;
+    {   // GEOAC_B200_SBPOLY=0: evaluate the absorption model in full at every step (A/B measurements, tests)
+        const char* e = std::getenv("GEOAC_B200_SBPOLY");
+        a.sbpoly = (ctx->is_grid || (e && std::atoi(e) == 0)) ? nullptr : ctx->d_sbpoly;
+    }
     a.consts = ctx->d_consts; a.theta = d_theta; a.phi = d_phi; a.n_rays = n_rays; a.n_rec = n_rec;
     a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
     a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1; a.warp_trips = ctx->d_counters + 2;

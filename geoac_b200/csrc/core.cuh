@@ -156,6 +156,7 @@ struct Table1D {
     int n;
     double xmin, xmax;
     double jump_scale;      // > 0 (cost scout only): (n-1)/(xmax-xmin), lets a far query jump near its interval before the walk
+    const double* sbpoly = nullptr;   // per-interval absorption polynomials (SBP_STRIDE doubles each, global memory) or nullptr
     GEOAC_HD const double* lvl(int k) const { return base + (size_t)k * TAB_NARR; }
 };
 
@@ -282,7 +283,9 @@ GEOAC_CONST_TABLE double kSBX5[6] = { -53.746, 1.5439, -1.8824E-2, 1.1587E-4, -3
 //   * the remaining exponentials (gas fractions 10^poly(z), rotational collision numbers, vibrational Boltzmann factors)
 //     are evaluated in lock step by the branch-free g_exp_n; the polynomials in z are Horner forms;
 //   * every quotient is a product with one of five reciprocals (two of them batched inversions).
-GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho) {
+// `parts` (table builder only): [0] = G2 with (a_cl + a_diff) * scale = sqrt(s1m1 * G2), [1] = (a_rot + a_vib) * scale, where
+// scale = tweak_abs * 8.685889 and s1m1 = sqrt(1 + nu^2) - 1 is the one non-smooth factor of the model (see below).
+GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho, double* parts = nullptr) {
     const double mu_o = 18.192E-6, S = 117.0;
     const double inv_c2 = inv_c * inv_c;
     const double c2 = (c * c) * 1.0e6;                                      // (1000 c)^2
@@ -417,7 +420,114 @@ GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, 
     const double rd = g_rcp(d01 * d23);
     const double r01 = rd * d23, r23 = rd * d01;
     const double a_vib = inv_c * ((num[0] * (r01 * den[1]) + num[1] * (r01 * den[0])) + (num[2] * (r23 * den[3]) + num[3] * (r23 * den[2])));
+    if (parts) {
+        const double sc2 = 1.003 * L.tweak_abs * 8.685889;
+        parts[0] = (w_c * w_c) * (0.5 * cchi2p1 * (rq * q2)) * (sc2 * sc2);
+        parts[1] = (a_rot + a_vib) * L.tweak_abs * 8.685889;
+    }
     return (a_cl + a_rot + a_diff + a_vib) * L.tweak_abs * 8.685889;
+}
+
+// ---- absorption of the stratified variants through per-interval polynomials ----
+// In a stratified atmosphere c and rho are functions of altitude alone, so the Sutherland-Bass coefficient is too, and inside
+// one spline interval (0.1 km in the G2S profiles) it is analytic EXCEPT for the classical term's factor
+// s1m1 = sqrt(1 + nu^2) - 1, whose cancellation noise (a staircase in z below ~60 km) is observable in the reference's output
+// and is therefore kept literal.  alpha = sqrt(s1m1 * G2(z)) + S(z): nu and s1m1 are computed exactly as in suthbass_alpha,
+// G2 and S -- all the exponentials -- are degree-6 interpolants of the exact function at the interval's Chebyshev nodes,
+// built once per launch configuration (freq, abs_coeff) by sbpoly_build_interval with the device's own suthbass_alpha.
+// An interval whose interpolants miss the exact function by more than 1e-12 relative at eight check points (a gas-fraction
+// threshold inside it, a coarse user profile) is flagged and evaluated exactly, as are queries outside the table.
+constexpr int SBP_DEG = 6;
+constexpr int SBP_STRIDE = 16;      // [0..6] G2 (monomials in s = 2X - 1), [7] flag (0 = valid), [8..14] S, [15] unused
+
+#if defined(__CUDA_ARCH__)
+GEOAC_HD Pair ldg_pair(const double* p) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); Pair r; r.a = v.x; r.b = v.y; return r; }
+#else
+GEOAC_HD Pair ldg_pair(const double* p) { Pair r; r.a = p[0]; r.b = p[1]; return r; }
+#endif
+
+// the full model, out of line: it is the rare path of sb_alpha_1d and must not set the register budget of the step loop
+#if defined(__CUDA_ARCH__)
+__device__ __noinline__ double suthbass_alpha_cold(const LaunchConsts& L, double z, double c, double inv_c, double rho) { return suthbass_alpha(L, L.sb, z, c, inv_c, rho); }
+#else
+inline double suthbass_alpha_cold(const LaunchConsts& L, double z, double c, double inv_c, double rho) { return suthbass_alpha(L, L.sb, z, c, inv_c, rho); }
+#endif
+
+// absorption [dB/km] at the point seg_locate(T, zq, k) found (interval k, offset sp.X); z_eff = altitude the model sees
+GEOAC_HD double sb_alpha_1d(const LaunchConsts& L, const Table1D& T, const SegPos& sp, int k, double zq, double z_eff, double c, double inv_c) {
+    const double rho = spl_f(T, TAB_RHO, sp);
+    if (T.sbpoly != nullptr && zq >= T.xmin && zq <= T.xmax) {
+        const double* q = T.sbpoly + (size_t)k * SBP_STRIDE;
+        const Pair g01 = ldg_pair(q), g23 = ldg_pair(q + 2), g45 = ldg_pair(q + 4), g67 = ldg_pair(q + 6);
+        const Pair s01 = ldg_pair(q + 8), s23 = ldg_pair(q + 10), s45 = ldg_pair(q + 12), s67 = ldg_pair(q + 14);
+        if (g67.b == 0.0) {
+            // nu exactly as suthbass_alpha computes it
+            const double S = 117.0, mu_o = 18.192E-6;
+            const double inv_c2 = inv_c * inv_c;
+            const double c2 = (c * c) * 1.0e6;
+            const double T_z = c2 * (1.0 / (kR * kGam));
+            const double inv_Tz = inv_c2 * (kR * kGam * 1.0e-6);
+            const double den1 = 1.0 + S * inv_Tz;
+            const double r1 = g_rcp(rho * den1);
+            const double inv_rho = r1 * den1, inv_den1 = r1 * rho;
+            const double inv_Pz = inv_rho * inv_c2 * (kGam * 1.0e-9);
+            const double sq = g_sqrt(T_z * L.sb.invTo);
+            const double mu_ratio = sq * (L.sb.visc_num * inv_den1);
+            const double nu = (8.0 * kPi * L.freq * mu_o * (1.0 / 3.0)) * mu_ratio * inv_Pz;
+            const double s1m1 = g_sqrt(1.0 + nu * nu) - 1.0;
+            const double s = fma(2.0, sp.X, -1.0);
+            const double G2 = fma(fma(fma(fma(fma(fma(g67.a, s, g45.b), s, g45.a), s, g23.b), s, g23.a), s, g01.b), s, g01.a);
+            const double Sm = fma(fma(fma(fma(fma(fma(s67.a, s, s45.b), s, s45.a), s, s23.b), s, s23.a), s, s01.b), s, s01.a);
+            return g_sqrt(fmax(s1m1 * G2, 1e-290)) + Sm;
+        }
+    }
+    return suthbass_alpha_cold(L, z_eff, c, inv_c, rho);
+}
+
+// Builds the SBP_STRIDE coefficients of interval k of a 1-D table (one thread per interval on the device).
+GEOAC_HD void sbpoly_build_interval(const LaunchConsts& L, const Table1D& T, bool glob, int k, double* out) {
+    const double x0 = T.lvl(k)[TAB_X], x1 = T.lvl(k + 1)[TAB_X], h = x1 - x0;
+    double f[2][SBP_DEG + 1], a[2][SBP_DEG + 1];
+    auto eval = [&](double s, double* g2, double* sm) {
+        double z = x0 + (0.5 * (s + 1.0)) * h;
+        z = (z < x0) ? x0 : ((z > x1) ? x1 : z);
+        int cur = k;
+        const SegPos sp = seg_locate(T, z, cur);
+        const double Tv = spl_f(T, TAB_T, sp), rho = spl_f(T, TAB_RHO, sp);
+        const double gT = kGamR * Tv;
+        const double inv_c = g_rsqrt(gT), c = gT * inv_c;
+        double parts[2];
+        suthbass_alpha(L, L.sb, glob ? z - kREarth : z, c, inv_c, rho, parts);
+        *g2 = parts[0]; *sm = parts[1];
+    };
+    const int N = SBP_DEG + 1;
+    for (int j = 0; j < N; j++) eval(cos((2 * j + 1) * (kPi / (2.0 * N))), &f[0][j], &f[1][j]);
+    for (int w = 0; w < 2; w++) {
+        for (int m = 0; m < N; m++) {
+            double acc = 0.0;
+            for (int j = 0; j < N; j++) acc += f[w][j] * cos((double)(m * (2 * j + 1)) * (kPi / (2.0 * N)));
+            a[w][m] = acc * ((m == 0 ? 1.0 : 2.0) / N);
+        }
+        double* o = out + 8 * w;                                           // Chebyshev -> monomials (degree 6)
+        o[0] = a[w][0] - a[w][2] + a[w][4] - a[w][6];
+        o[1] = a[w][1] - 3.0 * a[w][3] + 5.0 * a[w][5];
+        o[2] = 2.0 * a[w][2] - 8.0 * a[w][4] + 18.0 * a[w][6];
+        o[3] = 4.0 * a[w][3] - 20.0 * a[w][5];
+        o[4] = 8.0 * a[w][4] - 48.0 * a[w][6];
+        o[5] = 16.0 * a[w][5];
+        o[6] = 32.0 * a[w][6];
+    }
+    bool bad = false;
+    const double chk[8] = { -0.97, -0.75, -0.45, -0.15, 0.15, 0.45, 0.75, 0.97 };
+    for (int j = 0; j < 8; j++) {
+        double e[2]; eval(chk[j], &e[0], &e[1]);
+        for (int w = 0; w < 2; w++) {
+            const double* o = out + 8 * w; const double s = chk[j];
+            const double pv = o[0] + s * (o[1] + s * (o[2] + s * (o[3] + s * (o[4] + s * (o[5] + s * o[6])))));
+            if (!(fabs(pv - e[w]) <= 1e-12 * fabs(e[w])) || !(e[w] > 0.0)) bad = true;
+        }
+    }
+    out[7] = bad ? 1.0 : 0.0; out[15] = 0.0;
 }
 
 // fill the Sutherland-Bass invariants from the reference state (c, rho at the reference level)

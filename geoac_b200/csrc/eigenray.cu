@@ -232,9 +232,22 @@ struct Search {
     struct Call { int rcvr, n_bnc; Est e; Lm l; };
 
     // Replays every chain against the cache.  Returns true when nothing is missing.
-    bool replay(int n_rcvr, const double* rcv_xy, std::vector<Call>& calls) {
+    // direct != nullptr: -eig_direct (GeoAc3D_RunEigDirect, GeoAc3D_main.cpp:546-601): no estimate, one LM search per entry
+    // from the caller's { theta_est, phi_est [deg from the x axis], bounces }.
+    bool replay(int n_rcvr, const double* rcv_xy, const double* direct, std::vector<Call>& calls) {
         calls.clear();
         bool all = true;
+        if (direct) {
+            for (int ir = 0; ir < n_rcvr; ir++) {
+                const double rcv[2] = { rcv_xy[2 * ir], rcv_xy[2 * ir + 1] };
+                Call c; c.rcvr = ir; c.n_bnc = (int)direct[3 * ir + 2];
+                c.e.complete = c.e.ok = c.e.next_known = true; c.e.theta_est = direct[3 * ir]; c.e.phi_est = direct[3 * ir + 1]; c.e.theta_next = 0.0;
+                c.l = lm(rcv, c.e.theta_est, c.e.phi_est, c.n_bnc);
+                all = all && c.l.complete;
+                calls.push_back(c);
+            }
+            return all;
+        }
         for (int ir = 0; ir < n_rcvr; ir++) {
             const double rcv[2] = { rcv_xy[2 * ir], rcv_xy[2 * ir + 1] };
             for (int n_bnc = o.bnc_min; n_bnc <= o.bnc_max; n_bnc++) {
@@ -295,8 +308,8 @@ extern "C" int geoac_default_eig_opts(geoac_eig_opts* o) {
     return GEOAC_OK;
 }
 
-extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy,
-                                     int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats) {
+static int run_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy, const double* direct,
+                      int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats) {
     if (!ctx || !opts || !rcvr_xy || !n_rows || n_rcvr < 0 || (cap_rows > 0 && !rows)) return GEOAC_ERR_BAD_ARG;
     const int variant = geoac_get_variant(ctx);
     if (variant == GEOAC_2D) return GEOAC_ERR_BAD_ARG;                                    // GeoAc2D has no eigenray search
@@ -320,7 +333,7 @@ extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts,
     const int max_rounds = opts->max_rounds > 0 ? opts->max_rounds : 4096;
     bool done = false;
     for (S.rounds = 0; S.rounds < max_rounds; S.rounds++) {
-        done = S.replay(n_rcvr, rcvr_xy, calls);
+        done = S.replay(n_rcvr, rcvr_xy, direct, calls);
         if (done) break;
         rc = S.trace_requests(err);
         if (rc) { geoac_set_params(ctx, &user); return rc; }
@@ -387,4 +400,17 @@ extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts,
     }
     if (stats) { stats[0] = S.rounds; stats[1] = S.rays_traced; stats[2] = (int64_t)found.size(); }
     return (int64_t)calls.size() <= cap_rows ? GEOAC_OK : GEOAC_ERR_TOO_LARGE;
+}
+
+extern "C" int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy,
+                                     int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats) {
+    return run_search(ctx, opts, n_rcvr, rcvr_xy, nullptr, cap_rows, rows, n_rows, stats);
+}
+
+extern "C" int geoac_eigenray_direct(geoac_ctx* ctx, const geoac_eig_opts* opts, int n, const double* rcvr_xy, const double* estimates,
+                                     double* rows, int64_t* stats) {
+    if (!estimates) return GEOAC_ERR_BAD_ARG;
+    for (int i = 0; i < n; i++) if (!(estimates[3 * i + 2] >= 0.0) || estimates[3 * i + 2] > 1000.0) return GEOAC_ERR_BAD_ARG;
+    int64_t n_rows = 0;
+    return run_search(ctx, opts, n, rcvr_xy, estimates, n, rows, &n_rows, stats);
 }

@@ -121,14 +121,13 @@ struct Eq3D {
         const double Tv = spl_f(T, TAB_T, sp);
         const double u = spl_f(T, TAB_U, sp);
         const double v = spl_f(T, TAB_V, sp);
-        const double rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         const double nu_mag = (L.c_000 - rc.nx * u - rc.ny * v) * inv_c;            // c(0,0,0): App. A-4
         const double cn = c * g_rcp(nu_mag);
         const double cp0 = cn * rc.nx + u, cp1 = cn * rc.ny + v, cp2 = cn * nz;
         dtt = ds * g_rsqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
-        datt = suthbass_alpha(L, L.sb, zm, c, inv_c, rho) * ds;
+        datt = sb_alpha_1d(L, T, sp, cur, zm, zm, c, inv_c) * ds;
     }
 
     // GeoAc_ApproximateIntercept + GeoAc_SetReflectionConditions, 3DStratified.cpp:136-186
@@ -278,11 +277,10 @@ struct Eq2D {
         const double Tv = spl_f(T, TAB_T, sp);
         const double u = spl_f(T, TAB_U, sp);
         const double v = spl_f(T, TAB_V, sp);
-        const double rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         dtt = ds * g_rcp(c + u * rc.cphi + v * rc.sphi);
-        datt = suthbass_alpha(L, L.sb, zm, c, inv_c, rho) * ds;
+        datt = sb_alpha_1d(L, T, sp, cur, zm, zm, c, inv_c) * ds;
     }
 
     // GeoAc_ApproximateIntercept + GeoAc_SetReflectionConditions, 2DStratified.cpp:74-117

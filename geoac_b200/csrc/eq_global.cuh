@@ -156,13 +156,12 @@ struct EqGlobal {
         const double Tv = spl_f(T, TAB_T, sp);
         const double u = spl_f(T, TAB_U, sp);
         const double v = spl_f(T, TAB_V, sp);
-        const double rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         const double cn = c * g_rsqrt(n0 * n0 + n1 * n1 + n2 * n2);
         const double c0 = cn * n0, c1 = cn * n1 + v, c2 = cn * n2 + u;
         dtt = ds_tt * g_rsqrt(c0 * c0 + c1 * c1 + c2 * c2);
-        datt = suthbass_alpha(L, L.sb, rm - kREarth, c, inv_c, rho) * ds_sb;
+        datt = sb_alpha_1d(L, T, sp, cur, rm, rm - kREarth, c, inv_c) * ds_sb;
     }
 
     // GeoAc_ApproximateIntercept (first order only, App. A-7) + GeoAc_SetReflectionConditions, Global.cpp:140-205

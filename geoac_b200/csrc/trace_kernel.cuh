@@ -28,6 +28,7 @@ struct TraceArgs {
     const double* table;        // global copy of the table (n records of TAB_NARR doubles, 16-byte aligned)
     int table_n;
     double table_xmin, table_xmax;
+    const double* sbpoly;       // per-interval absorption polynomials of the table (core.cuh) or nullptr = exact evaluation
     const LaunchConsts* consts; // device
     const double* theta;        // [n_rays]
     const double* phi;
@@ -291,7 +292,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
         T = a.grid;
         T.scratch = work + 2 * NEQ;
     } else {
-        T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.jump_scale = 0.0;
+        T.n = a.table_n; T.xmin = a.table_xmin; T.xmax = a.table_xmax; T.jump_scale = 0.0; T.sbpoly = a.sbpoly;
         if (TABLE_IN_SMEM) {
             tma_stage_table(tab_s, a.table, (uint32_t)(TAB_NARR * a.table_n * sizeof(double)), bar);
             T.base = tab_s;
@@ -561,6 +562,88 @@ __global__ void order_scatter_kernel(const uint32_t* cost, int64_t n, int group,
             const int64_t r = g * group + l;
             order[(int64_t)pos * group + l] = (r < n) ? (uint32_t)r : 0xffffffffu;
         }
+    }
+}
+
+// ---- claim order of the stratified sets: (cost bucket descending, inclination, batch index) ----
+// A warp claims 32 consecutive entries and refills only when all of them have ended.  Sorted this way they are rays of
+// near-equal predicted cost, EQUAL inclination and neighbouring azimuths (the mains enumerate the grid azimuth by azimuth),
+// i.e. near-identical altitude histories: the lanes' table reads hit the same one or two records (a shared-memory broadcast
+// instead of the 5-way bank conflict of unrelated altitudes) and the interval searches do not diverge.
+// Two passes of a STABLE counting sort (LSD order): by inclination bucket, then by cost bucket.  Block b owns the contiguous
+// slice [b*chunk, (b+1)*chunk) of the sequence: per-block histograms, one scan over (bucket, block), then every block (one
+// warp) places its slice in order, ranks within a warp step from __match_any_sync.  The order only schedules: records do not
+// depend on it (tests/test_gpu_parity.py::test_longest_ray_first_schedule_is_result_neutral).
+__global__ void order_theta_range_kernel(const double* theta, int64_t n, double* range) {        // one block; range[0] = min, [1] = max
+    __shared__ double lo[32], hi[32];
+    double a = 1e300, b = -1e300;
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) { const double t = theta[i]; a = fmin(a, t); b = fmax(b, t); }
+    for (int off = 16; off > 0; off >>= 1) { a = fmin(a, __shfl_xor_sync(0xffffffffu, a, off)); b = fmax(b, __shfl_xor_sync(0xffffffffu, b, off)); }
+    if ((threadIdx.x & 31) == 0) { lo[threadIdx.x >> 5] = a; hi[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); w++) { a = fmin(a, lo[w]); b = fmax(b, hi[w]); }
+        range[0] = a; range[1] = b;
+    }
+}
+// cost_shift coarsens the cost key (256 >> shift levels): a level must be wide enough to hold a whole run of neighbouring
+// azimuths of one inclination, and narrow enough that the rays of a warp end within a few per cent of each other.
+__global__ void order_keys_kernel(const uint32_t* cost, const double* theta, int64_t n, const uint32_t* cost_max, const double* range,
+                                  uint8_t* key_theta, uint8_t* key_cost, int cost_shift) {
+    const uint32_t cmax = *cost_max;
+    const double t0 = range[0], span = range[1] - range[0];
+    const double sc = span > 0.0 ? (kCostBuckets - 1) / span : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int kt = (int)((theta[i] - t0) * sc + 0.5);
+        key_theta[i] = (uint8_t)(kt < 0 ? 0 : (kt > kCostBuckets - 1 ? kCostBuckets - 1 : kt));
+        key_cost[i] = (uint8_t)(cost_bucket(cost[i], cmax) >> cost_shift);
+    }
+}
+__global__ void stable_hist_kernel(const uint8_t* key, const uint32_t* src, int64_t n, int64_t chunk, uint32_t* blockhist) {
+    __shared__ uint32_t h[kCostBuckets];
+    for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
+    __syncthreads();
+    const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(n, g0 + chunk);
+    for (int64_t g = g0 + threadIdx.x; g < g1; g += blockDim.x) atomicAdd(&h[key[src ? src[g] : (uint32_t)g]], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) blockhist[(size_t)blockIdx.x * kCostBuckets + i] = h[i];
+}
+__global__ void stable_scan_kernel(uint32_t* blockhist, int nblk) {        // one block of kCostBuckets threads: counts -> start offsets
+    __shared__ uint32_t h[kCostBuckets];
+    const int t = threadIdx.x;
+    uint32_t tot = 0;
+    for (int b = 0; b < nblk; b++) tot += blockhist[(size_t)b * kCostBuckets + t];
+    h[t] = tot;
+    __syncthreads();
+    for (int off = 1; off < kCostBuckets; off <<= 1) {
+        const uint32_t v = (t >= off) ? h[t - off] : 0u;
+        __syncthreads();
+        h[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = h[t] - tot;
+    for (int b = 0; b < nblk; b++) { const uint32_t v = blockhist[(size_t)b * kCostBuckets + t]; blockhist[(size_t)b * kCostBuckets + t] = run; run += v; }
+}
+__global__ void stable_scatter_kernel(const uint8_t* key, const uint32_t* src, int64_t n, int64_t chunk, const uint32_t* blockoffs, uint32_t* dst) {   // 32 threads
+    __shared__ uint32_t base[kCostBuckets];
+    for (int i = threadIdx.x; i < kCostBuckets; i += 32) base[i] = blockoffs[(size_t)blockIdx.x * kCostBuckets + i];
+    __syncwarp();
+    const int64_t g0 = (int64_t)blockIdx.x * chunk, g1 = min(n, g0 + chunk);
+    const unsigned lane = threadIdx.x;
+    for (int64_t gb = g0; gb < g1; gb += 32) {
+        const int64_t g = gb + lane;
+        const bool on = g < g1;
+        const unsigned active = __ballot_sync(0xffffffffu, on);
+        if (on) {
+            const uint32_t r = src ? src[g] : (uint32_t)g;
+            const int b = key[r];
+            const unsigned m = __match_any_sync(active, b);
+            const uint32_t pos = base[b] + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            __syncwarp(active);
+            if ((int)lane == __ffs(m) - 1) base[b] += (uint32_t)__popc(m);
+            dst[pos] = r;
+        }
+        __syncwarp();
     }
 }
 

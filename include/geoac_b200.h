@@ -212,6 +212,13 @@ enum { GEOAC_EIG_NF = 18 };
 int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy,
                           int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats);
 
+/* -eig_direct (GeoAc3D_RunEigDirect, Code/GeoAc3D_main.cpp:546-601, and the other three 3-D mains): GeoAc_3DEigenray_LM
+ * alone, from caller-supplied estimates.  n searches at once: receiver i = rcvr_xy[2i..], estimates[3i..] = { theta_est
+ * [deg], phi_est [deg from the x axis = 90 - azimuth], bounces }.  rows: n * GEOAC_EIG_NF doubles, same columns as above
+ * (columns 3, 4 repeat the estimate; bnc_min / bnc_max / theta limits of opts are not used). */
+int geoac_eigenray_direct(geoac_ctx* ctx, const geoac_eig_opts* opts, int n, const double* rcvr_xy, const double* estimates,
+                          double* rows, int64_t* stats);
+
 /* Variant the context was created for; c, u, v, rho at the source point (device-sampled), 4 doubles. */
 int geoac_get_variant(const geoac_ctx* ctx);
 int geoac_source_state(geoac_ctx* ctx, double* out4);
@@ -221,8 +228,9 @@ int geoac_eq_count(int variant, int calc_amp);
 
 /* Scheduling counters of the last trace.  warp_trips: trips round the kernel's step loop summed over warps -- lane
  * occupancy = total_steps / (32 * warp_trips), i.e. how full the warps were on average (ray lifetimes differ; finished
- * lanes are refilled until the batch is exhausted).  kernel_launches: kernels the call enqueued (1 trace kernel, plus 4
- * when the longest-ray-first claim order was built: cost scout, histogram, scan, scatter).  Either pointer may be NULL. */
+ * lanes are refilled until the batch is exhausted).  kernel_launches: kernels the call enqueued (1 trace kernel; plus, when the
+ * longest-ray-first claim order was built, the cost scout and the counting sort: 3 kernels for the range-dependent sets,
+ * 8 for the stratified ones, whose order is (cost, inclination, batch index) in two stable passes).  Either pointer may be NULL. */
 int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kernel_launches);
 
 /* Device self-test of the kernel's branch-free FP64 primitives against the CUDA math library on n_per_thread random

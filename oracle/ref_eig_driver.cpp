@@ -70,7 +70,9 @@ int main(int argc, char** argv) {
     double Source_Loc[3] = { 0.0, 0.0, 0.0 }, Receiver_Loc[2] = { -250.0, 0.0 };
 #endif
     double theta_min = 0.5, theta_max = 45.0, azimuth_err_lim = 2.0, freq = 0.1;
-    int bnc_min = 0, bnc_max = 0, iterations = 25;
+    int bnc_min = 0, bnc_max = 0, iterations = 25, direct = 0;
+    double theta_direct = 0.5, phi_direct = 45.0;      // -eig_direct: theta_est= and phi_est= (phi_est as an azimuth, like the mains)
+    bool have_phi = false;
     char* fmt = (char*)"zTuvdp";
     verbose_output = false; z_grnd = 0.0; tweak_abs = 0.3;
     const int first_kv = 3 + nprof;
@@ -97,6 +99,9 @@ int main(int argc, char** argv) {
         else if (!strncmp(a, "y_rcvr=", 7))            Receiver_Loc[1] = atof(a + 7);
 #endif
         else if (!strncmp(a, "z_src=", 6))             Source_Loc[2] = atof(a + 6);
+        else if (!strncmp(a, "direct=", 7))            direct = atoi(a + 7);
+        else if (!strncmp(a, "theta_est=", 10))        theta_direct = atof(a + 10);
+        else if (!strncmp(a, "phi_est=", 8))           { phi_direct = 90.0 - atof(a + 8); have_phi = true; }      // GeoAc3D_main.cpp:588
         else if (!strncmp(a, "verbose=", 8))           verbose_output = atoi(a + 8) != 0;
         else if (!strncmp(a, "azimuth_err_lim=", 16))  azimuth_err_lim = atof(a + 16);
         else if (!strncmp(a, "iterations=", 11))       iterations = atof(a + 11);
@@ -121,6 +126,16 @@ int main(int argc, char** argv) {
     results.open("e_results.dat");
     std::vector<double> rows;
     const auto t0 = std::chrono::steady_clock::now();
+    if (direct) {                                      // GeoAc3D_RunEigDirect, GeoAc3D_main.cpp:546-601 (bounces= sets bnc_min = bnc_max here)
+#ifndef REF_GLOB
+        if (!have_phi) phi_direct = 180.0 / 3.14159 * atan2(Receiver_Loc[1], Receiver_Loc[0]);                       // :586
+#endif
+        double th = theta_direct, ph = phi_direct;
+        const int before = eigenray_count;
+        GeoAc_3DEigenray_LM(Source_Loc, Receiver_Loc, th, ph, freq, bnc_min, iterations, title);
+        double row[8] = { (double)bnc_min, 1.0, theta_direct, phi_direct, 0.0, eigenray_count > before ? 1.0 : 0.0, th, ph };
+        rows.insert(rows.end(), row, row + 8);
+    } else
     for (int n_bnc = bnc_min; n_bnc <= bnc_max; n_bnc++) {
         double theta_start = theta_min, theta_next, theta_est, phi_est;
         while (theta_start < theta_max) {

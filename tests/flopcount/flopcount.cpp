@@ -65,6 +65,10 @@ extern "C" int flopcount_1d(int variant, const geoac_params* p, int n, const dou
     LaunchConsts L; base_consts(L, variant, p);
     if (variant == GEOAC_2D || variant == GEOAC_3D) L.src[2] = std::max(p->z_grnd, p->src[2]); else L.src[0] = std::max(p->z_grnd, p->src[0]);
     fill_launch_consts_1d(L, T, variant);
+    // absorption through the per-interval polynomials, as the product does (core.cuh); building them is set-up, not counted (run() resets the tally)
+    std::vector<Cnt> sbp((size_t)(n - 1) * SBP_STRIDE);
+    for (int k = 0; k < n - 1; k++) sbpoly_build_interval(L, T, variant == GEOAC_GLOBAL, k, &sbp[(size_t)k * SBP_STRIDE]);
+    T.sbpoly = sbp.data();
     const int n_rec = p->bounces + 1;
     switch (variant) {
         case GEOAC_2D: run<Eq2D<true>>(L, T, n_rays, th, ph, n_rec, "2d"); return 0;

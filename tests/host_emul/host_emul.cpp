@@ -3,6 +3,8 @@
 // g++ so that the de-duplicated device math can be checked against the oracle in the build container, where there
 // is no GPU.  The real parity gate is tests/test_gpu_parity.py on a B200.
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <algorithm>
@@ -50,6 +52,14 @@ extern "C" long emul_trace_1d(int variant, const geoac_params* p, int n, const d
     L.step_limit = (int)(p->ray_limit * (int)(1.0 / (p->ds_min * 10)));
     L.per_bounce_zmax = 0;
     fill_launch_consts_1d(L, T, variant);
+    std::vector<double> sbp;                                  // GEOAC_EMUL_SBPOLY=1: absorption through the per-interval polynomials, as on the device
+    if (const char* e = std::getenv("GEOAC_EMUL_SBPOLY")) if (std::atoi(e) != 0) {
+        sbp.resize((size_t)(n - 1) * SBP_STRIDE);
+        long flagged = 0;
+        for (int k = 0; k < n - 1; k++) { sbpoly_build_interval(L, T, variant == GEOAC_GLOBAL, k, &sbp[(size_t)k * SBP_STRIDE]); flagged += sbp[(size_t)k * SBP_STRIDE + 7] != 0.0; }
+        if (std::atoi(e) > 1) std::fprintf(stderr, "sbpoly: %ld of %d intervals flagged for exact evaluation\n", flagged, n - 1);
+        T.sbpoly = sbp.data();
+    }
     RecOut o; o.rec = rec; o.status = status; o.n_steps = n_steps; o.n_rec = p->bounces + 1; o.n_slots = n_rays * o.n_rec;
     o.path = path; o.path_rows = path_rows; o.path_stride = path_stride; o.path_cap = path_cap;
     o.caus = caus; o.caus_rows = caus_rows; o.caus_cap = caus_cap;

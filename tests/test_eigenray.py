@@ -129,7 +129,11 @@ def test_cuda_eigenray_search_matches_reference(name):
     d, kv = load(name)
     tr = _tracer(d, kv)
     before = bytes(tr.params)
-    rows, stats = tr.eigenray_search([receiver(kv, d["variant"])], **opts_from(kv))
+    if "direct" in kv:         # -eig_direct: phi_est= is an azimuth on the command line, 90 - azimuth inside (GeoAc3D_main.cpp:588)
+        rows, stats = tr.eigenray_direct([receiver(kv, d["variant"])], [(float(kv["theta_est"]), 90.0 - float(kv["phi_est"]), int(kv["bounces"]))],
+                                         **{k: v for k, v in opts_from(kv).items() if k.startswith("src_")})
+    else:
+        rows, stats = tr.eigenray_search([receiver(kv, d["variant"])], **opts_from(kv))
     assert bytes(tr.params) == before, "the search must leave the context's parameters as it found them"
     check_rows(rows, d["rows"], name)
     check_attributes(rows, str(d["text"]), name)

@@ -160,3 +160,40 @@ def test_device_built_node_tables_match_set_slopes_multi(glob, monkeypatch):
     th.set_atmosphere_3d(ax0, ax1, axz, T, u, v, rho)
     tuv_h, rh_h = th.grid_tables(n0, n1, nz)
     assert np.array_equal(tuv.view(np.uint64), tuv_h.view(np.uint64)) and np.array_equal(rh.view(np.uint64), rh_h.view(np.uint64))
+
+
+@pytest.mark.parametrize("workload", ["config1", "config2", "config3"])
+def test_absorption_polynomials_match_the_full_model(workload, monkeypatch):
+    """The stratified kernels take the Sutherland-Bass coefficient from per-interval polynomials of its smooth factors
+    (core.cuh: sb_alpha_1d; the cancellation staircase of the classical term stays literal).  Against the full model
+    evaluated at every step (GEOAC_B200_SBPOLY=0) the accumulated absorption must agree to 1e-11 and every other output must
+    be bit-identical -- on ToyAtmo (no interval flagged) and on the config-3 profile (a few intervals fall back to the full
+    model because the piecewise-linear temperature kinks inside them)."""
+    _, _, _, th, ph = bench.workload_angles(workload)
+    step = max(1, len(th) // 3000)
+    th, ph = th[::step].copy(), ph[::step].copy()
+    tr, p = bench.setup_tracer(workload, 0)
+    monkeypatch.setenv("GEOAC_B200_SBPOLY", "1")
+    a = tr.trace(th, ph)
+    monkeypatch.setenv("GEOAC_B200_SBPOLY", "0")
+    b = tr.trace(th, ph)
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["n_steps"], b["n_steps"])
+    m = a["status"] == abi.ST_ARRIVAL
+    assert m.sum() > 100
+    for f in range(abi.NFIELDS):
+        if f == abi.F_ATTEN:
+            rel = np.abs(a["rec"][f][m] - b["rec"][f][m]) / np.abs(b["rec"][f][m])
+            assert rel.max() < 1e-11, rel.max()
+        else:
+            assert np.array_equal(a["rec"][f][m].view(np.uint64), b["rec"][f][m].view(np.uint64)), f
+    # a changed frequency rebuilds the table
+    q = tr.params
+    q.freq = 2.5
+    tr.params = q
+    monkeypatch.setenv("GEOAC_B200_SBPOLY", "1")
+    c = tr.trace(th[:200], ph[:200])
+    monkeypatch.setenv("GEOAC_B200_SBPOLY", "0")
+    d = tr.trace(th[:200], ph[:200])
+    mm = c["status"] == abi.ST_ARRIVAL
+    rel = np.abs(c["rec"][abi.F_ATTEN][mm] - d["rec"][abi.F_ATTEN][mm]) / np.abs(d["rec"][abi.F_ATTEN][mm])
+    assert rel.max() < 1e-11 and (c["rec"][abi.F_ATTEN][mm] > 5 * a["rec"][abi.F_ATTEN][:200][mm]).all()
