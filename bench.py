@@ -43,7 +43,7 @@ KERNEL_NAMES = {V2D: "geoac::trace_kernel<Eq2D<true>,512,true>", V3D: "geoac::tr
 #  * SURVEY_FLOPS_PER_STEP: SURVEY 8d's provisional hand de-duplication of the REFERENCE's formulation (+-25 %); reported
 #    next to it as `achieved_survey_figure`.  The range-dependent figures differ most: the tensor-product sampler needs
 #    17-19 k operations where the reference's five-bicubic-patch scheme, de-duplicated, needs ~39 k.
-ALGO_FLOPS_PER_STEP = {V2D: 766.0, V3D: 1270.0, VGLOBAL: 2225.2, V3DRD: 16988.7, VGLOBALRD: 18613.4}
+ALGO_FLOPS_PER_STEP = {V2D: 766.0, V3D: 1295.0, VGLOBAL: 2225.2, V3DRD: 16988.7, VGLOBALRD: 18613.4}
 SURVEY_FLOPS_PER_STEP = {V2D: 1400.0, V3D: 2200.0, VGLOBAL: 2800.0, V3DRD: 39000.0, VGLOBALRD: 40000.0}
 
 #               variant    theta_min, theta_max, theta_step, phi_min, phi_max, phi_step   bounces  atmosphere

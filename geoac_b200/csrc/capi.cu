@@ -470,7 +470,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             const int sblocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * std::max(1, s_per_sm), s_need);
             unsigned long long* scounter = ctx->d_counters + 3;
             const char* ce = std::getenv("GEOAC_B200_SCOUT_COARSE");        // experiments: step-size multiple of the scout
-            int coarse = ce ? std::max(1, std::atoi(ce)) : kScoutCoarse;
+            int coarse = ce ? std::max(1, std::atoi(ce)) : (kGrid ? kScoutCoarse : 2 * kScoutCoarse);   // stratified: 32x measured best (404.8 vs 421.0 / 443.3 ms at 16x / 64x)
             void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
         }
@@ -567,7 +567,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
             const int blk = e ? std::atoi(e) : 384;
             if (blk == 256) return launch_trace<Eq3D<true>, 256>(ctx, a, st);
             if (blk == 512) return launch_trace<Eq3D<true>, 512>(ctx, a, st);
-            return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 168 registers, no spills: 8.4 G steps/s vs 7.3 (320) / 7.1 (448) / 6.95 (512) / 7.13 (256)
+            return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 158 registers, no spills: 420 ms per config-2 pass vs 491 (256) / 494 (512); 416 / 448 lanes compile to 128 registers with spills
         }
 #ifdef GEOAC_HAVE_GLOBAL
         case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 384>(ctx, a, st) : launch_trace<EqGlobal<false>, 512>(ctx, a, st);

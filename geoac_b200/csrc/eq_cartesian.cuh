@@ -74,12 +74,15 @@ struct Eq3D {
         const SoundSpeed s = sound_speed2(Tv, dT, ddT);
         const double nz = p[3];
         const double nu_mag = (L.c_src - (rc.nx * u + rc.ny * v)) * s.inv_c;     // c0/c (1 - nu.v/c0), w = 0
+        // c_prop = c n/|n| + wind = q / nu_mag with q = c n + nu_mag wind: its direction and 1/|c_prop| = nu_mag/|q| need no
+        // reciprocal, so the Newton chains of 1/nu_mag (auxiliary equations only) and 1/|q| run side by side
         const double inv_nm = g_rcp(nu_mag);
+        const double q0 = fma(nu_mag, u, s.c * rc.nx), q1 = fma(nu_mag, v, s.c * rc.ny), q2 = s.c * nz;
+        const double inv_q = g_rsqrt(q0 * q0 + q1 * q1 + q2 * q2);
+        const double inv_cpm = nu_mag * inv_q;
         const double cn = s.c * inv_nm;
-        const double cp0 = cn * rc.nx + u, cp1 = cn * rc.ny + v, cp2 = cn * nz;
-        const double inv_cpm = g_rsqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
-        const double e0 = cp0 * inv_cpm, e1 = cp1 * inv_cpm, e2 = cp2 * inv_cpm;   // dx/ds
-        f[0] = e0; f[1] = e1; f[2] = e2;
+        const double cp0 = q0 * inv_nm, cp1 = q1 * inv_nm, cp2 = q2 * inv_nm;
+        f[0] = q0 * inv_q; f[1] = q1 * inv_q; f[2] = q2 * inv_q;                   // dx/ds
         const double G = nu_mag * s.dc + rc.nx * du + rc.ny * dv;
         f[3] = -G * inv_cpm;
         if (AMP) {
@@ -124,9 +127,8 @@ struct Eq3D {
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
         const double nu_mag = (L.c_000 - rc.nx * u - rc.ny * v) * inv_c;            // c(0,0,0): App. A-4
-        const double cn = c * g_rcp(nu_mag);
-        const double cp0 = cn * rc.nx + u, cp1 = cn * rc.ny + v, cp2 = cn * nz;
-        dtt = ds * g_rsqrt(cp0 * cp0 + cp1 * cp1 + cp2 * cp2);
+        const double q0 = fma(nu_mag, u, c * rc.nx), q1 = fma(nu_mag, v, c * rc.ny), q2 = c * nz;    // c_prop = q / nu_mag (see rhs)
+        dtt = (ds * nu_mag) * g_rsqrt(q0 * q0 + q1 * q1 + q2 * q2);
         datt = sb_alpha_1d(L, T, sp, cur, zm, zm, c, inv_c) * ds;
     }
 
