@@ -44,6 +44,7 @@ KERNEL_NAMES = {V2D: "geoac::trace_kernel<Eq2D<true>,512,true>", V3D: "geoac::tr
 #    next to it as `achieved_survey_figure`.  The range-dependent figures differ most: the tensor-product sampler needs
 #    17-19 k operations where the reference's five-bicubic-patch scheme, de-duplicated, needs ~39 k.
 ALGO_FLOPS_PER_STEP = {V2D: 766.0, V3D: 1295.0, VGLOBAL: 2225.2, V3DRD: 16988.7, VGLOBALRD: 18613.4}
+NCU_DRAM_BYTES_PER_RAY = {"config2": 502.0}       # measured with ncu --set full, see roofline.traffic_source
 SURVEY_FLOPS_PER_STEP = {V2D: 1400.0, V3D: 2200.0, VGLOBAL: 2800.0, V3DRD: 39000.0, VGLOBALRD: 40000.0}
 
 #               variant    theta_min, theta_max, theta_step, phi_min, phi_max, phi_step   bounces  atmosphere
@@ -397,7 +398,12 @@ def run_ours(args):
             "gpu_launches": args.steps * launches_per_pass,
             "clocks": sampler.summary(),
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
-                         "traffic": None, "kernel": KERNEL_NAMES[variant], "kernel_ms_per_launch": kern_ms,
+                         "traffic": (NCU_DRAM_BYTES_PER_RAY[args.workload] * n if args.workload in NCU_DRAM_BYTES_PER_RAY else None),
+                         "traffic_source": ("bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture "
+                                            "(profiles/r1_ncu_full_trace_kernel_Eq3D_final2.txt, 86 400-ray slice: 43.4 MB = 502 B per ray), scaled "
+                                            "to this launch's rays; algorithmic: 16 B of angles in + 216 B per arrival record out"
+                                            if args.workload in NCU_DRAM_BYTES_PER_RAY else None),
+                         "kernel": KERNEL_NAMES[variant], "kernel_ms_per_launch": kern_ms,
                          "algorithmic_flops_per_rk4_step": flops_step,
                          "achieved_survey_figure": SURVEY_FLOPS_PER_STEP[variant] * total_steps / (kern_ms * 1e-3) / 1e12,
                          "survey_flops_per_rk4_step": SURVEY_FLOPS_PER_STEP[variant],

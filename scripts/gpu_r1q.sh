@@ -4,4 +4,3 @@ run() { env "$@" timeout 600 python bench.py --workload ${WL:-config2} --no-cpu-
 import json,sys; d=json.loads(open('gpurun_out/r1q_tmp.json').read().strip().splitlines()[-1]); print('RESULT', sys.argv[1:], d['value'], d['rk4_steps_per_sec'], d['ms_per_step'], d['roofline']['frac'], d['config']['lane_occupancy'])" "$@"; }
 run A=1
 WL=config3 EXTRA="--steps 2 --warmup 1" run A=1
-WL=config3 EXTRA="--steps 2 --warmup 1" run GEOAC_B200_SCOUT_COARSE=16
