@@ -215,7 +215,10 @@ int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr
 /* -eig_direct (GeoAc3D_RunEigDirect, Code/GeoAc3D_main.cpp:546-601, and the other three 3-D mains): GeoAc_3DEigenray_LM
  * alone, from caller-supplied estimates.  n searches at once: receiver i = rcvr_xy[2i..], estimates[3i..] = { theta_est
  * [deg], phi_est [deg from the x axis = 90 - azimuth], bounces }.  rows: n * GEOAC_EIG_NF doubles, same columns as above
- * (columns 3, 4 repeat the estimate; bnc_min / bnc_max / theta limits of opts are not used). */
+ * (columns 3, 4 repeat the estimate; bnc_min / bnc_max / theta limits of opts are not used).  GeoAc3D (stratified) only:
+ * in this mode the reference evaluates `if(GeoAc_AtmoStrat) M_Comps = ...` (Eigenray.cpp:130-135) before anything has set
+ * that flag (GeoAc_ConfigureCalcAmp, :146), so it iterates with uninitialised Mach components; this entry point uses the
+ * ones -eig_search uses, and finds the same eigenray within `tolerance` rather than the same digits. */
 int geoac_eigenray_direct(geoac_ctx* ctx, const geoac_eig_opts* opts, int n, const double* rcvr_xy, const double* estimates,
                           double* rows, int64_t* stats);
 

@@ -32,9 +32,13 @@ CASES = {
     "eigglobal_w": (abi.GEOAC_GLOBAL, [mg.TOY], dict(bnc_min=0, bnc_max=1)),
     "eigglobal_nw": (abi.GEOAC_GLOBAL, [mg.TOY], dict(lat_src=41.5, lon_src=12.25, lat_rcvr=42.6, lon_rcvr=8.9, bnc_min=0, bnc_max=1, z_src=0.8, azimuth_err_lim=0.3)),
     "eigglobalrngdep": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(lat_src=33.3, lon_src=1.7, lat_rcvr=34.1, lon_rcvr=-1.2, bnc_min=0, bnc_max=0)),
-    # -eig_direct: GeoAc_3DEigenray_LM alone from a user estimate (phi_est given as an azimuth, as on the command line)
+    # -eig_direct: GeoAc_3DEigenray_LM alone from a user estimate (phi_est given as an azimuth, as on the command line).
+    # NB the two GeoAc3D (stratified) cases are NOT reproducible bit for bit: in this mode the reference reads M_Comps
+    # uninitialised (Eigenray.cpp:130-135 tests GeoAc_AtmoStrat before GeoAc_ConfigureCalcAmp :146 has set it), so its LM
+    # iterates depend on stack garbage; the tests only require the same eigenray within the search tolerance there.
     "eigdirect3d": (abi.GEOAC_3D, [mg.TOY], dict(direct=1, theta_est=24.0, phi_est=-90.6, bounces=0)),
     "eigdirect3d_bnc": (abi.GEOAC_3D, [mg.TOY], dict(direct=1, x_rcvr=-520, y_rcvr=60, theta_est=25.5, phi_est=-83.3, bounces=1)),
+    "eigdirect3drngdep": (abi.GEOAC_3D_RNGDEP, "grid_cart", dict(direct=1, x_src=13.7, y_src=-21.3, x_rcvr=-230, y_rcvr=95, theta_est=25.2, phi_est=-62.9, bounces=0)),
     "eigdirectglobal": (abi.GEOAC_GLOBAL, [mg.TOY], dict(direct=1, theta_est=7.0, phi_est=-89.0, bounces=0)),
 }
 
