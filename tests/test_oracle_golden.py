@@ -116,3 +116,35 @@ def test_device_math_host_emulation(oracle, name):
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
     problems, _ = util.compare_records(out, want, variant, p.calc_amp, util.RTOL, name, amp_rtol=1e-6)
     assert not problems, "\n".join(problems)
+
+
+@pytest.mark.parametrize("name", ["3d_elevated", "2d_config1", "global_c3"])
+def test_absorption_polynomials_host_emulation(oracle, name, monkeypatch, capfd):
+    """The stratified kernels take the Sutherland-Bass coefficient from per-interval polynomials of its smooth factors
+    (core.cuh: sb_alpha_1d / sbpoly_build_interval).  In the g++ build of the same code: with the polynomial table the
+    accumulated absorption agrees with the full model to 1e-12 and with the reference to the parity tolerance, every other
+    output is bit-identical, and only a few intervals (none on ToyAtmo, the temperature kinks of the config-3 profile) fall
+    back to the full model."""
+    from tests import emul
+    d, kv = util.load_case(name)
+    variant = int(d["variant"])
+    th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
+    arrs = oracle.load_met_1d(util.profile_path(d), global_taper=util.is_global(variant))
+    at = oracle.atmo1d(util.is_global(variant), *arrs)
+    p = util.apply_keys(variant, oracle.default_params(variant, at), kv)
+    monkeypatch.setenv("GEOAC_EMUL_SBPOLY", "2")
+    a = emul.trace(variant, p, arrs, th, ph)
+    err = capfd.readouterr().err
+    flagged, total = map(int, __import__("re").search(r"sbpoly: (\d+) of (\d+) intervals", err).groups())
+    assert flagged <= 0.02 * total and (flagged == 0) == (name != "global_c3"), (flagged, total)
+    monkeypatch.setenv("GEOAC_EMUL_SBPOLY", "0")
+    b = emul.trace(variant, p, arrs, th, ph)
+    m = d["status"] == abi.ST_ARRIVAL
+    for f in range(abi.NFIELDS):
+        if f == abi.F_ATTEN:
+            assert np.max(np.abs(a["rec"][f][m] - b["rec"][f][m]) / np.abs(b["rec"][f][m])) < 1e-12
+        else:
+            assert np.array_equal(a["rec"][f][m], b["rec"][f][m]), f
+    want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
+    problems, _ = util.compare_records(a, want, variant, p.calc_amp, util.RTOL, name, amp_rtol=1e-6)
+    assert not problems, "\n".join(problems)
