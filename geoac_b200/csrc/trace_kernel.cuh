@@ -126,6 +126,12 @@ GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, cons
 
 // Range-dependent sets keep the RK4 accumulator and the stage input in the lane's shared-memory record as well (their
 // right-hand side needs the registers for the 4x4-node sampler); the stratified sets keep them in registers.
+// The four RK4 stages are unrolled for the Cartesian stratified sets (the tail of a stage overlaps the head of the next;
+// config 2: 399.5 -> 387.5 ms per pass, config 1: 100 -> 88 ms) and kept as a loop for the spherical set (18 equations at
+// the register ceiling: unrolled it spills more, config 3: 3.76 -> 4.19 s) and for the range-dependent ones.
+#ifndef GEOAC_STAGE_UNROLL
+#define GEOAC_STAGE_UNROLL 4
+#endif
 template <class EQ> struct WorkInMem { static constexpr bool value = std::is_same<typename EQ::Atmo, Grid3D>::value; };
 
 // prev[i * pstride] holds y_{k-1}[i] (only maintained when NeedsPrev); work = 2 NEQ doubles (WorkInMem) or nullptr;
@@ -144,7 +150,8 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     double* const p = MEM ? work + NEQ : p_r;
 #pragma unroll
     for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = acc[i]; }
-#pragma unroll 1
+    constexpr int kStageUnroll = (MEM || NEQ > 12) ? 1 : GEOAC_STAGE_UNROLL;
+#pragma unroll(kStageUnroll)
     for (int s = 0; s < 4; s++) {
         EQ::rhs(L, T, d.rc, p, f, n.cur);
         const double dsa = ds * ((s == 2) ? 1.0 : 0.5);
