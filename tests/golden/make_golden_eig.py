@@ -25,6 +25,8 @@ CASES = {
     "eig3d_cross": (abi.GEOAC_3D, [mg.TOY], dict(x_rcvr=-280, y_rcvr=130, bnc_min=0, bnc_max=2)),
     "eig3d_east": (abi.GEOAC_3D, [mg.TOY], dict(x_rcvr=310, y_rcvr=-75, bnc_min=0, bnc_max=1, z_src=1.5, azimuth_err_lim=0.5, theta_min=2, theta_max=40)),
     "eig3d_north": (abi.GEOAC_3D, [mg.TOY], dict(x_rcvr=40, y_rcvr=420, bnc_min=1, bnc_max=2, azimuth_err_lim=0.05)),
+    # a tight azimuth limit forces the 4th / 5th correction passes, whose inclination step adapts ray by ray (Modify_d_theta)
+    "eig3d_adaptive": (abi.GEOAC_3D, [mg.TOY], dict(x_rcvr=-280, y_rcvr=130, bnc_min=0, bnc_max=0, azimuth_err_lim=0.0004)),
     "eig3d_far": (abi.GEOAC_3D, [mg.TOY], dict(x_rcvr=-520, y_rcvr=60, bnc_min=1, bnc_max=2, azimuth_err_lim=0.4)),
     # range-dependent Cartesian variant on the synthetic grid of the parity cases
     "eig3drngdep": (abi.GEOAC_3D_RNGDEP, "grid_cart", dict(x_src=13.7, y_src=-21.3, x_rcvr=-230, y_rcvr=95, bnc_min=0, bnc_max=1)),

@@ -142,7 +142,8 @@ def test_cuda_eigenray_search_matches_reference(name):
     else:
         check_rows(rows, d["rows"], name)
         check_attributes(rows, str(d["text"]), name)
-    assert stats["found"] == int(d["rows"][:, 5].sum()) and stats["rounds"] < 80
+    # fixed-step passes are one batch each; the 4th / 5th azimuth-correction passes (eig3d_adaptive) advance ray by ray
+    assert stats["found"] == int(d["rows"][:, 5].sum()) and stats["rounds"] < (600 if "adaptive" in name else 80)
     print(f"\n[{name}] reference {float(d['ref_seconds']):.1f} s one ray at a time; here {stats['rays']} rays in {stats['rounds']} batches")
 
 
