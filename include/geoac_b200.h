@@ -208,7 +208,9 @@ enum { GEOAC_EIG_NF = 18 };
 /* rcvr_xy: n_rcvr pairs (x, y) [km], or (lat, lon) [deg] for the Global variants (phi columns 4, 8 are then 90 - azimuth, as
  * inside the reference).  rows: cap_rows * GEOAC_EIG_NF doubles; *n_rows = rows produced (GEOAC_ERR_TOO_LARGE
  * if more than cap_rows).  stats (may be NULL): [0] trace batches, [1] rays traced, [2] eigenrays found.  The raypath file
- * of an eigenray (<title>_Eigenray-N.dat) is geoac_trace_paths at (theta, phi) with accum_per_segment = 1, stride 25. */
+ * of an eigenray (<title>_Eigenray-N.dat) is geoac_trace_paths at (theta, phi) with accum_per_segment = 1, stride 25.
+ * While it runs the call sets bounces / calc_amp / accum_per_segment (Global: the source) on the context and restores the
+ * caller's parameters before it returns, on the error paths too. */
 int geoac_eigenray_search(geoac_ctx* ctx, const geoac_eig_opts* opts, int n_rcvr, const double* rcvr_xy,
                           int64_t cap_rows, double* rows, int64_t* n_rows, int64_t* stats);
 
