@@ -153,34 +153,57 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU reference arm
-def _sample_stride(total, target_rays, n_proc, fast_axis):
-    stride = max(1, total // max(1, target_rays // n_proc))
-    stride = max(stride, n_proc) if total > n_proc else 1
-    while stride > 1 and math.gcd(stride, fast_axis) != 1:   # theta is the fast axis: keep the sample unbiased in theta
-        stride += 1
+def _theta_count(th_deg):
+    """Number of inclinations of the launch grid, taken from the ENUMERATED angles (theta is the fast axis of the mains'
+    loops); never recomputed from (max - min) / step, which is off by one for loop maxima placed half a step past the end."""
+    th_deg = np.asarray(th_deg)
+    change = np.nonzero(th_deg[1:] < th_deg[:-1])[0]
+    return int(change[0]) + 1 if len(change) else len(th_deg)
+
+
+def _sample_stride(total, want_rays, n_theta):
+    """Stride of a subsample `index = offset + k * stride` that is STRATIFIED in inclination: consecutive sample points step
+    through the theta axis by about 0.382 n_theta (golden-section spacing, coprime with n_theta), so any run of consecutive
+    points -- the whole sample as well as one process's share of it -- covers the inclinations evenly.  Ray lifetimes depend
+    on theta (14x between theta = 1 and 60 deg), so an unstratified sample misestimates rays/s by that much."""
+    stride = max(1, total // max(1, want_rays))
+    if n_theta <= 1 or total <= want_rays:
+        return stride
+    want_mod = max(1, int(round(0.381966 * n_theta)))
+    while math.gcd(want_mod, n_theta) != 1:
+        want_mod += 1
+    stride += (want_mod - stride) % n_theta
     return stride
 
 
-def cpu_reference_run(workload, target_rays, n_proc):
-    """Time the reference's own CPU implementation on every `stride`-th ray of the workload, split over n_proc processes
-    with disjoint ray sets.  Stratified workloads run oracle/_ref/ref_<variant> (the unmodified reference sources + a
-    driver main; kind "reference"); when it is not built, and for the range-dependent workloads (whose reference input
-    is 40 000+ node files), the C restatement in oracle/ is timed instead (kind "port").
-    Returns dict(rays, steps, seconds, kind, cores, sample)."""
+def _sample_sets(total, want_rays, n_proc, n_theta):
+    """Disjoint index sets, one per process: process i takes the sample points k = i, i + n_proc, i + 2 n_proc, ..."""
+    stride = _sample_stride(total, want_rays, n_theta)
+    pts = np.arange(0, total, stride, dtype=np.int64)[: max(n_proc, want_rays)]
+    return stride, [pts[i::n_proc] for i in range(n_proc)]
+
+
+def cpu_reference_run(workload, target_rays, n_proc, as_shipped=False):
+    """Time the reference's own CPU implementation on a theta-stratified subsample of the workload, split over n_proc
+    processes with disjoint ray sets.  Stratified workloads run oracle/_ref/ref_<variant> (the unmodified reference sources +
+    a driver main; kind "reference", built -O2; `as_shipped` runs the -O0 build the reference's makefile produces, kind
+    "reference-as-shipped"); when it is not built, and for the range-dependent workloads (whose reference input is
+    40 000+ node files), the C restatement in oracle/ is timed instead (kind "port").
+    Returns dict(rays, steps, seconds, rate, kind, cores, sample)."""
     from geoac_b200 import abi, synth
     variant, grid, bounces, atmo = WORKLOADS[workload]
     _, th_deg, _, _, _ = workload_angles(workload)
     total = len(th_deg)
-    n_theta = int(round((grid[1] - grid[0]) / grid[2])) + 1
-    stride = _sample_stride(total, target_rays, n_proc, n_theta)
-    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_" + abi.VARIANT_NAMES[variant])
+    n_theta = _theta_count(th_deg)
+    stride, sets = _sample_sets(total, target_rays, n_proc, n_theta)
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "ref_" + abi.VARIANT_NAMES[variant] + ("_O0" if as_shipped else ""))
     keys = dict(theta_min=grid[0], theta_max=grid[1], theta_step=grid[2], bounces=bounces)
     if variant != V2D:
         keys.update(phi_min=grid[3], phi_max=grid[4], phi_step=grid[5], accum_mode=0)
     if workload == "config3":
         keys.update(lat_src=30, lon_src=0, rng_max=3000)
     if os.path.exists(ref_bin) and atmo in ("toy", "c3"):
-        kind = "reference"
+        kind = "reference-as-shipped" if as_shipped else "reference"
         with tempfile.TemporaryDirectory() as td:
             prof = TOY
             if atmo == "c3":
@@ -188,27 +211,31 @@ def cpu_reference_run(workload, target_rays, n_proc):
                 synth.write_met(prof, synth.config3_profile())
             procs = []
             for i in range(n_proc):
-                # process i takes rays with index % stride == i * (stride // n_proc): disjoint, evenly spread
-                off = (i * (stride // n_proc)) % stride
-                cmd = [ref_bin, os.path.join(td, f"o{i}.bin"), prof] + [f"{k}={v}" for k, v in keys.items()] + [f"stride={stride}", f"offset={off}"]
+                # the driver takes rays with index % stride_i == offset_i: process i's points are offset i*stride, spaced n_proc*stride
+                cmd = [ref_bin, os.path.join(td, f"o{i}.bin"), prof] + [f"{k}={v}" for k, v in keys.items()] \
+                    + [f"stride={stride * n_proc}", f"offset={(i * stride) % (stride * n_proc)}"]
                 procs.append(subprocess.Popen(cmd, stdout=subprocess.PIPE, text=True))
             outs = [p.communicate()[0] for p in procs]
         infos = [json.loads(o.strip().splitlines()[-1]) for o in outs]
-        rays = sum(i["rays"] for i in infos)
-        steps = sum(i["steps"] for i in infos)
-        secs = max(i["t_trace_s"] for i in infos)                # slowest process, excluding profile load
+        per = [(i["rays"], i["steps"], i["t_trace_s"]) for i in infos]          # excluding profile load
     else:
+        if as_shipped:
+            return None
         kind = "port"
         from multiprocessing import Pool
-        idx = np.arange(total)
-        shards = [idx[(idx % stride) == ((i * (stride // n_proc)) % stride)] for i in range(n_proc)]
         with Pool(n_proc) as pool:
-            res = pool.starmap(_port_worker, [(workload, s) for s in shards])
-        secs = max(r[2] for r in res)                            # slowest process, excluding atmosphere set-up
-        rays = sum(r[0] for r in res)
-        steps = sum(r[1] for r in res)
-    return {"rays": rays, "steps": steps, "seconds": secs, "kind": kind, "cores": n_proc,
-            "sample": f"every {stride}th ray of {workload} ({rays} of {total} rays, {steps} RK4 steps), {n_proc} process(es)"}
+            per = pool.starmap(_port_worker, [(workload, s) for s in sets])       # excluding atmosphere set-up
+    rays = sum(r[0] for r in per)
+    steps = sum(r[1] for r in per)
+    secs = max(r[2] for r in per)
+    # steady-state throughput of n_proc busy cores: sum of the per-process rates (dividing by the slowest process instead
+    # would charge the sample's residual imbalance -- a few dozen rays per process -- to the reference)
+    rate = sum(r[0] / r[2] for r in per if r[2] > 0)
+    step_rate = sum(r[1] / r[2] for r in per if r[2] > 0)
+    return {"rays": rays, "steps": steps, "seconds": secs, "rate": rate, "step_rate": step_rate, "kind": kind, "cores": n_proc,
+            "steps_per_ray": steps / max(1, rays),
+            "sample": f"every {stride}th ray of {workload}, theta-stratified ({rays} of {total} rays, {steps} RK4 steps, "
+                      f"{steps / max(1, rays):.0f} steps/ray), {n_proc} process(es), sum of per-process rates"}
 
 
 def _port_worker(workload, idx):
@@ -254,16 +281,15 @@ def run_reference_arm(args):
         if i >= args.warmup:
             per_step.append(res)
     secs = sum(r["seconds"] for r in per_step)
-    rays = sum(r["rays"] for r in per_step)
-    steps = sum(r["steps"] for r in per_step)
-    val = rays / secs
-    line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "rk4_steps_per_sec": steps / secs,
+    val = float(np.mean([r["rate"] for r in per_step]))
+    step_rate = float(np.mean([r["step_rate"] for r in per_step]))
+    line = {"impl": "reference", "metric": "rays/sec", "value": val, "unit": "rays/s", "rk4_steps_per_sec": step_rate,
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
             "higher_is_better": True, "scaling": "strong" if args.workload in SHARDED else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic launch-angle grid; " + ("ToyAtmo.met profile" if WORKLOADS[args.workload][3] == "toy" else "synthetic G2S atmosphere (SURVEY 8d)"),
             "config": {"workload": DESCRIPTIONS[args.workload], "sample": res["sample"]},
             "cpu_baseline": {"value": val, "unit": "rays/s", "cores": res["cores"], "kind": res["kind"], "sample": res["sample"],
-                             "rk4_steps_per_sec": steps / secs},
+                             "rk4_steps_per_sec": step_rate, "steps_per_ray": res["steps_per_ray"]},
             "e2e": {"value": val, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -296,6 +322,9 @@ def run_ours(args):
     tr, p = setup_tracer(args.workload, local)
     if args.bounces >= 0:
         p.bounces = args.bounces
+        tr.params = p
+    if args.ray_limit > 0:
+        p.ray_limit = args.ray_limit
         tr.params = p
     n_rec = p.bounces + 1
     n_slots = n * n_rec
@@ -414,8 +443,19 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             rngdep = variant in (V3DRD, VGLOBALRD)
             cb = cpu_reference_run(args.workload, target_rays=(8 if rngdep else 120), n_proc=1)
-            line["cpu_baseline"] = {"value": cb["rays"] / cb["seconds"], "unit": "rays/s", "cores": 1, "kind": cb["kind"],
-                                    "sample": cb["sample"], "rk4_steps_per_sec": cb["steps"] / cb["seconds"]}
+            grid_spr = total_steps / max(1, n)
+            line["cpu_baseline"] = {"value": cb["rate"], "unit": "rays/s", "cores": 1, "kind": cb["kind"],
+                                    "sample": cb["sample"], "rk4_steps_per_sec": cb["step_rate"],
+                                    "steps_per_ray": cb["steps_per_ray"], "workload_steps_per_ray": grid_spr,
+                                    # the sample's rays/s rescaled to the workload's mean ray length (they agree within a few per cent
+                                    # when the sample is representative; the stratified sample makes it so)
+                                    "value_at_workload_steps_per_ray": cb["step_rate"] / grid_spr if grid_spr > 0 else None}
+            if not rngdep:
+                sh = cpu_reference_run(args.workload, target_rays=60, n_proc=1, as_shipped=True)
+                if sh is not None:
+                    line["cpu_baseline_as_shipped"] = {"value": sh["rate"], "unit": "rays/s", "cores": 1, "kind": sh["kind"],
+                                                       "sample": sh["sample"] + "; g++ -O0 as the reference's makefile builds it",
+                                                       "rk4_steps_per_sec": sh["step_rate"], "steps_per_ray": sh["steps_per_ray"]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -433,6 +473,7 @@ def main():
     ap.add_argument("--e2e-full", action="store_true", help="warm the end-to-end leg up even on the long workloads")
     ap.add_argument("--rays-cap", type=int, default=0, help="profiling aid: keep only the first N rays of the workload")
     ap.add_argument("--bounces", type=int, default=-1, help="profiling aid: override the workload's bounce count")
+    ap.add_argument("--ray-limit", type=float, default=0.0, help="profiling aid: override ray_limit (RK4 step limit per segment = 100 x ray_limit)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

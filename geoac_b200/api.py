@@ -64,6 +64,7 @@ def lib():
         L.geoac_eigenray_direct.argtypes = [C.c_void_p, C.POINTER(abi.GeoacEigOpts), C.c_int, _dp, _dp, _dp, C.POINTER(C.c_int64)]
         L.geoac_get_variant.argtypes = [C.c_void_p]
         L.geoac_source_state.argtypes = [C.c_void_p, _dp]
+        L.geoac_set_knob.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.geoac_measure_fp64_peak.restype = C.c_double
         L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _LIB = L
@@ -75,6 +76,7 @@ EXPORTED_SYMBOLS = [
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
     "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_eigenray_direct", "geoac_get_variant", "geoac_source_state",
+    "geoac_set_knob",
 ]
 
 
@@ -154,12 +156,21 @@ class Tracer:
         if rc != abi.GEOAC_OK:
             raise GeoAcError(f"{what} failed ({rc}): {lib().geoac_last_error(self._h).decode()}")
 
+    def set_knob(self, name, value):
+        """Tuning / experiment knob of this context (include/geoac_b200.h: geoac_set_knob)."""
+        self._check(lib().geoac_set_knob(self._h, name.encode(), int(value)), f"geoac_set_knob({name})")
+
     def set_atmosphere_1d(self, z, T, u, v, rho):
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (z, T, u, v, rho)]
+        if any(a.ndim != 1 or a.shape != arrs[0].shape for a in arrs):
+            raise GeoAcError("set_atmosphere_1d: z, T, u, v, rho must be 1-D arrays of one length")
         self._check(lib().geoac_set_atmosphere_1d(self._h, len(arrs[0]), *[_p(a) for a in arrs]), "geoac_set_atmosphere_1d")
 
     def set_atmosphere_3d(self, ax0, ax1, axz, T, u, v, rho):
         arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, axz, T, u, v, rho)]
+        nodes = len(arrs[0]) * len(arrs[1]) * len(arrs[2])
+        if any(a.ndim != 1 for a in arrs[:3]) or any(a.size != nodes for a in arrs[3:]):
+            raise GeoAcError(f"set_atmosphere_3d: fields must hold n0*n1*nz = {nodes} values ([n0][n1][nz], z fastest)")
         self._check(lib().geoac_set_atmosphere_3d(self._h, len(arrs[0]), len(arrs[1]), len(arrs[2]), *[_p(a) for a in arrs]),
                     "geoac_set_atmosphere_3d")
 
@@ -187,6 +198,8 @@ class Tracer:
         o = abi.GeoacEigOpts()
         lib().geoac_default_eig_opts(C.byref(o))
         for k, v in opts.items():
+            if not hasattr(o, k):
+                raise TypeError(f"unknown eigenray option {k}")
             setattr(o, k, v)
         rc = np.ascontiguousarray(receivers, dtype=np.float64).reshape(-1, 2)
         est = np.ascontiguousarray(estimates, dtype=np.float64).reshape(-1, 3)
@@ -224,9 +237,16 @@ class Tracer:
         phi = np.ascontiguousarray(phi, dtype=np.float64)
         n = len(theta)
         n_rec = self.params.bounces + 1
+        if phi.shape != theta.shape or theta.ndim != 1:
+            raise GeoAcError("trace: theta and phi must be 1-D arrays of one length")
         if out is None:
             out = {"rec": np.empty((abi.NFIELDS, n, n_rec)), "status": np.empty((n, n_rec), dtype=np.int32),
                    "n_steps": np.empty((n, n_rec), dtype=np.int32)}
+        else:
+            for k, dt, size in (("rec", np.float64, abi.NFIELDS * n * n_rec), ("status", np.int32, n * n_rec), ("n_steps", np.int32, n * n_rec)):
+                a = out[k]
+                if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"] and a.size == size):
+                    raise GeoAcError(f"trace: out['{k}'] must be a writeable C-contiguous {np.dtype(dt).name} array of {size} elements")
         self._check(lib().geoac_trace(self._h, n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip),
                                       out["n_steps"].ctypes.data_as(_ip)), "geoac_trace")
         return out

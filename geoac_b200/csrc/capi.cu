@@ -29,8 +29,33 @@ using namespace geoac;
 
 static thread_local std::string g_create_error;
 
+// Experiment / test knobs.  Defaults come from the GEOAC_B200_* environment variables, read ONCE in
+// geoac_create; afterwards only geoac_set_knob changes them -- nothing on the launch path touches the environment.
+struct Knobs {
+    int lpt = 1;            // claim order: 0 natural, 1 automatic, 2 always
+    int packet = -1;        // whole-warp refill for the stratified sets: -1 automatic, 0 / 1 forced
+    int scout_coarse = 0;   // step-size multiple of the cost scout (0 = default per variant)
+    int stable = 1;         // (cost, inclination, index) order for the stratified sets
+    int cost_shift = 2;     // log2 coarsening of the cost key
+    int coop = 1;           // cooperative (several lanes per ray) modes of the range-dependent sets
+    int sbpoly = 1;         // absorption through per-interval polynomials
+    int block3d = 384;      // lanes per SM of Eq3D<true>
+    int host_tables = 0;    // build the node tables on the host
+};
+static int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
+static Knobs knobs_from_env() {
+    Knobs k;
+    k.lpt = env_int("GEOAC_B200_LPT", k.lpt); k.packet = env_int("GEOAC_B200_PACKET", k.packet);
+    k.scout_coarse = std::max(0, env_int("GEOAC_B200_SCOUT_COARSE", 0)); k.stable = env_int("GEOAC_B200_STABLE", k.stable);
+    k.cost_shift = std::min(7, std::max(0, env_int("GEOAC_B200_COSTSHIFT", k.cost_shift))); k.coop = env_int("GEOAC_B200_COOP", k.coop);
+    k.sbpoly = env_int("GEOAC_B200_SBPOLY", k.sbpoly); k.block3d = env_int("GEOAC_B200_BLOCK", k.block3d);
+    k.host_tables = env_int("GEOAC_B200_HOST_TABLES", k.host_tables);
+    return k;
+}
+
 struct geoac_ctx {
     int variant = 0, device = 0, sm_count = 0;
+    Knobs knobs;
     geoac_params prm{};
     std::string err;
     // 1-D table
@@ -101,6 +126,7 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
     if (prop.major != 10) return bail(GEOAC_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", kernels are built for sm_100a only");
     geoac_ctx* ctx = new geoac_ctx();
     ctx->variant = variant; ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    ctx->knobs = knobs_from_env();
     geoac_default_params(variant, &ctx->prm);
     cudaSetDevice(device);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
@@ -132,6 +158,18 @@ extern "C" int geoac_set_params(geoac_ctx* ctx, const geoac_params* p) {
     if (!ctx || !p) return GEOAC_ERR_BAD_ARG;
     if (p->bounces < 0 || p->ds_min <= 0.0 || p->ray_limit <= 0.0) return fail(ctx, GEOAC_ERR_BAD_ARG, "bad params");
     ctx->prm = *p; ctx->consts_dirty = true; ctx->src_set = true; return GEOAC_OK;
+}
+
+extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
+    if (!ctx || !name) return GEOAC_ERR_BAD_ARG;
+    Knobs& k = ctx->knobs;
+    const std::string n(name);
+    if (n == "lpt") k.lpt = value; else if (n == "packet") k.packet = value; else if (n == "scout_coarse") k.scout_coarse = std::max(0, value);
+    else if (n == "stable") k.stable = value; else if (n == "cost_shift") k.cost_shift = std::min(7, std::max(0, value));
+    else if (n == "coop") k.coop = value; else if (n == "sbpoly") k.sbpoly = value; else if (n == "block3d") k.block3d = value;
+    else if (n == "host_tables") k.host_tables = value;
+    else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
+    return GEOAC_OK;
 }
 
 // ---- knot slopes of the natural spline: same tridiagonal recurrences as G2S_Spline1D.cpp:161-196 ----
@@ -181,11 +219,19 @@ extern "C" int geoac_set_atmosphere_1d(geoac_ctx* ctx, int n, const double* z, c
         natural_slopes(x, col.data(), slo.data());
         for (int i = 0; i < n; i++) { tb[(size_t)i * TAB_NARR + slots[f]] = col[i]; tb[(size_t)i * TAB_NARR + slots[f] + 1] = slo[i]; }
     }
-    cudaFree(ctx->d_table); ctx->d_table = nullptr;
-    cudaFree(ctx->d_sbpoly); ctx->d_sbpoly = nullptr;
-    CK(cudaMalloc(&ctx->d_sbpoly, (size_t)(n - 1) * SBP_STRIDE * sizeof(double)));
-    CK(cudaMalloc(&ctx->d_table, ctx->h_table.size() * sizeof(double)));
-    CK(cudaMemcpy(ctx->d_table, tb, ctx->h_table.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // build into fresh buffers and swap them in only after every step succeeded: a failed call leaves the previous
+    // atmosphere (or "none") fully intact instead of dangling pointers
+    double *nt = nullptr, *ns = nullptr;
+    if (cudaMalloc(&ns, (size_t)(n - 1) * SBP_STRIDE * sizeof(double)) != cudaSuccess
+        || cudaMalloc(&nt, ctx->h_table.size() * sizeof(double)) != cudaSuccess
+        || cudaMemcpy(nt, tb, ctx->h_table.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) {
+        const std::string m = cudaGetErrorString(cudaGetLastError());
+        cudaFree(nt); cudaFree(ns);
+        return fail(ctx, GEOAC_ERR_CUDA, "geoac_set_atmosphere_1d: " + m);
+    }
+    cudaStreamSynchronize(ctx->stream);                                          // no launch may still read the old tables
+    cudaFree(ctx->d_table); cudaFree(ctx->d_sbpoly);
+    ctx->d_table = nt; ctx->d_sbpoly = ns;
     ctx->n = n; ctx->xmin = x[0]; ctx->xmax = x[n - 1];
     // GeoAc_SetPropRegion: G2S_Spline1D.cpp:22-28 / G2S_GlobalSpline1D.cpp:22-30
     ctx->prm.vert_limit = ctx->xmax;
@@ -285,24 +331,29 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     const bool glob = ctx->variant == GEOAC_GLOBAL_RNGDEP;
     std::vector<double> z(nz);
     for (int k = 0; k < nz; k++) z[k] = axz[k] + (glob ? kREarth : 0.0);                     // r_vals[nr] += r_earth
-    cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax); ctx->d_tuv = ctx->d_rho = ctx->d_ax = nullptr;
-    CK(cudaMalloc(&ctx->d_tuv, nodes * MS_STRIDE * sizeof(double)));
-    CK(cudaMalloc(&ctx->d_rho, nodes * 2 * sizeof(double)));
+    // build into fresh buffers and swap them in only after every step succeeded (a failed call -- e.g. out of memory on a
+    // config-5-size grid -- leaves the previous atmosphere, or "none", fully intact)
+    double *n_tuv = nullptr, *n_rho = nullptr, *n_ax = nullptr, *d_f = nullptr, *d_aux = nullptr;
+    auto bail = [&](const std::string& what) {
+        const std::string m = cudaGetErrorString(cudaGetLastError());
+        cudaFree(n_tuv); cudaFree(n_rho); cudaFree(n_ax); cudaFree(d_f); cudaFree(d_aux);
+        return fail(ctx, GEOAC_ERR_CUDA, "geoac_set_atmosphere_3d: " + what + ": " + m);
+    };
+    if (cudaMalloc(&n_tuv, nodes * MS_STRIDE * sizeof(double)) != cudaSuccess) return bail("node tables");
+    if (cudaMalloc(&n_rho, nodes * 2 * sizeof(double)) != cudaSuccess) return bail("density table");
     std::vector<double> r0, r1, rz;
     build_axis_records(ax0, n0, r0); build_axis_records(ax1, n1, r1); build_axis_records(z.data(), nz, rz);
-    CK(cudaMalloc(&ctx->d_ax, (size_t)(n0 + n1 + nz) * AX * sizeof(double)));
-    const char* host_env = std::getenv("GEOAC_B200_HOST_TABLES");          // tests: build the tables on the host instead
-    if (host_env && std::atoi(host_env) != 0) {
+    if (cudaMalloc(&n_ax, (size_t)(n0 + n1 + nz) * AX * sizeof(double)) != cudaSuccess) return bail("axis records");
+    if (ctx->knobs.host_tables) {                                          // tests: build the tables on the host instead
         std::vector<double> zz, tuv, rh;
         build_grid_tables(glob, n0, n1, nz, ax0, ax1, axz, T, u, v, rho, zz, tuv, rh);
-        CK(cudaMemcpy(ctx->d_tuv, tuv.data(), tuv.size() * sizeof(double), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(ctx->d_rho, rh.data(), rh.size() * sizeof(double), cudaMemcpyHostToDevice));
+        if (cudaMemcpy(n_tuv, tuv.data(), tuv.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess
+            || cudaMemcpy(n_rho, rh.data(), rh.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail("table upload");
     } else {
         // raw fields + axis-only coefficients up, slopes and node differences built in HBM
         std::vector<double> aux; build_zaux(z, aux);
-        double *d_f = nullptr, *d_aux = nullptr;
-        CK(cudaMalloc(&d_f, nodes * 4 * sizeof(double)));
-        if (cudaMalloc(&d_aux, (aux.size() + n0 + n1) * sizeof(double)) != cudaSuccess) { cudaFree(d_f); return fail(ctx, GEOAC_ERR_CUDA, "table build: out of device memory"); }
+        if (cudaMalloc(&d_f, nodes * 4 * sizeof(double)) != cudaSuccess) return bail("raw fields");
+        if (cudaMalloc(&d_aux, (aux.size() + n0 + n1) * sizeof(double)) != cudaSuccess) return bail("axis coefficients");
         const double* src[4] = { T, u, v, rho };
         cudaError_t e = cudaSuccess;
         for (int F = 0; F < 4 && e == cudaSuccess; F++) e = cudaMemcpy(d_f + (size_t)F * nodes, src[F], nodes * sizeof(double), cudaMemcpyHostToDevice);
@@ -313,16 +364,19 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
             ZAux za; za.A = d_aux; za.DEN = d_aux + nz; za.NC = d_aux + 2 * (size_t)nz; za.P2LO = d_aux + 3 * (size_t)nz; za.P2HI = d_aux + 4 * (size_t)nz;
             const long long nthreads = (long long)n0 * n1 * 10;
             grid_tables_kernel<<<(unsigned)((nthreads + 127) / 128), 128, 0, ctx->stream>>>(glob ? 1 : 0, n0, n1, nz, d_aux + aux.size(), d_aux + aux.size() + n0, za,
-                                                                                           d_f, d_f + nodes, d_f + 2 * nodes, d_f + 3 * nodes, ctx->d_tuv, ctx->d_rho);
+                                                                                           d_f, d_f + nodes, d_f + 2 * nodes, d_f + 3 * nodes, n_tuv, n_rho);
             e = cudaGetLastError();
             if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
         }
-        cudaFree(d_f); cudaFree(d_aux);
-        if (e != cudaSuccess) { ctx->err = std::string("table build: ") + cudaGetErrorString(e); return GEOAC_ERR_CUDA; }
+        if (e != cudaSuccess) return bail("table build");
+        cudaFree(d_f); cudaFree(d_aux); d_f = d_aux = nullptr;
     }
-    CK(cudaMemcpy(ctx->d_ax, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ax + (size_t)n0 * AX, r1.data(), r1.size() * sizeof(double), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ax + (size_t)(n0 + n1) * AX, rz.data(), rz.size() * sizeof(double), cudaMemcpyHostToDevice));
+    if (cudaMemcpy(n_ax, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess
+        || cudaMemcpy(n_ax + (size_t)n0 * AX, r1.data(), r1.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess
+        || cudaMemcpy(n_ax + (size_t)(n0 + n1) * AX, rz.data(), rz.size() * sizeof(double), cudaMemcpyHostToDevice) != cudaSuccess) return bail("axis upload");
+    cudaStreamSynchronize(ctx->stream);                                          // no launch may still read the old tables
+    cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
+    ctx->d_tuv = n_tuv; ctx->d_rho = n_rho; ctx->d_ax = n_ax;
     Grid3D& g = ctx->grid;
     g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + (size_t)n0 * AX; g.axz = ctx->d_ax + (size_t)(n0 + n1) * AX;
     g.n0 = n0; g.n1 = n1; g.nz = nz; g.scratch = nullptr; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
@@ -436,12 +490,11 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     }
     a.prev = ctx->d_prev;
     a.order = nullptr; a.n_claims = a.n_rays; a.n_long = nullptr; a.counter_long = ctx->d_counters + 4;
-    { const char* pe = std::getenv("GEOAC_B200_PACKET"); a.packet_refill = pe ? std::atoi(pe) : 0; }   // experiments only
+    a.packet_refill = ctx->knobs.packet > 0 ? 1 : 0;
     ctx->last_launches = 0;
     // longest-predicted-ray-first claim order, when a lane will process more than one ray (see trace_kernel.cuh)
     // GEOAC_B200_LPT: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
-    const char* lpt_env = std::getenv("GEOAC_B200_LPT");
-    const int lpt_mode = lpt_env ? std::atoi(lpt_env) : 1;
+    const int lpt_mode = ctx->knobs.lpt;
     if ((lpt_mode == 2 || (lpt_mode == 1 && a.n_rays > (int64_t)grid * BLOCK)) && a.n_rays < ((int64_t)1 << 32)) {
         constexpr int group = PacketMode<EQ>::value ? 32 : 1;
         const int64_t n_entries = ((a.n_rays + group - 1) / group) * group;
@@ -469,15 +522,13 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             const int64_t s_need = (a.n_rays + kScoutBlock - 1) / kScoutBlock;
             const int sblocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * std::max(1, s_per_sm), s_need);
             unsigned long long* scounter = ctx->d_counters + 3;
-            const char* ce = std::getenv("GEOAC_B200_SCOUT_COARSE");        // experiments: step-size multiple of the scout
-            int coarse = ce ? std::max(1, std::atoi(ce)) : (kGrid ? kScoutCoarse : 2 * kScoutCoarse);   // stratified: 32x measured best (404.8 vs 421.0 / 443.3 ms at 16x / 64x)
+            int coarse = ctx->knobs.scout_coarse > 0 ? ctx->knobs.scout_coarse : (kGrid ? kScoutCoarse : 2 * kScoutCoarse);   // stratified: 32x measured best (404.8 vs 421.0 / 443.3 ms at 16x / 64x)
             void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
         }
         // stratified sets: order by (cost bucket, inclination, batch index) + whole-warp refill, so that a warp's lanes read
         // the same few table records (trace_kernel.cuh); GEOAC_B200_STABLE=0 keeps the plain counting sort (A/B measurements)
-        static const int stable_env = [] { const char* e = std::getenv("GEOAC_B200_STABLE"); return e ? std::atoi(e) : 1; }();
-        if (!PacketMode<EQ>::value && stable_env) {
+        if (!PacketMode<EQ>::value && ctx->knobs.stable) {
             const int nblk = ctx->sm_count;
             const int64_t n = a.n_rays, chunk = (n + nblk - 1) / nblk;
             if (!ctx->d_blockhist) CK(cudaMalloc(&ctx->d_blockhist, sizeof(uint32_t) * (size_t)nblk * kCostBuckets + 2 * sizeof(double)));
@@ -489,7 +540,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             double* trange = reinterpret_cast<double*>(ctx->d_blockhist + (size_t)nblk * kCostBuckets);
             uint8_t *key_t = ctx->d_keys, *key_c = ctx->d_keys + n;
             order_theta_range_kernel<<<1, 1024, 0, st>>>(a.theta, n, trange);
-            static const int cost_shift = [] { const char* e = std::getenv("GEOAC_B200_COSTSHIFT"); return e ? std::min(7, std::max(0, std::atoi(e))) : 2; }();
+            const int cost_shift = ctx->knobs.cost_shift;
             order_keys_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_c, cost_shift);
             stable_hist_kernel<<<nblk, 256, 0, st>>>(key_t, nullptr, n, chunk, ctx->d_blockhist);
             stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
@@ -498,7 +549,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
             stable_scatter_kernel<<<nblk, 32, 0, st>>>(key_c, ctx->d_order2, n, chunk, ctx->d_blockhist, ctx->d_order);
             ctx->last_launches += 8;
-            if (!std::getenv("GEOAC_B200_PACKET")) a.packet_refill = 1;
+            if (ctx->knobs.packet < 0) a.packet_refill = 1;
         } else {
             order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long);
             order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
@@ -507,8 +558,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         }
         CK(cudaGetLastError());
         a.n_claims = n_entries;
-        static const bool coop_off = [] { const char* e = std::getenv("GEOAC_B200_COOP"); return e && std::atoi(e) == 0; }();
-        a.n_long = (PacketMode<EQ>::value && !coop_off) ? n_long : nullptr;
+        a.n_long = (PacketMode<EQ>::value && ctx->knobs.coop) ? n_long : nullptr;
         a.order = ctx->d_order;
         ctx->last_launches += 1;                                        // the cost scout
     }
@@ -539,10 +589,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     TraceArgs a;
     a.grid = ctx->grid;
     a.table = ctx->d_table; a.table_n = ctx->n; a.table_xmin = ctx->xmin; a.table_xmax = ctx->xmax;
-    {   // GEOAC_B200_SBPOLY=0: evaluate the absorption model in full at every step (A/B measurements, tests)
-        const char* e = std::getenv("GEOAC_B200_SBPOLY");
-        a.sbpoly = (ctx->is_grid || (e && std::atoi(e) == 0)) ? nullptr : ctx->d_sbpoly;
-    }
+    a.sbpoly = (ctx->is_grid || !ctx->knobs.sbpoly) ? nullptr : ctx->d_sbpoly;   // knob sbpoly = 0: the full absorption model at every step (A/B measurements, tests)
     a.consts = ctx->d_consts; a.theta = d_theta; a.phi = d_phi; a.n_rays = n_rays; a.n_rec = n_rec;
     a.rec = d_rec; a.status = d_status; a.n_steps = d_n_steps;
     a.counter = ctx->d_counters; a.total_steps = ctx->d_counters + 1; a.warp_trips = ctx->d_counters + 2;
@@ -563,8 +610,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
         case GEOAC_3D: {
             if (!amp) return launch_trace<Eq3D<false>, 512>(ctx, a, st);
             // tuning knob for experiments (lanes per SM vs registers per lane); the default is the measured best
-            const char* e = std::getenv("GEOAC_B200_BLOCK");
-            const int blk = e ? std::atoi(e) : 384;
+            const int blk = ctx->knobs.block3d;
             if (blk == 256) return launch_trace<Eq3D<true>, 256>(ctx, a, st);
             if (blk == 512) return launch_trace<Eq3D<true>, 512>(ctx, a, st);
             return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 158 registers, no spills: 420 ms per config-2 pass vs 491 (256) / 494 (512); 416 / 448 lanes compile to 128 registers with spills

@@ -97,7 +97,15 @@ typedef struct geoac_params {
 
 typedef struct geoac_ctx geoac_ctx;
 
-/* Create a context for `variant` on CUDA device `device` (ordinal). Fails (NULL, *status set) without sm_100. */
+/* Create a context for `variant` on CUDA device `device` (ordinal). Fails (NULL, *status set) without sm_100.
+ *
+ * Concurrency contract: a context owns per-launch scratch (claim counters, claim order, per-launch invariants, the
+ * y_{k-1} history) that every trace reuses, so AT MOST ONE trace may be in flight per context, on ONE stream at a time:
+ * calls on one context are serialised by the caller (the reference itself is single-threaded and non-reentrant,
+ * Code/GeoAc/GeoAc.Parameters.h globals), and after geoac_trace_device the caller must synchronise the stream it passed
+ * before the next call on that context (any entry point, geoac_set_params included).  Different contexts are
+ * independent and may be driven from different host threads -- one context per device is how a front end uses
+ * several GPUs (geoac_trace_multi below does exactly that). */
 geoac_ctx* geoac_create(int variant, int device, int* status);
 void       geoac_destroy(geoac_ctx* ctx);
 const char* geoac_last_error(const geoac_ctx* ctx);     /* ctx may be NULL: last create() error    */
@@ -249,6 +257,12 @@ int geoac_selftest_math(geoac_ctx* ctx, int n_per_thread, double* max_rel_err);
  * G2S_GlobalMultiDimSpline3D.cpp:313-431); geoac_set_atmosphere_3d builds them ON THE DEVICE (one thread per column and
  * quantity), and the parity tests compare them bit for bit with the reference's recurrences. cap_* in doubles. */
 int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t cap_rho, double* rho);
+
+/* Tuning / experiment knobs of a context.  Their defaults are read from the GEOAC_B200_* environment
+ * variables ONCE, in geoac_create; nothing on the launch path reads the environment.  Names: "lpt" (claim order: 0 natural,
+ * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables".
+ * No knob changes a record bit except "sbpoly" (absorption sum to 1e-11) -- that is what the tests use them to prove. */
+int geoac_set_knob(geoac_ctx* ctx, const char* name, int value);
 
 /* FP64 DFMA micro-benchmark on ctx's device: returns measured TFLOP/s (2 flops per DFMA) -- the roofline denominator. */
 double geoac_measure_fp64_peak(geoac_ctx* ctx, double* out_ms);

@@ -114,15 +114,15 @@ def test_batch_order_independence_and_determinism():
 
 def test_longest_ray_first_schedule_is_result_neutral(monkeypatch):
     """The cost scout + counting sort only change the order in which lanes claim rays: records must be bitwise identical
-    with the schedule forced on (GEOAC_B200_LPT=2) and off (=0), for a stratified and a range-dependent variant."""
+    with the schedule forced on (knob lpt = 2) and off (=0), for a stratified and a range-dependent variant."""
     for case in ("3d_sub", "globalrngdep_sub"):
         d, kv = util.load_case(case)
         variant = int(d["variant"])
         th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
         outs = []
         for mode in ("0", "2"):
-            monkeypatch.setenv("GEOAC_B200_LPT", mode)
             tr = _tracer_for(variant, kv, d)
+            tr.set_knob("lpt", int(mode))
             outs.append(tr.trace(th, ph))
             assert tr.last_kernel_launches() == (1 if mode == "0" else (5 if util.is_rngdep(variant) else 10))
         assert np.array_equal(outs[0]["status"], outs[1]["status"]) and np.array_equal(outs[0]["n_steps"], outs[1]["n_steps"])

@@ -40,8 +40,8 @@ def test_config2_full_grid_properties(monkeypatch):
     occ = tr.last_lane_occupancy()
     b = tr.trace(th, ph)
     assert _checksum(a) == _checksum(b)
-    monkeypatch.setenv("GEOAC_B200_LPT", "0")
     tr2, _ = bench.setup_tracer("config2", 0)
+    tr2.set_knob("lpt", 0)
     c = tr2.trace(th, ph)
     assert tr2.last_kernel_launches() == 1 and _checksum(a) == _checksum(c)
     assert occ > 0.93                                                   # the scheduling pass keeps the warps full
@@ -67,9 +67,9 @@ def test_rngdep_scale_run_is_schedule_independent(monkeypatch):
     _, _, _, th, ph = bench.workload_angles("config4s")
     th, ph = th[::3].copy(), ph[::3].copy()
     tr, p = bench.setup_tracer("config4s", 0)
-    monkeypatch.setenv("GEOAC_B200_LPT", "2")
+    tr.set_knob("lpt", 2)
     a = tr.trace(th, ph)
-    monkeypatch.setenv("GEOAC_B200_LPT", "0")
+    tr.set_knob("lpt", 0)
     b = tr.trace(th, ph)
     assert _checksum(a) == _checksum(b)
     assert (a["status"][:, 0] != abi.ST_NONE).all() and (a["status"] == abi.ST_ARRIVAL).sum() > 1000
@@ -137,7 +137,7 @@ def test_device_built_node_tables_match_set_slopes_multi(glob, monkeypatch):
     """geoac_set_atmosphere_3d builds the node tables on the device (one thread per column and quantity).  They must be
     bit for bit what Set_Slopes_Multi yields (G2S_MultiDimSpline3D.cpp:306-425 / G2S_GlobalMultiDimSpline3D.cpp:313-431,
     restated by the oracle, incl. the Global file's dfdt[i]-dfdt[i+1] slip) and what the host builder of the same library
-    yields (GEOAC_B200_HOST_TABLES=1), on a non-uniform vertical axis so that every spacing-dependent term differs."""
+    yields (knob host_tables = 1), on a non-uniform vertical axis so that every spacing-dependent term differs."""
     from oracle import pyoracle as po          # checker only
     from geoac_b200 import synth
     n0, n1, nz = 9, 11, 57
@@ -155,8 +155,8 @@ def test_device_built_node_tables_match_set_slopes_multi(glob, monkeypatch):
             assert np.array_equal(tuv[..., 6 * F + w].view(np.uint64), ref[F, w].view(np.uint64)), (F, w)
     assert np.array_equal(rh[..., 0].view(np.uint64), ref[3, 0].view(np.uint64))
     assert np.array_equal(rh[..., 1].view(np.uint64), ref[3, 1].view(np.uint64))
-    monkeypatch.setenv("GEOAC_B200_HOST_TABLES", "1")
     th = g.Tracer(variant, 0)
+    th.set_knob("host_tables", 1)
     th.set_atmosphere_3d(ax0, ax1, axz, T, u, v, rho)
     tuv_h, rh_h = th.grid_tables(n0, n1, nz)
     assert np.array_equal(tuv.view(np.uint64), tuv_h.view(np.uint64)) and np.array_equal(rh.view(np.uint64), rh_h.view(np.uint64))
@@ -166,16 +166,16 @@ def test_device_built_node_tables_match_set_slopes_multi(glob, monkeypatch):
 def test_absorption_polynomials_match_the_full_model(workload, monkeypatch):
     """The stratified kernels take the Sutherland-Bass coefficient from per-interval polynomials of its smooth factors
     (core.cuh: sb_alpha_1d; the cancellation staircase of the classical term stays literal).  Against the full model
-    evaluated at every step (GEOAC_B200_SBPOLY=0) the accumulated absorption must agree to 1e-11 and every other output must
+    evaluated at every step (knob sbpoly = 0) the accumulated absorption must agree to 1e-11 and every other output must
     be bit-identical -- on ToyAtmo (no interval flagged) and on the config-3 profile (a few intervals fall back to the full
     model because the piecewise-linear temperature kinks inside them)."""
     _, _, _, th, ph = bench.workload_angles(workload)
     step = max(1, len(th) // 3000)
     th, ph = th[::step].copy(), ph[::step].copy()
     tr, p = bench.setup_tracer(workload, 0)
-    monkeypatch.setenv("GEOAC_B200_SBPOLY", "1")
+    tr.set_knob("sbpoly", 1)
     a = tr.trace(th, ph)
-    monkeypatch.setenv("GEOAC_B200_SBPOLY", "0")
+    tr.set_knob("sbpoly", 0)
     b = tr.trace(th, ph)
     assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["n_steps"], b["n_steps"])
     m = a["status"] == abi.ST_ARRIVAL
@@ -190,9 +190,9 @@ def test_absorption_polynomials_match_the_full_model(workload, monkeypatch):
     q = tr.params
     q.freq = 2.5
     tr.params = q
-    monkeypatch.setenv("GEOAC_B200_SBPOLY", "1")
+    tr.set_knob("sbpoly", 1)
     c = tr.trace(th[:200], ph[:200])
-    monkeypatch.setenv("GEOAC_B200_SBPOLY", "0")
+    tr.set_knob("sbpoly", 0)
     d = tr.trace(th[:200], ph[:200])
     mm = c["status"] == abi.ST_ARRIVAL
     rel = np.abs(c["rec"][abi.F_ATTEN][mm] - d["rec"][abi.F_ATTEN][mm]) / np.abs(d["rec"][abi.F_ATTEN][mm])
