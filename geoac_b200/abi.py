@@ -8,8 +8,8 @@ VARIANT_NAMES = {GEOAC_2D: "2d", GEOAC_3D: "3d", GEOAC_GLOBAL: "global",
 GEOAC_OK, GEOAC_ERR_NO_DEVICE, GEOAC_ERR_BAD_ARG, GEOAC_ERR_NO_ATMO, GEOAC_ERR_CUDA, GEOAC_ERR_TOO_LARGE, GEOAC_ERR_IO = range(7)
 
 F_STATE0 = 0
-F_TRAVELTIME, F_ATTEN, F_TURNHEIGHT, F_AMPLITUDE, F_INCLINATION, F_BACKAZ, F_AUX, F_MARGIN = range(18, 26)
-NFIELDS = 26
+F_TRAVELTIME, F_ATTEN, F_TURNHEIGHT, F_AMPLITUDE, F_INCLINATION, F_BACKAZ, F_AUX, F_MARGIN, F_JACOBIAN, F_CAUSTICS = range(18, 28)
+NFIELDS = 28
 CAUSTIC_NF = 6         # doubles per caustic event row: state[0..2], travel time, bounce, step
 PATH_NF = 8            # doubles per raypath row (geoac_trace_paths): state[0..2], amplitude, absorption, travel time, bounce, step
 ST_NONE, ST_ARRIVAL, ST_BREAK, ST_LIMIT = range(4)

@@ -173,6 +173,10 @@ struct SegPos { const double* r0; double X, h, invh; };      // r0 = record of t
 // clamp without the NaN plumbing of fmin/fmax (one compare + select per bound)
 GEOAC_HD double clampd(double v, double lo, double hi) { v = (v > hi) ? hi : v; return (v < lo) ? lo : v; }
 
+// BREAK margin (GEOAC_F_MARGIN of a BREAK slot): fraction of the step a -> b that lay beyond a limit, from the excesses
+// e = value - limit (> 0 outside) at both ends; the smallest over the violated limits is kept
+GEOAC_HD double frac_beyond(double ea, double eb, double best) { return (eb > 0.0) ? fmin(best, eb / (eb - ea)) : best; }
+
 // locate the interval containing x, clamped into the table range like every reference look-up (G2S_Spline1D.cpp:335),
 // starting from cursor k.  Same tie-breaking as the reference's Find_Segment (G2S_Spline1D.cpp:202-243): a point on a
 // knot stays in the interval the cursor is already in.  Fast path: the query is still inside the cursor's interval

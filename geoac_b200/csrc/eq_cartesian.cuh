@@ -112,6 +112,10 @@ struct Eq3D {
         return (y[2] > L.vert_limit) || (r2 > L.range_limit * L.range_limit);      // sqrt(r2) > limit
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[2] < L.z_grnd; }
+    GEOAC_HD static double break_margin(const LaunchConsts& L, const RayC&, const double* ya, const double* yb) {
+        double m = frac_beyond(ya[2] - L.vert_limit, yb[2] - L.vert_limit, 2.0);
+        return frac_beyond(sqrt(ya[0] * ya[0] + ya[1] * ya[1]) - L.range_limit, sqrt(yb[0] * yb[0] + yb[1] * yb[1]) - L.range_limit, m);
+    }
 
     // one segment of GeoAc_TravelTime + GeoAc_SB_Atten, 3DStratified.cpp:348-405, 456-490 (shared midpoint sample)
     GEOAC_HD static void segment(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ya, const double* yb,
@@ -268,6 +272,9 @@ struct Eq2D {
         return (y[1] > L.vert_limit) || (y[0] > L.range_limit);
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[1] < L.z_grnd; }
+    GEOAC_HD static double break_margin(const LaunchConsts& L, const RayC&, const double* ya, const double* yb) {
+        return frac_beyond(ya[0] - L.range_limit, yb[0] - L.range_limit, frac_beyond(ya[1] - L.vert_limit, yb[1] - L.vert_limit, 2.0));
+    }
 
     // one segment of GeoAc_TravelTimeSegment + GeoAc_SB_AttenSegment, 2DStratified.cpp:235-286
     GEOAC_HD static void segment(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* ya, const double* yb,

@@ -140,6 +140,13 @@ struct EqGlobal {
         return far;
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[0] < L.ground; }
+    GEOAC_HD static double break_margin(const LaunchConsts& L, const RayC& rc, const double* ya, const double* yb) {
+        auto range = [&](const double* y) {
+            const double s1 = sin((y[1] - L.src[1]) * 0.5), s2 = sin((y[2] - L.src[2]) * 0.5);
+            return 2.0 * kREarth * asin(sqrt(s1 * s1 + rc.cos_lat_src * cos(y[1]) * (s2 * s2)));
+        };
+        return frac_beyond(range(ya) - L.range_limit, range(yb) - L.range_limit, frac_beyond(ya[0] - L.vert_limit, yb[0] - L.vert_limit, 2.0));
+    }
 
     // one segment of GeoAc_TravelTime + GeoAc_SB_Atten, Global.cpp:527-589, 634-670 (one shared midpoint sample;
     // the absorption path length uses sin(lat) where the travel time uses cos(lat): App. A-6)

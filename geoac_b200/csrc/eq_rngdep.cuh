@@ -117,6 +117,15 @@ struct Eq3DRD {
         return (y[0] > L.box_max[0]) || (y[0] < L.box_min[0]) || (y[1] > L.box_max[1]) || (y[1] < L.box_min[1]) || (y[2] > L.vert_limit);
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[2] < L.z_grnd; }
+    GEOAC_HD static double break_margin(const LaunchConsts& L, const RayC&, const double* ya, const double* yb) {
+        double m = frac_beyond(ya[2] - L.vert_limit, yb[2] - L.vert_limit, 2.0);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            m = frac_beyond(ya[i] - L.box_max[i], yb[i] - L.box_max[i], m);
+            m = frac_beyond(L.box_min[i] - ya[i], L.box_min[i] - yb[i], m);
+        }
+        return m;
+    }
 
     // one segment of GeoAc_TravelTime + GeoAc_SB_Atten, 3DRngDep.cpp:478-542, 597-635
     GEOAC_HD static void segment(const LaunchConsts& L, const Grid3D& G, const RayC&, const double* ya, const double* yb,
@@ -333,6 +342,15 @@ struct EqGlobalRD {
         return (y[0] > L.vert_limit) || (y[1] < L.box_min[0]) || (y[1] > L.box_max[0]) || (y[2] < L.box_min[1]) || (y[2] > L.box_max[1]);
     }
     GEOAC_HD static bool below_ground(const LaunchConsts& L, const double* y) { return y[0] < L.ground; }
+    GEOAC_HD static double break_margin(const LaunchConsts& L, const RayC&, const double* ya, const double* yb) {
+        double m = frac_beyond(ya[0] - L.vert_limit, yb[0] - L.vert_limit, 2.0);
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            m = frac_beyond(ya[1 + i] - L.box_max[i], yb[1 + i] - L.box_max[i], m);
+            m = frac_beyond(L.box_min[i] - ya[1 + i], L.box_min[i] - yb[1 + i], m);
+        }
+        return m;
+    }
 
     // one segment of GeoAc_TravelTime + GeoAc_SB_Atten (same arithmetic as Global.cpp:527-589, 634-670).  The absorption
     // model's reference state is sampled at (r = z_grnd -> lowest level, lat, lon) of the query point (App. A-14).

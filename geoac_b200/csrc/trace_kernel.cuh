@@ -108,6 +108,7 @@ struct LaneI {
     typename EQ::Cursor cur;
     int bounce, ksteps;
     int path_n, caus_n;     // raypath rows / caustic events emitted so far (PATHS kernels)
+    int caus_b;             // caustic events of the current bounce segment (GeoAc_CausticCnt)
     int64_t ray;
 };
 
@@ -119,7 +120,7 @@ template <class EQ> struct NeedsPrev { static constexpr bool value = !(EQ::VARIA
 
 template <class EQ>
 GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, const typename EQ::Atmo& T, int64_t idx, double theta, double phi) {
-    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.path_n = 0; n.caus_n = 0; n.cur = typename EQ::Cursor{};
+    n.ray = idx; n.bounce = 0; n.ksteps = 0; n.path_n = 0; n.caus_n = 0; n.caus_b = 0; n.cur = typename EQ::Cursor{};
     d.tt_total = d.att_total = d.tt_b = d.att_b = d.zmax = 0.0; d.D_prev = 0.0;
     EQ::init(L, T, theta, phi, d.rc, d.y, n.cur);
 }
@@ -133,6 +134,19 @@ GEOAC_HD void lane_start(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, cons
 #define GEOAC_STAGE_UNROLL 4
 #endif
 template <class EQ> struct WorkInMem { static constexpr bool value = std::is_same<typename EQ::Atmo, Grid3D>::value; };
+
+// Cooperative mode (several lanes advance ONE ray on its shared-memory record, every lane executing the same read-modify-write
+// of the record redundantly): the lanes of the group must not run ahead of each other between a read and the matching write.
+// They are in lock step by construction, but the CUDA memory model does not promise it, so the group synchronises around the
+// record updates.  No-op for one lane per ray.
+GEOAC_HD void group_sync(const Table1D&) {}
+GEOAC_HD void group_sync(const Grid3D& g) {
+#if defined(__CUDA_ARCH__)
+    if (g.nrole > 1) __syncwarp(g.gmask);
+#else
+    (void)g;
+#endif
+}
 
 // prev[i * pstride] holds y_{k-1}[i] (only maintained when NeedsPrev); work = 2 NEQ doubles (WorkInMem) or nullptr;
 // returns false when the ray has ended.  PATHS: also emit one raypath row every o.path_stride steps (WriteRays=True of the
@@ -156,10 +170,20 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
         EQ::rhs(L, T, d.rc, p, f, n.cur);
         const double dsa = ds * ((s == 2) ? 1.0 : 0.5);
         const double dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+        if (MEM) {                                             // the record is shared by the lanes of a cooperative group
+            double a_new[NEQ];
 #pragma unroll
-        for (int i = 0; i < NEQ; i++) {
-            acc[i] = fma(f[i], dsb, acc[i]);                   // y + k1/6 + k2/3 + k3/3 + k4/6, left to right (k_i = ds f_i)
-            p[i] = fma(f[i], dsa, y[i]);                       // y + k_i/2 (stage 4: y + k_3)
+            for (int i = 0; i < NEQ; i++) a_new[i] = fma(f[i], dsb, acc[i]);
+            group_sync(T);                                     // every lane has read acc / p (rhs) before any lane overwrites them
+#pragma unroll
+            for (int i = 0; i < NEQ; i++) { acc[i] = a_new[i]; p[i] = fma(f[i], dsa, y[i]); }
+            group_sync(T);
+        } else {
+#pragma unroll
+            for (int i = 0; i < NEQ; i++) {
+                acc[i] = fma(f[i], dsb, acc[i]);               // y + k1/6 + k2/3 + k3/3 + k4/6, left to right (k_i = ds f_i)
+                p[i] = fma(f[i], dsa, y[i]);                   // y + k_i/2 (stage 4: y + k_3)
+            }
         }
     }
     n.ksteps++;
@@ -183,7 +207,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
                         row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = d.tt_total;
                         row[4] = (double)n.bounce; row[5] = (double)n.ksteps;
                     }
-                    n.caus_n++;
+                    n.caus_n++; n.caus_b++;
                 }
                 d.D_prev = D;
             }
@@ -210,6 +234,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     if (!gnd) {
         o.status[slot] = brk ? GEOAC_ST_BREAK : GEOAC_ST_LIMIT;
         o.n_steps[slot] = brk ? n.ksteps : L.step_limit;
+        if (brk) o.rec[(int64_t)GEOAC_F_MARGIN * o.n_slots + slot] = EQ::break_margin(L, d.rc, y, acc);   // how marginal the break was
         if (PATHS) { if (o.path_rows) o.path_rows[n.ray] = n.path_n; if (o.caus_rows) o.caus_rows[n.ray] = n.caus_n; }
         return false;
     }
@@ -226,6 +251,8 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     o.rec[(int64_t)GEOAC_F_BACKAZ * o.n_slots + slot] = baz;
     o.rec[(int64_t)GEOAC_F_AUX * o.n_slots + slot] = aux;
     o.rec[(int64_t)GEOAC_F_MARGIN * o.n_slots + slot] = margin;
+    o.rec[(int64_t)GEOAC_F_JACOBIAN * o.n_slots + slot] = EQ::jacobian(L, T, d.rc, acc, n.cur);
+    o.rec[(int64_t)GEOAC_F_CAUSTICS * o.n_slots + slot] = (PATHS && o.caus_cap > 0) ? (double)n.caus_b : -1.0;
     o.status[slot] = GEOAC_ST_ARRIVAL;
     o.n_steps[slot] = n.ksteps;
     if (n.bounce >= L.bounces) {
@@ -238,7 +265,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     EQ::reflect(L, T, d.rc, ym2, y, acc, y0, n.cur);
 #pragma unroll
     for (int i = 0; i < NEQ; i++) y[i] = y0[i];
-    n.bounce++; n.ksteps = 0;
+    n.bounce++; n.ksteps = 0; n.caus_b = 0;
     if (L.per_bounce_zmax) d.zmax = 0.0;
     return true;
 }
@@ -387,6 +414,7 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             gi.bounce = __shfl_sync(0xffffffffu, li.bounce, owner); gi.ksteps = __shfl_sync(0xffffffffu, li.ksteps, owner);
             gi.ray = __shfl_sync(0xffffffffu, (long long)li.ray, owner);
             gi.path_n = __shfl_sync(0xffffffffu, li.path_n, owner); gi.caus_n = __shfl_sync(0xffffffffu, li.caus_n, owner);
+            gi.caus_b = PATHS ? __shfl_sync(0xffffffffu, li.caus_b, owner) : 0;
             const int othread = (int)(threadIdx.x & ~31u) + owner;
             double* const rec = lanes + (size_t)othread * LaneLayout<EQ>::STRIDE;
             double* const gwork = rec + LaneLayout<EQ>::WORK;
@@ -402,8 +430,9 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             const int bbo = __shfl_sync(0xffffffffu, gi.bounce, src), bks = __shfl_sync(0xffffffffu, gi.ksteps, src);
             const int bal = __shfl_sync(0xffffffffu, (int)alive, src);
             const int bpn = __shfl_sync(0xffffffffu, gi.path_n, src), bcn = __shfl_sync(0xffffffffu, gi.caus_n, src);
+            const int bcb = PATHS ? __shfl_sync(0xffffffffu, gi.caus_b, src) : 0;
             if (have_ray) {
-                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks; li.path_n = bpn; li.caus_n = bcn;
+                li.cur.ka = bka; li.cur.kb = bkb; li.cur.kz = bkz; li.bounce = bbo; li.ksteps = bks; li.path_n = bpn; li.caus_n = bcn; li.caus_b = bcb;
                 have_ray = bal != 0;
                 my_steps++;
             }

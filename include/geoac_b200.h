@@ -54,9 +54,15 @@ enum {
     GEOAC_F_INCLINATION= 22,   /* [deg] as printed by the variant's main (sign conventions App. A-16) */
     GEOAC_F_BACKAZ     = 23,   /* [deg] as printed by the variant's main; 0 for 2D                 */
     GEOAC_F_AUX        = 24,   /* Global variants: celerity [km/s]; otherwise 0                    */
-    GEOAC_F_MARGIN     = 25,   /* (z_k - z_grnd)/|z_k - z_{k-1}|  in (-1,0): how far into the last step the ground
-                                  was crossed; values within ~1e-9 of 0 or -1 flag near-threshold rays */
-    GEOAC_NFIELDS      = 26,
+    GEOAC_F_MARGIN     = 25,   /* ARRIVAL: (z_k - z_grnd)/|z_k - z_{k-1}| in (-1,0): how far into the last step the ground was
+                                  crossed.  BREAK: fraction in (0,1] of the last step that lay beyond the violated limit
+                                  (smallest over the limits violated).  Values within ~1e-6 of 0 / -1 / 1 flag rays whose step
+                                  count or outcome is within rounding of a branch threshold (geoac_b200/nearthreshold.py) */
+    GEOAC_F_JACOBIAN   = 26,   /* GeoAc_Jacobian(solution,k): the determinant D the amplitude divides by (0 if !calc_amp);
+                                  |D| small against its own terms = near a caustic, amplitude ill-conditioned */
+    GEOAC_F_CAUSTICS   = 27,   /* GeoAc_CausticCnt(solution,1,k): sign changes of D within this bounce segment, counted only by
+                                  geoac_trace_paths with caustic_cap > 0 (the plain trace does not evaluate D per step): else -1 */
+    GEOAC_NFIELDS      = 28,
     /* one raypath row (geoac_trace_paths): state[0..2], amplitude (linear), absorption sum, travel-time sum, bounce, step */
     GEOAC_PATH_NF      = 8,
     /* one caustic event: state[0..2] at the step where the Jacobian changed sign, travel-time sum, bounce, step */

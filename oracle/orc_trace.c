@@ -75,13 +75,14 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
         ray.theta = theta[iray]; ray.phi = phi[iray];
         e->init(&ray, sol[0]);
         double tt = 0.0, att = 0.0, zmax = 0.0;
-        int32_t prow = 0, crow = 0;
+        int32_t prow = 0, crow = 0, crow_b = 0;
         for (int b = 0; b < n_rec; b++) {
             int64_t slot = iray * n_rec + b;
             int left; int k = propagate_rk4(e, &ray, sol, step_limit, &left);
             total += k;
             if (seg_mode) {
                 double D = 0.0, D_prev = 0.0;
+                crow_b = 0;
                 if (caus_cap > 0) D_prev = e->jacobian(&ray, sol[1]);              /* Code/GeoAc3D_main.cpp:245 */
                 for (int m = 1; m < k; m++) {
                     if (caus_cap > 0) D = e->jacobian(&ray, sol[m]);
@@ -100,7 +101,7 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
                             double* row = caus + (iray * caus_cap + crow) * GEOAC_CAUSTIC_NF;
                             row[0] = sol[m][0]; row[1] = sol[m][1]; row[2] = sol[m][2]; row[3] = tt; row[4] = (double)b; row[5] = (double)m;
                         }
-                        crow++;
+                        crow++; crow_b++;
                     }
                     if (caus_cap > 0) D_prev = D;
                 }
@@ -123,6 +124,8 @@ int64_t orc_trace_paths(int variant, orc_atmo* atmo, const geoac_params* p, int6
             rec[(int64_t)GEOAC_F_ATTEN * n_slots + slot] = att;
             rec[(int64_t)GEOAC_F_TURNHEIGHT * n_slots + slot] = zmax;
             rec[(int64_t)GEOAC_F_AMPLITUDE * n_slots + slot] = p->calc_amp ? e->amplitude(&ray, sol[k]) : 0.0;
+            rec[(int64_t)GEOAC_F_JACOBIAN * n_slots + slot] = p->calc_amp ? e->jacobian(&ray, sol[k]) : 0.0;
+            rec[(int64_t)GEOAC_F_CAUSTICS * n_slots + slot] = (caus_cap > 0) ? (double)crow_b : -1.0;
             double incl, baz, aux, margin;
             e->finish(&ray, sol[k - 1], sol[k], tt, &incl, &baz, &aux, &margin);
             rec[(int64_t)GEOAC_F_INCLINATION * n_slots + slot] = incl;

@@ -189,7 +189,7 @@ def read_ref_bin(path):
     n, n_rec, nf, eq = int(raw[1]), int(raw[2]), int(raw[3]), int(raw[4])
     ang = raw[8: 8 + 2 * n].reshape(n, 2)
     recs = raw[8 + 2 * n:].reshape(n, n_rec, nf)
-    rec = np.ascontiguousarray(np.transpose(recs[:, :, : abi.NFIELDS], (2, 0, 1)))
+    rec = np.ascontiguousarray(np.transpose(recs[:, :, :26], (2, 0, 1)))         # fields 0..25 of include/geoac_b200.h
     return {"theta_deg": ang[:, 0].copy(), "phi_deg": ang[:, 1].copy(), "rec": rec,
             "status": recs[:, :, REF_F_STATUS].astype(np.int32), "n_steps": recs[:, :, REF_F_NSTEPS].astype(np.int32),
             "eq_cnt": eq, "total_steps": int(raw[5]), "t_rk4_s": raw[6], "t_post_s": raw[7]}

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import geoac_b200 as g
-from geoac_b200 import abi
+from geoac_b200 import abi, nearthreshold as nt
 from tests import util
 
 pytestmark = pytest.mark.gpu
@@ -23,9 +23,25 @@ def _tracer_for(variant, kv, case=None):
     return tr
 
 
-# near-grazing / near-caustic rays have |D| -> 0 and amplify rounding (up to 1.2e-8 for theta = 1 deg);
-# they are compared at a looser amplitude tolerance and LISTED in the test output rather than hidden
-AMP_RTOL = 1e-6
+# Amplitude, Jacobian and the auxiliary (launch-angle derivative) states are ill-conditioned near caustic-forming rays (their
+# condition number with respect to the launch angle reaches 1e9): such an entry may differ from the reference by more than
+# 1e-9 ONLY where a 1e-10 rad change of the launch angle moves it by more than a tenth of that difference, and is then
+# listed with |D| (geoac_b200/nearthreshold.py).  Everything else -- positions, eikonal, travel time, attenuation, turning
+# height, inclination, back azimuth, celerity -- is held to 1e-9 on every arrival, discrete outputs to equality.
+AMP_RTOL = 1e-6          # raypath rows only (amplitude sampled along the path passes through caustics)
+
+
+def _verdict(tr, variant, th, ph, out, want, label, capsys=None):
+    calc_amp = tr.params.calc_amp
+    cond = nt.conditioning(tr.trace, th, ph, out, variant, calc_amp)
+    tainted, _ = nt.margin_flags(out, variant, tr.params)
+    problems, listed, stats, n_disc = nt.check_against(out, want, variant, calc_amp, tainted, cond, rtol=util.RTOL, label=label)
+    if capsys is not None:
+        with capsys.disabled():
+            print(f"\n[{label}] max rel diff per field: " + ", ".join(f"{k}:{v:.1e}" for k, v in sorted(stats.items())))
+            for i, b, name, rel, resp, D in listed:
+                print(f"   listed: ray {i} bounce {b}: {name} differs {rel:.2e} (moves {resp:.2e} under a 1e-10 rad change of the launch angle; |D| = {D:.3e})")
+    return problems, listed, n_disc, tainted
 
 
 @pytest.mark.parametrize("name", util.golden_cases())
@@ -36,13 +52,9 @@ def test_cuda_matches_reference_golden(name, capsys):
     th, ph = util.angles_rad(d["theta_deg"], d["phi_deg"])
     out = tr.trace(th, ph)
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
-    problems, stats = util.compare_records(out, want, variant, tr.params.calc_amp, util.RTOL, name, amp_rtol=AMP_RTOL)
-    with capsys.disabled():
-        print(f"\n[{name}] max rel diff per field: " + ", ".join(f"{k}:{v:.1e}" for k, v in sorted(stats.items())))
-        tight, _ = util.compare_records(out, want, variant, tr.params.calc_amp, util.RTOL, name)
-        for t in tight:
-            print("   listed (auxiliary/amplitude beyond 1e-9, near-caustic amplification):", t)
+    problems, listed, n_disc, tainted = _verdict(tr, variant, th, ph, out, want, name, capsys)
     assert not problems, "\n".join(problems)
+    assert n_disc == 0 and not tainted.any()          # the golden sets hold no near-threshold ray: discrete outputs equal everywhere
 
 
 @pytest.mark.parametrize("name", util.path_cases())
@@ -62,26 +74,30 @@ def test_cuda_raypath_rows_match_reference(name):
     only_c = tr.trace_paths(th, ph, 0, 0, caustic_cap=32)               # events without raypath rows
     assert np.array_equal(only_c["caustic"], out["caustic"]) and np.array_equal(only_c["caustic_rows"], out["caustic_rows"])
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
-    rp, _ = util.compare_records(out, want, variant, tr.params.calc_amp, util.RTOL, name, amp_rtol=AMP_RTOL)
+    rp, _, _, _ = _verdict(tr, variant, th, ph, out, want, name)
     assert not (problems + rp), "\n".join((problems + rp)[:10])
     # a row capacity that is too small drops the surplus rows but still reports how many were produced
     small = tr.trace_paths(th, ph, int(kv["path_stride"]), 5)
     assert np.array_equal(small["path_rows"], want_rows) and np.array_equal(small["path"][:, :5], out["path"][:, :5])
 
 
-def test_cuda_matches_oracle_seeded(oracle):
+def test_cuda_matches_oracle_seeded(oracle, capsys):
+    """Freshly seeded launch angles, the three stratified variants on ToyAtmo (the range-dependent ones are seeded on the
+    full config-4 / config-5 grids in tests/test_gpu_scale_parity.py)."""
     rng = np.random.default_rng(20251018)
     n = 96
     theta_deg = rng.uniform(2.0, 55.0, n)
     phi_deg = rng.uniform(-180.0, 180.0, n)
     th, ph = util.angles_rad(theta_deg, phi_deg)
-    for variant in (abi.GEOAC_3D, abi.GEOAC_2D):
+    for variant in (abi.GEOAC_3D, abi.GEOAC_2D, abi.GEOAC_GLOBAL):
         tr = _tracer_for(variant, {"bounces": 1})
         out = tr.trace(th, ph)
-        at = oracle.atmo1d(False, *oracle.load_met_1d(util.TOY))
-        want = oracle.trace(variant, at, tr.params, th, ph)
-        problems, _ = util.compare_records(out, want, variant, 1, util.RTOL, f"variant {variant}", amp_rtol=AMP_RTOL)
+        glob = variant == abi.GEOAC_GLOBAL
+        at = oracle.atmo1d(glob, *oracle.load_met_1d(util.TOY, global_taper=glob))
+        want = util.oracle_trace_parallel(oracle, variant, at, tr.params, th, ph)
+        problems, listed, n_disc, tainted = _verdict(tr, variant, th, ph, out, want, f"seeded variant {variant}", capsys)
         assert not problems, "\n".join(problems)
+        assert n_disc == 0
 
 
 def test_edge_cases():

@@ -189,3 +189,29 @@ def compare_caustics(got, got_rows, want, want_rows, rtol, label=""):
         if nr and rel.max() > rtol:
             problems.append(f"{label}: ray {i}: caustic rows differ by {rel.max():.3e}")
     return problems
+
+
+# ---- the CPU oracle over all host cores (fork: the children share the atmosphere tables and never touch CUDA) ----
+_ORC = {}
+
+
+def _orc_chunk(sl):
+    po, variant, at, p, th, ph = _ORC["args"]
+    return sl, po.trace(variant, at, p, th[sl], ph[sl])
+
+
+def oracle_trace_parallel(po, variant, at, p, th, ph, chunk=8, max_procs=32):
+    """po.trace split over the host cores; `at` must have been built before the call (shared copy-on-write)."""
+    import multiprocessing as mp
+    n = len(th)
+    out = {"rec": np.zeros((abi.NFIELDS, n, p.bounces + 1)), "status": np.zeros((n, p.bounces + 1), dtype=np.int32),
+           "n_steps": np.zeros((n, p.bounces + 1), dtype=np.int32)}
+    if n == 0:
+        return out
+    _ORC["args"] = (po, variant, at, p, np.ascontiguousarray(th), np.ascontiguousarray(ph))
+    slices = [slice(i, min(n, i + chunk)) for i in range(0, n, chunk)]
+    nproc = max(1, min(len(os.sched_getaffinity(0)), max_procs, len(slices)))
+    with mp.get_context("fork").Pool(nproc) as pool:
+        for sl, o in pool.imap_unordered(_orc_chunk, slices):
+            out["rec"][:, sl] = o["rec"]; out["status"][sl] = o["status"]; out["n_steps"][sl] = o["n_steps"]
+    return out
