@@ -316,6 +316,10 @@ def run_ours(args):
     if sharded and world > 1:
         mine = shard_indices(len(th), rank, world)
         th, ph = np.ascontiguousarray(th[mine]), np.ascontiguousarray(ph[mine])
+    elif sharded and args.shard_of:                                      # development aid: rank R's share of a W-way split on ONE GPU
+        r_, w_ = (int(x) for x in args.shard_of.split("/"))
+        mine = shard_indices(len(th), r_, w_)
+        th, ph = np.ascontiguousarray(th[mine]), np.ascontiguousarray(ph[mine])
     if args.rays_cap > 0:
         th, ph = np.ascontiguousarray(th[: args.rays_cap]), np.ascontiguousarray(ph[: args.rays_cap])
     n = len(th)
@@ -392,15 +396,18 @@ def run_ours(args):
     out = {"rec": h_rec.numpy(), "status": h_status.numpy(), "n_steps": h_nsteps.numpy()}
     long_run = args.workload in ("config3", "config4", "config5") and not args.e2e_full
     e2e_k = 1 if long_run else max(1, min(args.steps, 3))
-    tr.reserve(n)                                                       # device staging allocated outside the timed region
-    if not long_run:
-        tr.trace(h_th.numpy(), h_ph.numpy(), out)                       # warm-up pass
+    if args.no_e2e:
+        e2e_k = 0
+    else:
+        tr.reserve(n)                                                   # device staging allocated outside the timed region
+        if not long_run:
+            tr.trace(h_th.numpy(), h_ph.numpy(), out)                   # warm-up pass
     barrier()
     e0 = time.perf_counter()
     for _ in range(e2e_k):
         tr.trace(h_th.numpy(), h_ph.numpy(), out)                       # synchronous: returns with results on the host
     barrier()
-    e2e_s = time.perf_counter() - e0
+    e2e_s = max(time.perf_counter() - e0, 1e-9)
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -408,6 +415,11 @@ def run_ours(args):
     h2d = 2 * n * 8
     d2h = abi.NFIELDS * n_slots * 8 + 2 * n_slots * 4 + 16
 
+    strong = None
+    if not args.no_strong and args.workload == "config2" and not args.rays_cap:
+        tr_keep = tr
+        strong = strong_scaling_record(world, rank, local, dev, barrier)
+        tr = tr_keep
     if rank == 0:
         peak_tf, peak_ms = tr.measure_fp64_peak()
         flops_step = ALGO_FLOPS_PER_STEP[variant]
@@ -440,6 +452,11 @@ def run_ours(args):
                                         "HBM is not the bound: ~0.03 B/step of record traffic"},
             "wall_s_timed_region": t_wall,
         }
+        if strong is not None:
+            strong["roofline_frac"] = strong["roofline_frac"] / peak_tf if peak_tf > 0 else None
+            line["strong"] = strong
+        if variant in (V3DRD, VGLOBALRD):
+            line["config"]["schedule"] = tr.last_schedule()
         if world == 1 and not args.no_cpu_baseline:
             rngdep = variant in (V3DRD, VGLOBALRD)
             cb = cpu_reference_run(args.workload, target_rays=(8 if rngdep else 120), n_proc=1)
@@ -462,6 +479,58 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def strong_scaling_record(world, rank, local, dev, barrier):
+    """Config 5 (the "1e6 rays sharded across 1/2/4/8 B200" configuration of BASELINE.json) in FULL, one timed pass, the ray list
+    split across the ranks in interleaved 4096-ray blocks (geoac_b200/sharding.py) -- carried in every bench line so that the
+    strong-scaling curve N = 1, 2, 4, 8 is in the driver's own record.  Device-resident angles, CUDA events, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from geoac_b200 import abi
+    _, _, _, th, ph = workload_angles("config5")
+    n_total = len(th)
+    if world > 1:
+        mine = shard_indices(n_total, rank, world)
+        th, ph = np.ascontiguousarray(th[mine]), np.ascontiguousarray(ph[mine])
+    n = len(th)
+    t0 = time.perf_counter()
+    tr, p = setup_tracer("config5", local)
+    setup_s = time.perf_counter() - t0
+    n_slots = n * (p.bounces + 1)
+    d_th, d_ph = torch.from_numpy(th).to(dev), torch.from_numpy(ph).to(dev)
+    d_rec = torch.empty((abi.NFIELDS, n_slots), dtype=torch.float64, device=dev)
+    d_status = torch.empty(n_slots, dtype=torch.int32, device=dev)
+    d_nsteps = torch.empty(n_slots, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    tr.trace_device(n, d_th.data_ptr(), d_ph.data_ptr(), d_rec.data_ptr(), d_status.data_ptr(), d_nsteps.data_ptr(), stream.cuda_stream)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    steps, _ = tr.last_stats()
+    occ = tr.last_lane_occupancy()
+    sched = tr.last_schedule()
+    arrivals = int((d_status == abi.ST_ARRIVAL).sum().item())
+    checksum = int(d_nsteps.to(torch.int64).sum().item())
+    t = torch.tensor([ms, float(steps), float(n), float(arrivals), float(checksum), occ], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tmin = t.clone(); dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
+        tsum = t.clone(); dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    else:
+        tmax = tmin = tsum = t
+    tr.close()
+    secs = tmax[0].item() * 1e-3
+    return {"workload": DESCRIPTIONS["config5"], "scaling": "strong", "n_gpus": world, "passes": 1, "ms": tmax[0].item(), "ms_fastest_rank": tmin[0].item(),
+            "rays": int(tsum[2].item()), "rays_per_sec": tsum[2].item() / secs, "rk4_steps": int(tsum[1].item()), "rk4_steps_per_sec": tsum[1].item() / secs,
+            "arrival_records": int(tsum[3].item()), "n_steps_checksum": int(tsum[4].item()),
+            "lane_occupancy_min_rank": tmin[5].item(), "setup_s_rank0": setup_s,
+            "schedule_rank0": sched,
+            "roofline_frac": ALGO_FLOPS_PER_STEP[VGLOBALRD] * tsum[1].item() / secs / 1e12 / max(1, world),   # divided by the measured peak below
+            "note": "whole-job time = slowest rank; one ray list split across ranks, atmosphere replicated, no collective on the data path"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -473,6 +542,9 @@ def main():
     ap.add_argument("--e2e-full", action="store_true", help="warm the end-to-end leg up even on the long workloads")
     ap.add_argument("--rays-cap", type=int, default=0, help="profiling aid: keep only the first N rays of the workload")
     ap.add_argument("--bounces", type=int, default=-1, help="profiling aid: override the workload's bounce count")
+    ap.add_argument("--shard-of", default="", help="development aid: 'R/W' traces rank R's share of a W-way split of a sharded workload on one GPU")
+    ap.add_argument("--no-e2e", action="store_true", help="development aid: skip the end-to-end leg")
+    ap.add_argument("--no-strong", action="store_true", help="skip the config-5 strong-scaling sub-record")
     ap.add_argument("--ray-limit", type=float, default=0.0, help="profiling aid: override ray_limit (RK4 step limit per segment = 100 x ray_limit)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -65,6 +65,13 @@ def lib():
         L.geoac_get_variant.argtypes = [C.c_void_p]
         L.geoac_source_state.argtypes = [C.c_void_p, _dp]
         L.geoac_set_knob.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.geoac_last_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        _cp = C.POINTER(C.c_void_p)
+        L.geoac_create_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, _cp, C.POINTER(C.c_int)]
+        L.geoac_multi_set_atmosphere_1d.argtypes = [_cp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
+        L.geoac_multi_set_atmosphere_3d.argtypes = [_cp, C.c_int, C.c_int, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.geoac_multi_set_params.argtypes = [_cp, C.c_int, C.POINTER(GeoacParams)]
+        L.geoac_trace_multi.argtypes = [_cp, C.c_int, C.c_int64, _dp, _dp, _dp, _ip, _ip]
         L.geoac_measure_fp64_peak.restype = C.c_double
         L.geoac_measure_fp64_peak.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         _LIB = L
@@ -76,7 +83,8 @@ EXPORTED_SYMBOLS = [
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
     "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_eigenray_direct", "geoac_get_variant", "geoac_source_state",
-    "geoac_set_knob",
+    "geoac_set_knob", "geoac_last_schedule",
+    "geoac_create_multi", "geoac_multi_set_atmosphere_1d", "geoac_multi_set_atmosphere_3d", "geoac_multi_set_params", "geoac_trace_multi",
 ]
 
 
@@ -295,6 +303,12 @@ class Tracer:
         self._check(lib().geoac_last_trace_counters(self._h, None, C.byref(k)), "geoac_last_trace_counters")
         return k.value
 
+    def last_schedule(self):
+        """Scheduling facts of the last trace: packet grouping, long-region packets, exclusive long-region CTAs, kernels."""
+        o = (C.c_int64 * 4)()
+        self._check(lib().geoac_last_schedule(self._h, o), "geoac_last_schedule")
+        return {"rd_group": o[0], "long_packets": o[1], "long_ctas": o[2], "launches": o[3]}
+
     def selftest_math(self, n_per_thread=2000):
         """Max relative error of the kernel's rcp / rsqrt / sqrt / exp / exp10 against the CUDA math library."""
         out = np.zeros(7)
@@ -304,3 +318,73 @@ class Tracer:
     def measure_fp64_peak(self):
         ms = C.c_double(0)
         return lib().geoac_measure_fp64_peak(self._h, C.byref(ms)), ms.value
+
+
+def trace_multi(tracers, theta, phi, out=None):
+    """geoac_trace_multi over existing contexts (one per device; same variant / atmosphere / parameters on each): the batch is
+    dealt to them in interleaved GEOAC_SHARD_BLOCK-ray blocks by host threads INSIDE the library and merged by ray index.
+    Bitwise identical to tracing the batch on one context."""
+    theta = np.ascontiguousarray(theta, dtype=np.float64)
+    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    if phi.shape != theta.shape or theta.ndim != 1:
+        raise GeoAcError("trace_multi: theta and phi must be 1-D arrays of one length")
+    n = len(theta)
+    n_rec = tracers[0].params.bounces + 1
+    if out is None:
+        out = {"rec": np.empty((abi.NFIELDS, n, n_rec)), "status": np.empty((n, n_rec), dtype=np.int32),
+               "n_steps": np.empty((n, n_rec), dtype=np.int32)}
+    handles = (C.c_void_p * len(tracers))(*[t._h for t in tracers])
+    rc = lib().geoac_trace_multi(handles, len(tracers), n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip),
+                                 out["n_steps"].ctypes.data_as(_ip))
+    if rc != abi.GEOAC_OK:
+        raise GeoAcError(f"geoac_trace_multi failed ({rc}): {lib().geoac_last_error(tracers[0]._h).decode()}")
+    return out
+
+
+class MultiTracer:
+    """One context per device behind one object (geoac_create_multi + the geoac_multi_* helpers + geoac_trace_multi)."""
+
+    def __init__(self, variant, devices):
+        devices = list(devices)
+        ids = (C.c_int * len(devices))(*devices)
+        hs = (C.c_void_p * len(devices))()
+        st = C.c_int(0)
+        rc = lib().geoac_create_multi(variant, ids, len(devices), hs, C.byref(st))
+        if rc != abi.GEOAC_OK:
+            raise GeoAcError(f"geoac_create_multi failed ({st.value}): {lib().geoac_last_error(None).decode()}")
+        self.tracers = []
+        for h, d in zip(hs, devices):
+            t = Tracer.__new__(Tracer)
+            t._h, t.variant, t.device = h, variant, d
+            self.tracers.append(t)
+        self._hs = hs
+        self.variant = variant
+
+    def _check(self, rc, what):
+        if rc != abi.GEOAC_OK:
+            raise GeoAcError(f"{what} failed ({rc}): {lib().geoac_last_error(self.tracers[0]._h).decode()}")
+
+    def set_atmosphere_1d(self, z, T, u, v, rho):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (z, T, u, v, rho)]
+        self._check(lib().geoac_multi_set_atmosphere_1d(self._hs, len(self.tracers), len(arrs[0]), *[_p(a) for a in arrs]), "geoac_multi_set_atmosphere_1d")
+
+    def set_atmosphere_3d(self, ax0, ax1, axz, T, u, v, rho):
+        arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (ax0, ax1, axz, T, u, v, rho)]
+        self._check(lib().geoac_multi_set_atmosphere_3d(self._hs, len(self.tracers), len(arrs[0]), len(arrs[1]), len(arrs[2]), *[_p(a) for a in arrs]),
+                    "geoac_multi_set_atmosphere_3d")
+
+    @property
+    def params(self):
+        return self.tracers[0].params
+
+    @params.setter
+    def params(self, p):
+        self._check(lib().geoac_multi_set_params(self._hs, len(self.tracers), C.byref(p)), "geoac_multi_set_params")
+
+    def trace(self, theta, phi, out=None):
+        return trace_multi(self.tracers, theta, phi, out)
+
+    def close(self):
+        for t in self.tracers:
+            t.close()
+        self.tracers = []

@@ -41,6 +41,11 @@ struct Knobs {
     int sbpoly = 1;         // absorption through per-interval polynomials
     int block3d = 384;      // lanes per SM of Eq3D<true>
     int host_tables = 0;    // build the node tables on the host
+    int rd_group = -1;      // range-dependent packets: 0 = 32 consecutive rays (inclination neighbours), 1 = equal inclination / neighbouring azimuth, -1 = automatic
+    int long_alpha = 100;   // a packet is LONG if its cost exceeds long_alpha % of the average work of a lane
+    int long_width = 8;     // long-region CTAs: 8 = cooperative kernel (four lanes per ray, cell cache in shared memory), 32 = one thread per ray
+    int long_sm_pct = 50;   // at most this share of the SMs is given to the long-region launch
+    int exclusive = 1;      // long-region launch keeps its SMs to itself (0: one launch, long packets first)
 };
 static int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
 static Knobs knobs_from_env() {
@@ -50,6 +55,9 @@ static Knobs knobs_from_env() {
     k.cost_shift = std::min(7, std::max(0, env_int("GEOAC_B200_COSTSHIFT", k.cost_shift))); k.coop = env_int("GEOAC_B200_COOP", k.coop);
     k.sbpoly = env_int("GEOAC_B200_SBPOLY", k.sbpoly); k.block3d = env_int("GEOAC_B200_BLOCK", k.block3d);
     k.host_tables = env_int("GEOAC_B200_HOST_TABLES", k.host_tables);
+    k.rd_group = env_int("GEOAC_B200_RD_GROUP", k.rd_group); k.long_alpha = std::max(1, env_int("GEOAC_B200_LONG_ALPHA", k.long_alpha));
+    k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 32 ? 32 : 8;
+    k.long_sm_pct = std::min(90, std::max(1, env_int("GEOAC_B200_LONG_SM_PCT", k.long_sm_pct))); k.exclusive = env_int("GEOAC_B200_EXCLUSIVE", k.exclusive);
     return k;
 }
 
@@ -80,11 +88,15 @@ struct geoac_ctx {
     double *d_theta = nullptr, *d_phi = nullptr, *d_rec = nullptr;
     int32_t *d_status = nullptr, *d_nsteps = nullptr;
     int64_t cap_rays = 0, cap_slots = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream = nullptr, stream_long = nullptr;      // stream_long: the concurrent long-region launch of the range-dependent sets
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    double grid_dh = 0.0, grid_dz = 0.0;                       // median node spacing [km] of the range-dependent grid (packet grouping heuristic)
+    int last_long_packets = 0, last_long_ctas = 0, last_rd_group = 0;
     int64_t last_steps = 0; double last_ms = 0.0;
     bool consts_dirty = true;
     bool src_set = false;
+    // pinned host staging of geoac_trace_multi (this context's share of the batch: angles in, records out)
+    struct Pin { void* p = nullptr; size_t cap = 0; } pin_theta, pin_phi, pin_rec, pin_status, pin_nsteps;
 };
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
@@ -129,8 +141,12 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
     ctx->knobs = knobs_from_env();
     geoac_default_params(variant, &ctx->prm);
     cudaSetDevice(device);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     bool ok = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess
+           && cudaStreamCreateWithPriority(&ctx->stream_long, cudaStreamNonBlocking, prio_hi) == cudaSuccess
            && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess
+           && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess
            && cudaMalloc(&ctx->d_consts, sizeof(LaunchConsts)) == cudaSuccess
            && cudaMalloc(&ctx->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); delete ctx; return bail(GEOAC_ERR_CUDA, "context allocation failed: " + m); }
@@ -145,8 +161,12 @@ extern "C" void geoac_destroy(geoac_ctx* ctx) {
     cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_blockhist); cudaFree(ctx->d_order2); cudaFree(ctx->d_keys); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows); cudaFree(ctx->d_caus); cudaFree(ctx->d_caus_rows);
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
+    cudaFreeHost(ctx->pin_theta.p); cudaFreeHost(ctx->pin_phi.p); cudaFreeHost(ctx->pin_rec.p); cudaFreeHost(ctx->pin_status.p); cudaFreeHost(ctx->pin_nsteps.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+    if (ctx->stream_long) cudaStreamDestroy(ctx->stream_long);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -168,6 +188,9 @@ extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
     else if (n == "stable") k.stable = value; else if (n == "cost_shift") k.cost_shift = std::min(7, std::max(0, value));
     else if (n == "coop") k.coop = value; else if (n == "sbpoly") k.sbpoly = value; else if (n == "block3d") k.block3d = value;
     else if (n == "host_tables") k.host_tables = value;
+    else if (n == "rd_group") k.rd_group = value; else if (n == "long_alpha") k.long_alpha = std::max(1, value);
+    else if (n == "long_width") k.long_width = (value == 32) ? 32 : 8; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
+    else if (n == "exclusive") k.exclusive = value;
     else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
     return GEOAC_OK;
 }
@@ -381,6 +404,8 @@ extern "C" int geoac_set_atmosphere_3d(geoac_ctx* ctx, int n0, int n1, int nz, c
     g.tuv = ctx->d_tuv; g.rho = ctx->d_rho; g.ax0 = ctx->d_ax; g.ax1 = ctx->d_ax + (size_t)n0 * AX; g.axz = ctx->d_ax + (size_t)(n0 + n1) * AX;
     g.n0 = n0; g.n1 = n1; g.nz = nz; g.scratch = nullptr; g.role = 0; g.nrole = 1; g.glane0 = 0; g.gmask = 0;
     g.amin = ax0[0]; g.amax = ax0[n0 - 1]; g.bmin = ax1[0]; g.bmax = ax1[n1 - 1]; g.zmin = z[0]; g.zmax = z[nz - 1];
+    ctx->grid_dh = 0.5 * ((ax0[n0 - 1] - ax0[0]) / (n0 - 1) + (ax1[n1 - 1] - ax1[0]) / (n1 - 1)) * (glob ? kREarth : 1.0);   // mean node spacing [km]
+    ctx->grid_dz = (z[nz - 1] - z[0]) / (nz - 1);
     // GeoAc_SetPropRegion: G2S_MultiDimSpline3D.cpp:22-33 / G2S_GlobalMultiDimSpline3D.cpp:22-33
     ctx->prm.vert_limit = g.zmax;
     ctx->prm.box_min[0] = g.amin; ctx->prm.box_max[0] = g.amax; ctx->prm.box_min[1] = g.bmin; ctx->prm.box_max[1] = g.bmax;
@@ -489,11 +514,12 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         }
     }
     a.prev = ctx->d_prev;
-    a.order = nullptr; a.n_claims = a.n_rays; a.n_long = nullptr; a.counter_long = ctx->d_counters + 4;
+    a.order = nullptr; a.n_claims = a.n_rays; a.n_long_packets = 0; a.counter_long = ctx->d_counters + 4; a.prefer_long = 0; a.long_width = 32;
     a.packet_refill = ctx->knobs.packet > 0 ? 1 : 0;
-    ctx->last_launches = 0;
+    ctx->last_launches = 0; ctx->last_long_packets = 0; ctx->last_long_ctas = 0; ctx->last_rd_group = 0;
+    int grid_long = 0;
     // longest-predicted-ray-first claim order, when a lane will process more than one ray (see trace_kernel.cuh)
-    // GEOAC_B200_LPT: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
+    // knob lpt: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
     const int lpt_mode = ctx->knobs.lpt;
     if ((lpt_mode == 2 || (lpt_mode == 1 && a.n_rays > (int64_t)grid * BLOCK)) && a.n_rays < ((int64_t)1 << 32)) {
         constexpr int group = PacketMode<EQ>::value ? 32 : 1;
@@ -503,12 +529,13 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             CK(cudaMalloc(&ctx->d_cost, sizeof(uint32_t) * n_entries)); CK(cudaMalloc(&ctx->d_order, sizeof(uint32_t) * n_entries));
             ctx->cap_order = n_entries;
         }
-        // d_hist: [0..255] buckets, [256] largest cost, [257] number of long packets, [258..259] cost sum (64 bit)
-        if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 8)));
-        CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 8), st));
+        // d_hist: [0..255] buckets, [256] largest cost, [257] number of long packets, [258..259] cost sum (64 bit), [260..265] grid shape (3 doubles)
+        if (!ctx->d_hist) CK(cudaMalloc(&ctx->d_hist, sizeof(uint32_t) * (kCostBuckets + 16)));
+        CK(cudaMemsetAsync(ctx->d_hist, 0, sizeof(uint32_t) * (kCostBuckets + 16), st));
         uint32_t* cmax = ctx->d_hist + kCostBuckets;
         uint32_t* n_long = ctx->d_hist + kCostBuckets + 1;
         unsigned long long* cost_sum = reinterpret_cast<unsigned long long*>(ctx->d_hist + kCostBuckets + 2);
+        double* shape = reinterpret_cast<double*>(ctx->d_hist + kCostBuckets + 4);
         {   // cost scout: persistent, the table in shared memory when it fits
             using SEQ = typename EQ::Scout;
             constexpr int kScoutBlock = ScoutBlock<SEQ>::value;
@@ -526,44 +553,121 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
         }
-        // stratified sets: order by (cost bucket, inclination, batch index) + whole-warp refill, so that a warp's lanes read
-        // the same few table records (trace_kernel.cuh); GEOAC_B200_STABLE=0 keeps the plain counting sort (A/B measurements)
-        if (!PacketMode<EQ>::value && ctx->knobs.stable) {
+        // Range-dependent sets: which 32 rays make a packet (trace_kernel.cuh: grid_shape_kernel).  The choice only schedules.
+        bool by_theta = !PacketMode<EQ>::value;
+        if (PacketMode<EQ>::value) {
+            int mode = ctx->knobs.rd_group;
+            if (mode < 0) {
+                double h_shape[3] = { 0, 0, 0 };
+                grid_shape_kernel<<<1, 1024, 0, st>>>(a.theta, a.phi, a.n_rays, shape);
+                CK(cudaMemcpyAsync(h_shape, shape, sizeof h_shape, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                ctx->last_launches += 1;
+                // spread of a packet per km of path, in cells: 32 dtheta / dz (inclination neighbours) vs 32 dphi / dh (azimuth neighbours)
+                mode = (h_shape[1] > 0.0 && h_shape[0] > 0.0 && ctx->grid_dh > 0.0 && ctx->grid_dz > 0.0
+                        && h_shape[1] / ctx->grid_dh < h_shape[0] / ctx->grid_dz) ? 1 : 0;
+            }
+            by_theta = mode == 1;
+            ctx->last_rd_group = mode;
+        }
+        // order by (cost bucket, inclination, batch index) + whole-warp refill: a warp's lanes then read the same few table
+        // records (stratified sets: trace_kernel.cuh) / walk through the same grid cells (range-dependent sets with azimuth
+        // neighbours); knob stable = 0 keeps the plain counting sort for the stratified sets (A/B measurements)
+        if (by_theta && (PacketMode<EQ>::value || ctx->knobs.stable)) {
             const int nblk = ctx->sm_count;
             const int64_t n = a.n_rays, chunk = (n + nblk - 1) / nblk;
             if (!ctx->d_blockhist) CK(cudaMalloc(&ctx->d_blockhist, sizeof(uint32_t) * (size_t)nblk * kCostBuckets + 2 * sizeof(double)));
-            if (n > ctx->cap_keys) {
+            if (n_entries > ctx->cap_keys) {
                 cudaFree(ctx->d_keys); cudaFree(ctx->d_order2); ctx->d_keys = nullptr; ctx->d_order2 = nullptr; ctx->cap_keys = 0;
-                CK(cudaMalloc(&ctx->d_keys, (size_t)2 * n)); CK(cudaMalloc(&ctx->d_order2, sizeof(uint32_t) * n));
-                ctx->cap_keys = n;
+                CK(cudaMalloc(&ctx->d_keys, (size_t)3 * n_entries)); CK(cudaMalloc(&ctx->d_order2, sizeof(uint32_t) * n_entries));
+                ctx->cap_keys = n_entries;
             }
             double* trange = reinterpret_cast<double*>(ctx->d_blockhist + (size_t)nblk * kCostBuckets);
-            uint8_t *key_t = ctx->d_keys, *key_c = ctx->d_keys + n;
+            uint8_t *key_t = ctx->d_keys, *key_c = ctx->d_keys + n, *key_t2 = ctx->d_keys + 2 * n;
             order_theta_range_kernel<<<1, 1024, 0, st>>>(a.theta, n, trange);
             const int cost_shift = ctx->knobs.cost_shift;
-            order_keys_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_c, cost_shift);
-            stable_hist_kernel<<<nblk, 256, 0, st>>>(key_t, nullptr, n, chunk, ctx->d_blockhist);
-            stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
-            stable_scatter_kernel<<<nblk, 32, 0, st>>>(key_t, nullptr, n, chunk, ctx->d_blockhist, ctx->d_order2);
-            stable_hist_kernel<<<nblk, 256, 0, st>>>(key_c, ctx->d_order2, n, chunk, ctx->d_blockhist);
-            stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
-            stable_scatter_kernel<<<nblk, 32, 0, st>>>(key_c, ctx->d_order2, n, chunk, ctx->d_blockhist, ctx->d_order);
-            ctx->last_launches += 8;
-            if (ctx->knobs.packet < 0) a.packet_refill = 1;
+            auto pass = [&](const uint8_t* key, const uint32_t* src, uint32_t* dst) {
+                stable_hist_kernel<<<nblk, 256, 0, st>>>(key, src, n, chunk, ctx->d_blockhist);
+                stable_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_blockhist, nblk);
+                stable_scatter_kernel<<<nblk, 32, 0, st>>>(key, src, n, chunk, ctx->d_blockhist, dst);
+            };
+            if (PacketMode<EQ>::value) {           // 16-bit inclination key: a packet holds ONE inclination wherever a row of the grid is long enough
+                order_keys16_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_t2, key_c, cost_shift);
+                pass(key_t, nullptr, ctx->d_order);
+                pass(key_t2, ctx->d_order, ctx->d_order2);
+                pass(key_c, ctx->d_order2, ctx->d_order);
+                if (n_entries > n) CK(cudaMemsetAsync(ctx->d_order + n, 0xff, sizeof(uint32_t) * (n_entries - n), st));
+                packet_long_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_order, ctx->d_cost, n_entries / 32, n, cost_sum, (long long)grid * BLOCK, ctx->knobs.long_alpha, n_long);
+                ctx->last_launches += 12;
+            } else {
+                order_keys_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_c, cost_shift);
+                pass(key_t, nullptr, ctx->d_order2);
+                pass(key_c, ctx->d_order2, ctx->d_order);
+                ctx->last_launches += 8;
+                if (ctx->knobs.packet < 0) a.packet_refill = 1;
+            }
         } else {
-            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long);
+            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long, ctx->knobs.long_alpha);
             order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
             order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
             ctx->last_launches += 3;
         }
         CK(cudaGetLastError());
         a.n_claims = n_entries;
-        a.n_long = (PacketMode<EQ>::value && ctx->knobs.coop) ? n_long : nullptr;
         a.order = ctx->d_order;
         ctx->last_launches += 1;                                        // the cost scout
+        if (PacketMode<EQ>::value && ctx->knobs.coop) {
+            // the long region: packets that would outlast the pass on a fully loaded SM.  Their count sizes the second launch.
+            uint32_t h_long = 0;
+            CK(cudaMemcpyAsync(&h_long, n_long, sizeof h_long, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            a.n_long_packets = std::min<int64_t>(h_long, n_entries / 32);
+            ctx->last_long_packets = (int)a.n_long_packets;
+            if (a.n_long_packets > 0 && ctx->knobs.exclusive && !PATHS) {
+                const int64_t per_cta = (ctx->knobs.long_width == 8) ? kCoopSlots : BLOCK;      // rays a long-region CTA holds at a time
+                grid_long = (int)std::min<int64_t>((a.n_long_packets * 32 + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * ctx->knobs.long_sm_pct / 100);
+                grid_long = std::max(grid_long, 1);
+            }
+        }
+    }
+    a.long_width = 32;                                                  // one-thread-per-ray CTAs take whole packets
+    if (grid_long > 0) {
+        // Two concurrent launches.  The long region -- packets that would outlast the pass on a loaded SM -- goes to CTAs that
+        // keep their SM to themselves (their shared-memory request leaves no room for a main CTA), launched first on a
+        // high-priority stream; the main launch fills the other SMs, and its surplus CTAs start as SMs free up.  Each side
+        // drains its own region first and then helps with the other.  knob long_width = 8 (default): the cooperative kernel
+        // (four lanes per ray, the ray's cell in shared memory via TMA: trace_kernel.cuh); 32: the same one-thread-per-ray kernel.
+        const bool coop = ctx->knobs.long_width == 8;
+        const void* fn_long = fn; size_t smem_long = 0; int block_long = BLOCK; size_t lanes_long = (size_t)grid_long * BLOCK;
+        if constexpr (PacketMode<EQ>::value) {
+            if (coop) { fn_long = (const void*)trace_coop_kernel<EQ>; smem_long = CoopLayout<EQ>::bytes(); block_long = kCoopBlock; lanes_long = (size_t)grid_long * kCoopSlots; }
+        }
+        if (!smem_long) smem_long = std::min((size_t)max_optin, std::max(smem, (size_t)max_optin - smem + 4096));   // no room for a main CTA beside it
+        if (smem_long > (size_t)max_optin) return fail(ctx, GEOAC_ERR_CUDA, "cooperative kernel does not fit in shared memory");
+        CK(cudaFuncSetAttribute(fn_long, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long));
+        if (NeedsPrev<EQ>::value) {
+            const size_t need = (size_t)EQ::NEQ * ((size_t)grid * BLOCK + lanes_long) * sizeof(double);
+            if (need > ctx->cap_prev) {
+                CK(cudaStreamSynchronize(st));
+                cudaFree(ctx->d_prev); ctx->d_prev = nullptr; ctx->cap_prev = 0;
+                CK(cudaMalloc(&ctx->d_prev, need));
+                ctx->cap_prev = need;
+            }
+            a.prev = ctx->d_prev;
+        }
+        TraceArgs al = a;
+        al.prefer_long = 1;
+        if (NeedsPrev<EQ>::value) al.prev = ctx->d_prev + (size_t)EQ::NEQ * grid * BLOCK;
+        CK(cudaEventRecord(ctx->ev_fork, st));
+        CK(cudaStreamWaitEvent(ctx->stream_long, ctx->ev_fork, 0));
+        void* largs[] = { (void*)&al };
+        CK(cudaLaunchKernel(fn_long, dim3(grid_long), dim3(block_long), largs, smem_long, ctx->stream_long));
+        CK(cudaEventRecord(ctx->ev_join, ctx->stream_long));
+        ctx->last_launches += 1; ctx->last_long_ctas = grid_long;
     }
     void* args[] = { (void*)&a };
     CK(cudaLaunchKernel(fn, dim3(grid), dim3(BLOCK), args, smem, st));
+    if (grid_long > 0) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     ctx->last_launches += 1;
     return GEOAC_OK;
 }
@@ -737,6 +841,120 @@ extern "C" int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* t
     if (path_stride < 0 || caustic_cap < 0 || (path_stride == 0 && caustic_cap == 0))
         return ctx ? fail(ctx, GEOAC_ERR_BAD_ARG, "ask for raypath rows (path_stride > 0) and / or caustic events (caustic_cap > 0)") : GEOAC_ERR_BAD_ARG;
     return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, path_stride, path_cap, path, path_rows, caustic_cap, caustic, caustic_rows);
+}
+
+// Scheduling facts of the last trace (range-dependent sets): out[0] packet grouping used (0 = consecutive rays, 1 = equal
+// inclination / neighbouring azimuth), out[1] packets in the long region, out[2] CTAs of the exclusive long-region launch,
+// out[3] kernels enqueued.
+extern "C" int geoac_last_schedule(geoac_ctx* ctx, int64_t* out4) {
+    if (!ctx || !out4) return GEOAC_ERR_BAD_ARG;
+    out4[0] = ctx->last_rd_group; out4[1] = ctx->last_long_packets; out4[2] = ctx->last_long_ctas; out4[3] = ctx->last_launches;
+    return GEOAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Several devices behind one call.  Rays are independent, so the flattened launch-angle list (the mains'
+// phi-major, theta-minor order, Code/GeoAc3D_main.cpp:226-227) is dealt to the contexts in interleaved blocks of
+// GEOAC_SHARD_BLOCK rays -- lifetimes vary smoothly with theta, so interleaving balances the load -- one host thread per
+// context gathers its share into that context's PINNED staging, traces it (geoac_trace: H2D, kernels, D2H) and puts the
+// records back at the rays' places in the caller's arrays.  No collective, no exchange between devices; the merged result
+// is bitwise what one context yields (tests/test_gpu_parity.py).
+// ---------------------------------------------------------------------------------------------------------------
+static int pin_grow(geoac_ctx* ctx, geoac_ctx::Pin& b, size_t need) {
+    if (need <= b.cap) return GEOAC_OK;
+    cudaFreeHost(b.p); b.p = nullptr; b.cap = 0;
+    CK(cudaHostAlloc(&b.p, need, cudaHostAllocDefault));
+    b.cap = need;
+    return GEOAC_OK;
+}
+
+extern "C" int geoac_create_multi(int variant, const int* device_ids, int n_devices, geoac_ctx** ctxs, int* status) {
+    if (!device_ids || !ctxs || n_devices < 1) { if (status) *status = GEOAC_ERR_BAD_ARG; g_create_error = "geoac_create_multi: need device ordinals and room for the contexts"; return GEOAC_ERR_BAD_ARG; }
+    for (int i = 0; i < n_devices; i++) {
+        int st = GEOAC_OK;
+        ctxs[i] = geoac_create(variant, device_ids[i], &st);
+        if (!ctxs[i]) {
+            for (int j = 0; j < i; j++) { geoac_destroy(ctxs[j]); ctxs[j] = nullptr; }
+            if (status) *status = st;
+            return st;
+        }
+    }
+    if (status) *status = GEOAC_OK;
+    return GEOAC_OK;
+}
+
+template <class F>
+static int for_each_ctx(geoac_ctx* const* ctxs, int n_ctx, F f) {          // one host thread per context; first failure wins
+    if (!ctxs || n_ctx < 1) return GEOAC_ERR_BAD_ARG;
+    for (int i = 0; i < n_ctx; i++) if (!ctxs[i]) return GEOAC_ERR_BAD_ARG;
+    std::vector<int> rc((size_t)n_ctx, GEOAC_OK);
+    std::vector<std::thread> pool;
+    for (int i = 1; i < n_ctx; i++) pool.emplace_back([&, i] { rc[(size_t)i] = f(ctxs[i], i); });
+    rc[0] = f(ctxs[0], 0);
+    for (auto& t : pool) t.join();
+    for (int i = 0; i < n_ctx; i++) if (rc[(size_t)i] != GEOAC_OK) { if (i) ctxs[0]->err = "context " + std::to_string(i) + ": " + ctxs[i]->err; return rc[(size_t)i]; }
+    return GEOAC_OK;
+}
+
+extern "C" int geoac_multi_set_atmosphere_1d(geoac_ctx* const* ctxs, int n_ctx, int n, const double* z, const double* T,
+                                             const double* u, const double* v, const double* rho) {
+    return for_each_ctx(ctxs, n_ctx, [&](geoac_ctx* c, int) { return geoac_set_atmosphere_1d(c, n, z, T, u, v, rho); });
+}
+extern "C" int geoac_multi_set_atmosphere_3d(geoac_ctx* const* ctxs, int n_ctx, int n0, int n1, int nz, const double* ax0, const double* ax1,
+                                             const double* axz, const double* T, const double* u, const double* v, const double* rho) {
+    return for_each_ctx(ctxs, n_ctx, [&](geoac_ctx* c, int) { return geoac_set_atmosphere_3d(c, n0, n1, nz, ax0, ax1, axz, T, u, v, rho); });
+}
+extern "C" int geoac_multi_set_params(geoac_ctx* const* ctxs, int n_ctx, const geoac_params* p) {
+    return for_each_ctx(ctxs, n_ctx, [&](geoac_ctx* c, int) { return geoac_set_params(c, p); });
+}
+
+static int trace_host(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                      double* rec, int32_t* status, int32_t* n_steps, int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
+                      int64_t caus_cap, double* caus, int32_t* caus_rows);
+
+extern "C" int geoac_trace_multi(geoac_ctx* const* ctxs, int n_ctx, int64_t n_rays, const double* theta, const double* phi,
+                                 double* rec, int32_t* status, int32_t* n_steps) {
+    if (!ctxs || n_ctx < 1 || n_rays < 0) return GEOAC_ERR_BAD_ARG;
+    for (int i = 0; i < n_ctx; i++) if (!ctxs[i]) return GEOAC_ERR_BAD_ARG;
+    if (n_rays > 0 && (!theta || !phi || !rec || !status || !n_steps)) return fail(ctxs[0], GEOAC_ERR_BAD_ARG, "geoac_trace_multi: null buffer");
+    for (int i = 1; i < n_ctx; i++)
+        if (ctxs[i]->variant != ctxs[0]->variant || ctxs[i]->prm.bounces != ctxs[0]->prm.bounces || ctxs[i]->prm.calc_amp != ctxs[0]->prm.calc_amp)
+            return fail(ctxs[0], GEOAC_ERR_BAD_ARG, "geoac_trace_multi: the contexts must share variant, bounces and calc_amp (set the same atmosphere and parameters on each)");
+    if (n_rays == 0) return GEOAC_OK;
+    const int n_rec = ctxs[0]->prm.bounces + 1;
+    const int64_t B = GEOAC_SHARD_BLOCK, n_blocks = (n_rays + B - 1) / B, n_slots = n_rays * n_rec;
+    return for_each_ctx(ctxs, n_ctx, [&](geoac_ctx* c, int r) -> int {
+        cudaSetDevice(c->device);
+        int64_t mine = 0;                                                       // rays of the blocks b = r, r + n_ctx, r + 2 n_ctx, ...
+        for (int64_t b = r; b < n_blocks; b += n_ctx) mine += std::min(B, n_rays - b * B);
+        if (mine == 0) return GEOAC_OK;
+        const int64_t my_slots = mine * n_rec;
+        int g = pin_grow(c, c->pin_theta, sizeof(double) * mine); if (g) return g;
+        g = pin_grow(c, c->pin_phi, sizeof(double) * mine); if (g) return g;
+        g = pin_grow(c, c->pin_rec, sizeof(double) * GEOAC_NFIELDS * my_slots); if (g) return g;
+        g = pin_grow(c, c->pin_status, sizeof(int32_t) * my_slots); if (g) return g;
+        g = pin_grow(c, c->pin_nsteps, sizeof(int32_t) * my_slots); if (g) return g;
+        double *h_th = (double*)c->pin_theta.p, *h_ph = (double*)c->pin_phi.p, *h_rec = (double*)c->pin_rec.p;
+        int32_t *h_st = (int32_t*)c->pin_status.p, *h_ns = (int32_t*)c->pin_nsteps.p;
+        int64_t at = 0;
+        for (int64_t b = r; b < n_blocks; b += n_ctx) {
+            const int64_t s0 = b * B, len = std::min(B, n_rays - s0);
+            std::memcpy(h_th + at, theta + s0, sizeof(double) * len); std::memcpy(h_ph + at, phi + s0, sizeof(double) * len);
+            at += len;
+        }
+        const int rc = trace_host(c, mine, h_th, h_ph, h_rec, h_st, h_ns, 0, 0, nullptr, nullptr, 0, nullptr, nullptr);
+        if (rc != GEOAC_OK) return rc;
+        at = 0;
+        for (int64_t b = r; b < n_blocks; b += n_ctx) {                          // merge by ray index
+            const int64_t s0 = b * B, len = std::min(B, n_rays - s0);
+            for (int f = 0; f < GEOAC_NFIELDS; f++)
+                std::memcpy(rec + (int64_t)f * n_slots + s0 * n_rec, h_rec + (int64_t)f * my_slots + at * n_rec, sizeof(double) * len * n_rec);
+            std::memcpy(status + s0 * n_rec, h_st + at * n_rec, sizeof(int32_t) * len * n_rec);
+            std::memcpy(n_steps + s0 * n_rec, h_ns + at * n_rec, sizeof(int32_t) * len * n_rec);
+            at += len;
+        }
+        return GEOAC_OK;
+    });
 }
 
 extern "C" int geoac_get_variant(const geoac_ctx* ctx) { return ctx ? ctx->variant : -1; }

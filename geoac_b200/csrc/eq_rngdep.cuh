@@ -369,8 +369,12 @@ struct EqGlobalRD {
         const double cn = c * g_rsqrt(n0 * n0 + n1 * n1 + n2 * n2);
         const double c0 = cn * n0, c1 = cn * n1 + w[2], c2 = cn * n2 + w[1];
         dtt = ds_tt * g_rsqrt(c0 * c0 + c1 * c1 + c2 * c2);
-        Cur3 cref = cur; cref.kz = 0;
-        ms_wrappers<true, true, false>(G, tm, pm, L.z_grnd, cref, wr, dzs);
+        {   // reference state at the lowest levels under the query point; the ray's own cursor carries the cache tags
+            const int kz_ray = cur.kz;
+            cur.kz = 0;
+            ms_wrappers<true, true, false, true>(G, tm, pm, L.z_grnd, cur, wr, dzs);
+            cur.kz = kz_ray;
+        }
         SBRef ref; suthbass_ref(ref, sqrt(kGamR * wr[0]), wr[3]);
         datt = suthbass_alpha(L, ref, rm - kREarth, c, inv_c, w[3]) * ds_sb;
     }

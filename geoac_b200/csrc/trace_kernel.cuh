@@ -42,8 +42,14 @@ struct TraceArgs {
     unsigned long long* warp_trips;   // trips round the step loop, summed over warps (lane occupancy = steps / (32 trips))
     const uint32_t* order;            // claim order (longest-predicted first) or nullptr = natural order; 0xffffffff = empty slot
     int64_t n_claims;                 // entries of `order` (a multiple of 32 in packet mode), or n_rays
-    const uint32_t* n_long;           // packet mode: number of leading packets of `order` to trace four-lanes-per-ray from the start (or nullptr)
-    unsigned long long* counter_long; // next unclaimed entry of that leading region (claimed 8 rays at a time)
+    // packet mode (range-dependent sets): the first n_long_packets packets of `order` are the LONG region -- packets whose
+    // predicted cost exceeds the average work of a lane, i.e. which would outlast the pass on a fully loaded SM.  They are
+    // claimed by the CTAs of a second, concurrent launch that keeps its SMs to itself (one warp per scheduler: see capi.cu),
+    // `long_width` rays at a time (32 = whole packets, 8 = quarter packets traced four lanes per ray from the start).
+    int64_t n_long_packets;
+    unsigned long long* counter_long; // next unclaimed entry of the long region
+    int prefer_long;                  // this launch claims the long region first (1) or the main region first (0)
+    int long_width;
     int packet_refill;                // experiment knob: refill a warp only when all of its lanes are idle (always on for PacketMode sets)
     double* path; int32_t* path_rows; int path_stride; int64_t path_cap;   // raypath capture (PATHS kernels), else unused
     double* caus; int32_t* caus_rows; int64_t caus_cap;                    // caustic events (PATHS kernels), else unused
@@ -192,8 +198,12 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     const bool brk = EQ::left_region(L, d.rc, acc);              // BreakCheck first (Solver.cpp:57-64)
     const bool gnd = !brk && EQ::below_ground(L, acc);
     const bool lim = !brk && !gnd && (n.ksteps >= L.step_limit - 1);
-    if (L.seg_mode) { if (!(brk || gnd || lim)) { d.tt_total += dtt; d.att_total += datt; } }
-    else            { d.tt_b += dtt; d.att_b += datt; }
+    {   // running sums: read, (cooperative group: everyone has read), write
+        const double tt0 = d.tt_total, at0 = d.att_total, tb0 = d.tt_b, ab0 = d.att_b;
+        if (MEM) group_sync(T);
+        if (L.seg_mode) { if (!(brk || gnd || lim)) { d.tt_total = tt0 + dtt; d.att_total = at0 + datt; } }
+        else            { d.tt_b = tb0 + dtt; d.att_b = ab0 + datt; }
+    }
 
     if (!(brk || gnd || lim)) {
         if (PATHS) {
@@ -201,7 +211,8 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
                 // WriteCaustics=True (Code/GeoAc3D_main.cpp:241-268): D_prev starts as the Jacobian of step 1 of each bounce; a
                 // row { position, travel time } wherever D * D_prev < 0
                 const double D = EQ::jacobian(L, T, d.rc, acc, n.cur);
-                if (n.ksteps > 1 && D * d.D_prev < 0.0) {
+                const double Dp = d.D_prev;
+                if (n.ksteps > 1 && D * Dp < 0.0) {
                     if (n.caus_n < o.caus_cap) {
                         double* row = o.caus + ((int64_t)n.ray * o.caus_cap + n.caus_n) * GEOAC_CAUSTIC_NF;
                         row[0] = acc[0]; row[1] = acc[1]; row[2] = acc[2]; row[3] = d.tt_total;
@@ -209,6 +220,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
                     }
                     n.caus_n++; n.caus_b++;
                 }
+                if (MEM) group_sync(T);
                 d.D_prev = D;
             }
             if (o.path_stride > 0 && n.ksteps % o.path_stride == 0) {   // row for state m = ksteps (m < k: never the sub-ground point)
@@ -223,10 +235,10 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
             }
         }
 #pragma unroll
-        for (int i = 0; i < NEQ; i++) {
-            if (NeedsPrev<EQ>::value) prev[i * pstride] = y[i];
-            y[i] = acc[i];
-        }
+        for (int i = 0; i < NEQ; i++) { if (NeedsPrev<EQ>::value) prev[i * pstride] = y[i]; }
+        if (MEM) group_sync(T);                                 // every lane of the group has parked y_k before it becomes y_{k+1}
+#pragma unroll
+        for (int i = 0; i < NEQ; i++) y[i] = acc[i];
         return true;
     }
     // ---------------- rare tail: end of a bounce segment ----------------
@@ -238,7 +250,12 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
         if (PATHS) { if (o.path_rows) o.path_rows[n.ray] = n.path_n; if (o.caus_rows) o.caus_rows[n.ray] = n.caus_n; }
         return false;
     }
-    if (!L.seg_mode) { d.tt_total += d.tt_b; d.att_total += d.att_b; d.tt_b = 0.0; d.att_b = 0.0; }
+    if (!L.seg_mode) {
+        const double tt0 = d.tt_total + d.tt_b, at0 = d.att_total + d.att_b;
+        if (MEM) group_sync(T);
+        d.tt_total = tt0; d.att_total = at0; d.tt_b = 0.0; d.att_b = 0.0;
+        if (MEM) group_sync(T);
+    }
     double amp, incl, baz, aux, margin;
     EQ::arrival(L, T, d.rc, y, acc, d.tt_total, n.cur, amp, incl, baz, aux, margin);
 #pragma unroll
@@ -263,6 +280,7 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
 #pragma unroll
     for (int i = 0; i < NEQ; i++) ym2[i] = NeedsPrev<EQ>::value ? prev[i * pstride] : 0.0;
     EQ::reflect(L, T, d.rc, ym2, y, acc, y0, n.cur);
+    if (MEM) group_sync(T);                                     // the intercept read y_{k-1} (= y) and y_k on every lane of the group
 #pragma unroll
     for (int i = 0; i < NEQ; i++) y[i] = y0[i];
     n.bounce++; n.ksteps = 0; n.caus_b = 0;
@@ -346,52 +364,63 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
     // y_{k-1} history (quadratic intercept only): [eq][global thread] in an L2-resident global scratch, written once per step
     const int64_t pstride = (int64_t)gridDim.x * BLOCK;
     double* prev = a.prev + ((int64_t)blockIdx.x * BLOCK + threadIdx.x);
-    bool have_ray = false, exhausted = false, long_done = false;
+    bool have_ray = false, exhausted = false;
+    unsigned region_done = 0;          // packet mode, lane 0: bit 0 = long region drained, bit 1 = main region drained
     unsigned long long my_steps = 0;
     unsigned my_trips = 0;
 
     while (true) {
         // ---------------- refill idle lanes (warp-aggregated claim) ----------------
-        // PACKET sets (range dependent): a warp takes 32 rays with neighbouring launch angles at once and refills only
-        // when all of them have ended, so its lanes walk through the same few grid cells and share their node data in L1.
-        const bool busy = (PacketMode<EQ>::value || a.packet_refill) && __any_sync(0xffffffffu, have_ray);
-        const bool want = !have_ray && !exhausted && !busy;
-        const unsigned wmask = __ballot_sync(0xffffffffu, want);
-        if (wmask) {
-            unsigned long long base = 0;
-            int width = __popc(wmask);                                   // entries this claim takes
-            const int leader = __ffs(wmask) - 1;
-            if ((int)lane == leader) {
-                bool got = false;
-                if (PacketMode<EQ>::value && a.n_long && !long_done) {
-                    // the longest packets are traced four lanes per ray from the start (see the straggler path below): a warp
-                    // takes a quarter packet.  A cooperative trip needs ~0.57x the instructions of a serial one, so those
-                    // packets advance faster while they share the SM with the bulk of the batch (measured: config-5 slice
-                    // 15.3 s -> 12.8 s).  It does NOT shorten a lone warp's trip: that is bound by the dependent chain
-                    // of one RK4 step (~44 us), which row-splitting leaves as it is.
-                    const unsigned long long nl = (unsigned long long)(*a.n_long) * 32ull;
-                    if (nl) {
-                        const unsigned long long q = atomicAdd(a.counter_long, 8ull);
-                        if (q < nl) { base = q; width = 8; got = true; }
+        if constexpr (PacketMode<EQ>::value) {
+            // PACKET sets (range dependent): a warp takes 32 rays of one packet at once -- neighbouring launch angles, chosen by
+            // the host so that the lanes walk through the same few grid cells (capi.cu) -- and refills only when all of them have
+            // ended.  Two regions of the claim order, two counters; which one a warp drains first depends on the launch it
+            // belongs to (long-region CTAs run one warp per scheduler, so a long packet advances at lone-warp speed).
+            if (!exhausted && !__any_sync(0xffffffffu, have_ray)) {
+                unsigned long long base = 0; int width = 0;
+                if (lane == 0) {
+                    const unsigned long long nl = (unsigned long long)a.n_long_packets * 32ull;
+                    const unsigned long long nm = (unsigned long long)a.n_claims - nl;
+                    for (int attempt = 0; attempt < 2 && width == 0; attempt++) {
+                        const bool from_long = (attempt == 0) == (a.prefer_long != 0);
+                        if (from_long) {
+                            if (nl && !(region_done & 1u)) {
+                                const unsigned long long q = atomicAdd(a.counter_long, (unsigned long long)a.long_width);
+                                if (q < nl) { base = q; width = a.long_width; } else region_done |= 1u;
+                            }
+                        } else if (nm && !(region_done & 2u)) {
+                            const unsigned long long q = atomicAdd(a.counter, 32ull);
+                            if (q < nm) { base = nl + q; width = 32; } else region_done |= 2u;
+                        }
                     }
-                    if (!got) width = -width;                            // tells the warp that the leading region is used up
                 }
-                if (!got) {
-                    const unsigned long long nl = (PacketMode<EQ>::value && a.n_long) ? (unsigned long long)(*a.n_long) * 32ull : 0ull;
-                    base = nl + atomicAdd(a.counter, (unsigned long long)__popc(wmask));
-                }
-            }
-            base = __shfl_sync(0xffffffffu, base, leader);
-            width = __shfl_sync(0xffffffffu, width, leader);
-            if (width < 0) { long_done = true; width = -width; }
-            const int rank = __popc(wmask & ((1u << lane) - 1u));
-            if (want && rank < width) {
-                const int64_t idx = (int64_t)base + rank;
-                if (idx < a.n_claims) {
+                base = __shfl_sync(0xffffffffu, base, 0);
+                width = __shfl_sync(0xffffffffu, width, 0);
+                if (width == 0) exhausted = true;
+                else if ((int)lane < width) {
+                    const int64_t idx = (int64_t)base + lane;
                     const int64_t r = a.order ? (int64_t)a.order[idx] : idx;
                     if (r < a.n_rays) { lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]); have_ray = true; }
                 }
-                else exhausted = true;
+            }
+        } else {
+            const bool busy = a.packet_refill && __any_sync(0xffffffffu, have_ray);
+            const bool want = !have_ray && !exhausted && !busy;
+            const unsigned wmask = __ballot_sync(0xffffffffu, want);
+            if (wmask) {
+                unsigned long long base = 0;
+                const int leader = __ffs(wmask) - 1;
+                if ((int)lane == leader) base = atomicAdd(a.counter, (unsigned long long)__popc(wmask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const int rank = __popc(wmask & ((1u << lane) - 1u));
+                if (want) {
+                    const int64_t idx = (int64_t)base + rank;
+                    if (idx < a.n_claims) {
+                        const int64_t r = a.order ? (int64_t)a.order[idx] : idx;
+                        if (r < a.n_rays) { lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]); have_ray = true; }
+                    }
+                    else exhausted = true;
+                }
             }
         }
         const unsigned act = __ballot_sync(0xffffffffu, have_ray);
@@ -445,6 +474,130 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
     }
     for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
     if (lane == 0 && my_steps) { atomicAdd(a.total_steps, my_steps); atomicAdd(a.warp_trips, (unsigned long long)my_trips); }   // per warp
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Cooperative kernel of the range-dependent sets: FOUR LANES PER RAY, eight rays per warp, the ray's cell in shared memory.
+//
+// Why: in the one-thread-per-ray kernel a warp whose 32 rays sit in 32 different grid cells streams 32 x 4.6 KB of node data
+// through L1 for every sample, five samples per step; long rays decorrelate (config 5: 2.5 % of the rays travel 20 000 km and
+// take 25 % of the steps), L1 thrashes, every dependent load round waits for L2, and a step costs ~100 us however empty the SM
+// is -- so the pass cannot be shorter than (longest ray) x 100 us, which is what capped the 8-GPU scaling of config 5.
+// Here a ray's 4 x 4 x 2 node block (5 KB) is staged into shared memory by TMA bulk copies when the ray enters a cell and every
+// sample of the >= 50 that follow reads it from there (mspline.cuh: ms_cache_cell); 32 rays per SM is what shared memory holds,
+// so four lanes share a ray: lane r evaluates row r of the node block, the row contributions are accumulated lane after lane in
+// the serial order, everything else is executed redundantly -- the arithmetic, hence every record bit, is that of the
+// one-thread-per-ray kernel.  Slots refill one by one (a cell cache makes packets pointless), so no lane waits for a straggler.
+// Used for the LONG region of the claim order (capi.cu), on SMs of its own.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kCoopBlock = 128;                       // 4 warps x 8 rays
+constexpr int kCoopSlots = kCoopBlock / 4;
+template <class EQ> struct CoopLayout {
+    static constexpr int REC = LaneLayout<EQ>::STRIDE;                                     // doubles per ray record (incl. work + sampler scratch)
+    static constexpr size_t bytes() {
+        return ((sizeof(LaunchConsts) + 15) / 16) * 16 + sizeof(double) * (size_t)kCoopSlots * (REC + 1 + MS_CACHE_TUV + MS_CACHE_RHO + MS_CACHE_GND)
+               + sizeof(uint64_t) * 2 * kCoopSlots + 64;
+    }
+};
+
+template <class EQ>
+__global__ void __launch_bounds__(kCoopBlock, 1) trace_coop_kernel(const __grid_constant__ TraceArgs a) {
+    constexpr int NEQ = EQ::NEQ;
+    static_assert(PacketMode<EQ>::value, "cooperative kernel: range-dependent sets only");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    LaunchConsts* Ls = reinterpret_cast<LaunchConsts*>(smem_raw);
+    double* base = reinterpret_cast<double*>(smem_raw + ((sizeof(LaunchConsts) + 15) / 16) * 16);
+    double* c_tuv = base;                                                    // 16-byte aligned blocks first (TMA destinations)
+    double* c_rho = c_tuv + (size_t)kCoopSlots * MS_CACHE_TUV;
+    double* c_gnd = c_rho + (size_t)kCoopSlots * MS_CACHE_RHO;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(c_gnd + (size_t)kCoopSlots * MS_CACHE_GND);
+    double* recs = reinterpret_cast<double*>(bars + 2 * kCoopSlots);
+    for (int i = threadIdx.x; i < (int)(sizeof(LaunchConsts) / 8); i += kCoopBlock)
+        reinterpret_cast<double*>(Ls)[i] = reinterpret_cast<const double*>(a.consts)[i];
+    const unsigned lane = threadIdx.x & 31;
+    const int slot = (int)(threadIdx.x >> 2), role = (int)lane & 3;
+    if (role == 0) {
+        const uint32_t b0 = smem_u32(bars + 2 * slot);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0 + 8));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const LaunchConsts& L = *Ls;
+    double* const rec = recs + (size_t)slot * (CoopLayout<EQ>::REC | 1);
+    double* const work = rec + LaneLayout<EQ>::WORK;
+    typename EQ::Atmo T = a.grid;
+    T.scratch = work + 2 * NEQ;
+    T.role = role; T.nrole = 4; T.glane0 = (int)lane & ~3; T.gmask = 0xFu << ((int)lane & ~3);
+    T.cache_tuv = c_tuv + (size_t)slot * MS_CACHE_TUV; T.cache_rho = c_rho + (size_t)slot * MS_CACHE_RHO;
+    T.cache_gnd = c_gnd + (size_t)slot * MS_CACHE_GND; T.cache_bar = bars + 2 * slot;
+    RecOut o; o.rec = a.rec; o.status = a.status; o.n_steps = a.n_steps; o.n_rec = a.n_rec; o.n_slots = a.n_rays * a.n_rec;
+    o.path = nullptr; o.path_rows = nullptr; o.path_stride = 0; o.path_cap = 0; o.caus = nullptr; o.caus_rows = nullptr; o.caus_cap = 0;
+    LaneD<EQ>& ld = *reinterpret_cast<LaneD<EQ>*>(rec);
+    LaneI<EQ> li;                                                            // replicated in the four lanes of the group
+    unsigned cache_phase = 0;                                                // mbarrier phases outlive the rays of a slot
+    const int64_t pstride = (int64_t)gridDim.x * kCoopSlots;
+    double* prev = a.prev + ((int64_t)blockIdx.x * kCoopSlots + slot);
+    bool have_ray = false, exhausted = false;
+    unsigned region_done = 0;
+    unsigned long long my_steps = 0;
+    unsigned my_trips = 0;
+    const unsigned long long nl = (unsigned long long)a.n_long_packets * 32ull;
+    const unsigned long long nm = (unsigned long long)a.n_claims - nl;
+
+    while (true) {
+        // ---------------- refill idle slots one by one (warp-aggregated claim, long region first) ----------------
+        const unsigned wmask = __ballot_sync(0xffffffffu, role == 0 && !have_ray && !exhausted);
+        if (wmask) {
+            const int want_n = __popc(wmask);
+            unsigned long long b1 = 0, b2 = 0; int n1 = 0, n2 = 0;             // up to two runs of entries: one per region
+            if (lane == (unsigned)(__ffs(wmask) - 1)) {
+                int need = want_n;
+                for (int attempt = 0; attempt < 2 && need > 0; attempt++) {
+                    const bool from_long = (attempt == 0) == (a.prefer_long != 0);
+                    unsigned long long q = 0, lim = 0, off = 0;
+                    if (from_long) { if (!nl || (region_done & 1u)) continue; q = atomicAdd(a.counter_long, (unsigned long long)need); lim = nl; }
+                    else           { if (!nm || (region_done & 2u)) continue; q = atomicAdd(a.counter, (unsigned long long)need); lim = nm; off = nl; }
+                    const int got = (q < lim) ? (int)((lim - q < (unsigned long long)need) ? (lim - q) : (unsigned long long)need) : 0;
+                    if (got < need) region_done |= from_long ? 1u : 2u;
+                    if (got > 0) { if (n1 == 0) { b1 = off + q; n1 = got; } else { b2 = off + q; n2 = got; } need -= got; }
+                }
+            }
+            const int leader = __ffs(wmask) - 1;
+            b1 = __shfl_sync(0xffffffffu, b1, leader); b2 = __shfl_sync(0xffffffffu, b2, leader);
+            n1 = __shfl_sync(0xffffffffu, n1, leader); n2 = __shfl_sync(0xffffffffu, n2, leader);
+            const unsigned my_bit = 1u << (lane & ~3u);                         // bit of this group's role-0 lane
+            const bool wants = (wmask & my_bit) != 0;
+            if (wants) {
+                const int rank = __popc(wmask & (my_bit - 1u));
+                long long idx = -1;
+                if (rank < n1) idx = (long long)b1 + rank; else if (rank < n1 + n2) idx = (long long)b2 + (rank - n1);
+                if (idx < 0) exhausted = true;
+                else {
+                    const int64_t r = a.order ? (int64_t)a.order[idx] : idx;
+                    if (r < a.n_rays) {
+                        lane_start<EQ>(ld, li, L, T, r, a.theta[r], a.phi[r]);
+                        li.cur.phase = cache_phase;                             // the slot's mbarriers keep their phase across rays
+                        have_ray = true;
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have_ray)) {
+            if (__all_sync(0xffffffffu, exhausted)) break;
+            continue;
+        }
+        my_trips++;
+        if (have_ray) {
+            __syncwarp(T.gmask);
+            have_ray = lane_advance<EQ, false>(ld, li, L, T, prev, pstride, o, work);
+            cache_phase = li.cur.phase;
+            if (role == 0) my_steps++;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) my_steps += __shfl_xor_sync(0xffffffffu, my_steps, off);
+    // lane occupancy is reported in units of 32-lane trips: a cooperative trip advances 8 rays with 32 lanes
+    if (lane == 0 && my_steps) { atomicAdd(a.total_steps, my_steps); atomicAdd(a.warp_trips, (unsigned long long)my_trips / 4ull); }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -558,14 +711,14 @@ __device__ __forceinline__ uint32_t group_cost(const uint32_t* cost, int64_t n, 
 // Also counts the LONG groups: those whose predicted cost exceeds the average work of a lane (cost_sum / lanes) -- traced
 // serially such a packet alone would outlast the rest of the batch, so it is traced four lanes per ray instead.
 __global__ void order_hist_kernel(const uint32_t* cost, int64_t n, int group, const uint32_t* cost_max, uint32_t* hist,
-                                  const unsigned long long* cost_sum, long long lanes, uint32_t* n_long) {
+                                  const unsigned long long* cost_sum, long long lanes, uint32_t* n_long, int alpha_pct) {
     __shared__ uint32_t h[kCostBuckets];
     __shared__ uint32_t nl;
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
     if (threadIdx.x == 0) nl = 0;
     __syncthreads();
     const uint32_t cmax = *cost_max;
-    const unsigned long long thr = *cost_sum / (unsigned long long)lanes;
+    const unsigned long long thr = (*cost_sum / (unsigned long long)lanes) * (unsigned long long)alpha_pct / 100ull;
     const int64_t ng = (n + group - 1) / group;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t c = group_cost(cost, n, g, group);
@@ -681,6 +834,58 @@ __global__ void stable_scatter_kernel(const uint8_t* key, const uint32_t* src, i
         }
         __syncwarp();
     }
+}
+
+// ---- range-dependent sets: which rays share a packet ----
+// A warp's 32 rays should walk through the same grid cells (their node data then come out of L1 as a few shared lines instead
+// of 32 private blocks).  The mains enumerate the launch grid azimuth by azimuth, inclination fastest, so 32 consecutive rays
+// are neighbours in INCLINATION: they stay in one vertical plane and spread over altitude ~ s * 32 dtheta.  32 rays of EQUAL
+// inclination and neighbouring AZIMUTH share their altitude history and spread sideways ~ s * 32 dphi.  Measured in cells
+// (vertical spacing dz, horizontal spacing dh) the second grouping is the tighter one iff dphi / dh < dtheta / dz -- config 5
+// (0.36 deg steps on a 1 deg = 111 km grid), not config 4 (3.6 deg steps on a 5 km grid).  grid_shape_kernel reads the two steps
+// off the batch: shape[0] = dtheta between the first two rays, shape[1] = dphi between the first two azimuth rows (0 if the batch
+// is not such a grid), shape[2] = rays per azimuth row.
+__global__ void grid_shape_kernel(const double* theta, const double* phi, int64_t n, double* shape) {
+    __shared__ int first_wrap;
+    if (threadIdx.x == 0) first_wrap = 0x7fffffff;
+    __syncthreads();
+    const int64_t lim = n < 65536 ? n : 65536;
+    for (int64_t i = 1 + threadIdx.x; i < lim; i += blockDim.x)
+        if (theta[i] < theta[i - 1]) atomicMin(&first_wrap, (int)i);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int w = first_wrap;
+        shape[0] = (n > 1) ? fabs(theta[1] - theta[0]) : 0.0;
+        shape[1] = (w != 0x7fffffff && w < n) ? fabs(phi[w] - phi[0]) : 0.0;
+        shape[2] = (w != 0x7fffffff) ? (double)w : (double)n;
+    }
+}
+// 16-bit inclination key (two stable 8-bit passes) + cost bucket: order = (cost bucket descending, inclination, batch index)
+__global__ void order_keys16_kernel(const uint32_t* cost, const double* theta, int64_t n, const uint32_t* cost_max, const double* range,
+                                    uint8_t* key_lo, uint8_t* key_hi, uint8_t* key_cost, int cost_shift) {
+    const uint32_t cmax = *cost_max;
+    const double t0 = range[0], span = range[1] - range[0];
+    const double sc = span > 0.0 ? 65535.0 / span : 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int kt = (int)((theta[i] - t0) * sc + 0.5);
+        kt = kt < 0 ? 0 : (kt > 65535 ? 65535 : kt);
+        key_lo[i] = (uint8_t)(kt & 255); key_hi[i] = (uint8_t)(kt >> 8);
+        key_cost[i] = (uint8_t)(cost_bucket(cost[i], cmax) >> cost_shift);
+    }
+}
+// packets of the final order whose longest ray exceeds the average work of a lane (times alpha_pct / 100): the long region.
+// The order is sorted by cost bucket, so they sit at its head; the count is all the launch needs.
+__global__ void packet_long_kernel(const uint32_t* order, const uint32_t* cost, int64_t n_packets, int64_t n_rays,
+                                   const unsigned long long* cost_sum, long long lanes, int alpha_pct, uint32_t* n_long) {
+    const unsigned long long thr = (*cost_sum / (unsigned long long)lanes) * (unsigned long long)alpha_pct / 100ull;
+    uint32_t cnt = 0;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_packets; g += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t c = 0;
+        for (int l = 0; l < 32; l++) { const uint32_t r = order[g * 32 + l]; if (r < n_rays) c = max(c, cost[r]); }
+        if ((unsigned long long)c > thr) cnt++;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_long, cnt);
 }
 
 #endif  // __CUDACC__

@@ -46,8 +46,14 @@ def merge_shards(n_rays, n_rec, shards):
 
 
 def trace_multi(tracers, theta, phi, block=SHARD_BLOCK):
-    """Trace one batch on several contexts (one per device, same variant / atmosphere / parameters) from host threads
-    and return the merged records.  The result is bitwise identical to tracing the batch on one device."""
+    """Trace one batch on several contexts (one per device, same variant / atmosphere / parameters) and return the merged
+    records -- a thin binding over geoac_trace_multi (include/geoac_b200.h): the partition, the host threads, the pinned staging
+    and the merge by ray index all live in the library, which is what a C++ front end calls too.  `block` other than the
+    library's GEOAC_SHARD_BLOCK is honoured with the host-side partition below (tests exercise ragged blocks with it).
+    The result is bitwise identical to tracing the batch on one device."""
+    from . import api
+    if block == SHARD_BLOCK:
+        return api.trace_multi(tracers, theta, phi)
     theta = np.ascontiguousarray(theta, dtype=np.float64)
     phi = np.ascontiguousarray(phi, dtype=np.float64)
     world = len(tracers)

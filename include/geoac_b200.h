@@ -166,6 +166,26 @@ int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* theta, const
                       int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
                       int64_t caustic_cap, double* caustic, int32_t* caustic_rows);
 
+/* ---- several devices behind one call (the data-parallel axis is the launch-angle loop, Code/GeoAc3D_main.cpp:226-227) ----
+ * A front end creates one context per device (geoac_create_multi, or geoac_create in a loop), gives every context the same
+ * atmosphere and parameters (the geoac_multi_set_* helpers do that from one host thread per context) and traces with
+ * geoac_trace_multi: the ray list is dealt to the contexts in interleaved blocks of GEOAC_SHARD_BLOCK rays, one host thread
+ * per context stages its share through pinned memory owned by that context, traces it, and writes the records back at the
+ * rays' own places in rec / status / n_steps (same layout as geoac_trace for the whole batch).  There is no exchange between
+ * devices.  The result is bitwise what a single context returns.  device_ids may name a device twice (two contexts on one
+ * GPU -- that is how the tests exercise the path on a one-GPU box).  Contexts are destroyed one by one with geoac_destroy.
+ * On failure the message of the failing context is copied to ctxs[0] (geoac_last_error(ctxs[0])). */
+enum { GEOAC_SHARD_BLOCK = 4096 };
+int geoac_create_multi(int variant, const int* device_ids, int n_devices, geoac_ctx** ctxs, int* status);
+int geoac_multi_set_atmosphere_1d(geoac_ctx* const* ctxs, int n_ctx, int n, const double* z, const double* T,
+                                  const double* u, const double* v, const double* rho);
+int geoac_multi_set_atmosphere_3d(geoac_ctx* const* ctxs, int n_ctx, int n0, int n1, int nz,
+                                  const double* ax0, const double* ax1, const double* axz,
+                                  const double* T, const double* u, const double* v, const double* rho);
+int geoac_multi_set_params(geoac_ctx* const* ctxs, int n_ctx, const geoac_params* p);
+int geoac_trace_multi(geoac_ctx* const* ctxs, int n_ctx, int64_t n_rays, const double* theta, const double* phi,
+                      double* rec, int32_t* status, int32_t* n_steps);
+
 /* Optional: allocate the device staging geoac_trace() needs for batches of up to n_rays rays (with the current
  * `bounces`) ahead of time, so that the first trace call does not pay for it.  geoac_trace() grows it on demand anyway. */
 int geoac_reserve(geoac_ctx* ctx, int64_t n_rays);
@@ -252,6 +272,11 @@ int geoac_eq_count(int variant, int calc_amp);
  * 8 for the stratified ones, whose order is (cost, inclination, batch index) in two stable passes).  Either pointer may be NULL. */
 int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kernel_launches);
 
+/* Scheduling facts of the last trace on ctx: out4[0] packet grouping of the range-dependent sets (0 = 32 consecutive rays,
+ * 1 = equal inclination / neighbouring azimuth), out4[1] packets in the long region (predicted to outlast the pass on a loaded
+ * SM), out4[2] CTAs of the concurrent launch that traced them on SMs of their own, out4[3] kernels enqueued. */
+int geoac_last_schedule(geoac_ctx* ctx, int64_t* out4);
+
 /* Device self-test of the kernel's branch-free FP64 primitives against the CUDA math library on n_per_thread random
  * operands per thread: max_err[7] = maximum relative error of reciprocal, reciprocal square root, square root, exp, 10^x
  * and maximum absolute error of sin, cos (arguments within a few turns), in that order. */
@@ -266,7 +291,8 @@ int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t 
 
 /* Tuning / experiment knobs of a context.  Their defaults are read from the GEOAC_B200_* environment
  * variables ONCE, in geoac_create; nothing on the launch path reads the environment.  Names: "lpt" (claim order: 0 natural,
- * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables".
+ * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables",
+ * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive".
  * No knob changes a record bit except "sbpoly" (absorption sum to 1e-11) -- that is what the tests use them to prove. */
 int geoac_set_knob(geoac_ctx* ctx, const char* name, int value);
 
