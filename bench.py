@@ -415,6 +415,15 @@ def run_ours(args):
     h2d = 2 * n * 8
     d2h = abi.NFIELDS * n_slots * 8 + 2 * n_slots * 4 + 16
 
+    multi = None
+    if world > 1 and args.workload in ("config1", "config2") and not args.rays_cap:
+        barrier()
+        if rank == 0:
+            try:
+                multi = single_process_multi_record(args, world)
+            except Exception as e:                                       # reported, never fatal for the bench line
+                multi = {"error": str(e)}
+        barrier()
     strong = None
     if not args.no_strong and args.workload == "config2" and not args.rays_cap:
         tr_keep = tr
@@ -452,6 +461,8 @@ def run_ours(args):
                                         "HBM is not the bound: ~0.03 B/step of record traffic"},
             "wall_s_timed_region": t_wall,
         }
+        if multi is not None:
+            line["single_process_multi"] = multi
         if strong is not None:
             strong["roofline_frac"] = strong["roofline_frac"] / peak_tf if peak_tf > 0 else None
             line["strong"] = strong
@@ -477,6 +488,39 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def single_process_multi_record(args, world):
+    """Rank 0 only, the other ranks idle at a barrier: ONE process drives all `world` devices through the product's own multi-device
+    entry point (geoac_create_multi + geoac_trace_multi: host threads, interleaved 4096-ray blocks, pinned staging, merge by ray
+    index) -- the path a C++ front end uses -- on the concatenation of every rank's batch, host buffers in and out."""
+    from geoac_b200 import api, abi
+    variant, _, bounces, atmo = WORKLOADS[args.workload]
+    ths, phs = [], []
+    for r in range(world):
+        _, _, _, th, ph = workload_angles(args.workload, r)
+        ths.append(th); phs.append(ph)
+    th, ph = np.concatenate(ths), np.concatenate(phs)
+    mt = api.MultiTracer(variant, list(range(world)))
+    try:
+        if atmo == "toy":
+            mt.set_atmosphere_1d(*api.load_met_1d(TOY))
+        else:
+            return None
+        p = mt.params
+        p.bounces, p.calc_amp, p.accum_per_segment = bounces, 1, (1 if variant == V2D else 0)
+        mt.params = p
+        out = mt.trace(th, ph)                                           # warm-up: staging allocated, kernels loaded
+        t0 = time.perf_counter()
+        k = 2
+        for _ in range(k):
+            mt.trace(th, ph, out)
+        secs = (time.perf_counter() - t0) / k
+        return {"devices": world, "rays": int(len(th)), "rays_per_sec": len(th) / secs, "ms_per_pass": 1e3 * secs,
+                "arrival_records": int((out["status"] == abi.ST_ARRIVAL).sum()),
+                "api": "geoac_create_multi + geoac_multi_set_* + geoac_trace_multi (one process, one host thread per device, host buffers)"}
+    finally:
+        mt.close()
 
 
 def strong_scaling_record(world, rank, local, dev, barrier):

@@ -41,11 +41,12 @@ struct Knobs {
     int sbpoly = 1;         // absorption through per-interval polynomials
     int block3d = 384;      // lanes per SM of Eq3D<true>
     int host_tables = 0;    // build the node tables on the host
-    int rd_group = -1;      // range-dependent packets: 0 = 32 consecutive rays (inclination neighbours), 1 = equal inclination / neighbouring azimuth, -1 = automatic
+    int rd_group = 0;       // range-dependent packets: 0 = 32 consecutive rays (inclination neighbours), 1 = equal inclination / neighbouring azimuth, -1 = automatic
     int long_alpha = 100;   // a packet is LONG if its cost exceeds long_alpha % of the average work of a lane
-    int long_width = 8;     // long-region CTAs: 8 = cooperative kernel (four lanes per ray, cell cache in shared memory), 32 = one thread per ray
+    int long_width = 32;    // long-region CTAs: 32 = one thread per ray, 8 = cooperative kernel (four lanes per ray, cell cache in shared memory)
     int long_sm_pct = 50;   // at most this share of the SMs is given to the long-region launch
     int exclusive = 1;      // long-region launch keeps its SMs to itself (0: one launch, long packets first)
+    int rd_ctas = 0;        // range-dependent sets: CTAs per SM of the main launch (0 = as many as fit)
 };
 static int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
 static Knobs knobs_from_env() {
@@ -56,8 +57,9 @@ static Knobs knobs_from_env() {
     k.sbpoly = env_int("GEOAC_B200_SBPOLY", k.sbpoly); k.block3d = env_int("GEOAC_B200_BLOCK", k.block3d);
     k.host_tables = env_int("GEOAC_B200_HOST_TABLES", k.host_tables);
     k.rd_group = env_int("GEOAC_B200_RD_GROUP", k.rd_group); k.long_alpha = std::max(1, env_int("GEOAC_B200_LONG_ALPHA", k.long_alpha));
-    k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 32 ? 32 : 8;
+    k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 8 ? 8 : 32;
     k.long_sm_pct = std::min(90, std::max(1, env_int("GEOAC_B200_LONG_SM_PCT", k.long_sm_pct))); k.exclusive = env_int("GEOAC_B200_EXCLUSIVE", k.exclusive);
+    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas));
     return k;
 }
 
@@ -89,7 +91,8 @@ struct geoac_ctx {
     int32_t *d_status = nullptr, *d_nsteps = nullptr;
     int64_t cap_rays = 0, cap_slots = 0;
     cudaStream_t stream = nullptr, stream_long = nullptr;      // stream_long: the concurrent long-region launch of the range-dependent sets
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_m0 = nullptr, ev_m1 = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
+    bool timed_launches = false;
     double grid_dh = 0.0, grid_dz = 0.0;                       // median node spacing [km] of the range-dependent grid (packet grouping heuristic)
     int last_long_packets = 0, last_long_ctas = 0, last_rd_group = 0;
     int64_t last_steps = 0; double last_ms = 0.0;
@@ -147,6 +150,7 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
            && cudaStreamCreateWithPriority(&ctx->stream_long, cudaStreamNonBlocking, prio_hi) == cudaSuccess
            && cudaEventCreate(&ctx->ev0) == cudaSuccess && cudaEventCreate(&ctx->ev1) == cudaSuccess
            && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess
+           && cudaEventCreate(&ctx->ev_m0) == cudaSuccess && cudaEventCreate(&ctx->ev_m1) == cudaSuccess && cudaEventCreate(&ctx->ev_l0) == cudaSuccess && cudaEventCreate(&ctx->ev_l1) == cudaSuccess
            && cudaMalloc(&ctx->d_consts, sizeof(LaunchConsts)) == cudaSuccess
            && cudaMalloc(&ctx->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); delete ctx; return bail(GEOAC_ERR_CUDA, "context allocation failed: " + m); }
@@ -164,6 +168,10 @@ extern "C" void geoac_destroy(geoac_ctx* ctx) {
     cudaFreeHost(ctx->pin_theta.p); cudaFreeHost(ctx->pin_phi.p); cudaFreeHost(ctx->pin_rec.p); cudaFreeHost(ctx->pin_status.p); cudaFreeHost(ctx->pin_nsteps.p);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_m0) cudaEventDestroy(ctx->ev_m0);
+    if (ctx->ev_m1) cudaEventDestroy(ctx->ev_m1);
+    if (ctx->ev_l0) cudaEventDestroy(ctx->ev_l0);
+    if (ctx->ev_l1) cudaEventDestroy(ctx->ev_l1);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     if (ctx->stream_long) cudaStreamDestroy(ctx->stream_long);
@@ -189,8 +197,8 @@ extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
     else if (n == "coop") k.coop = value; else if (n == "sbpoly") k.sbpoly = value; else if (n == "block3d") k.block3d = value;
     else if (n == "host_tables") k.host_tables = value;
     else if (n == "rd_group") k.rd_group = value; else if (n == "long_alpha") k.long_alpha = std::max(1, value);
-    else if (n == "long_width") k.long_width = (value == 32) ? 32 : 8; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
-    else if (n == "exclusive") k.exclusive = value;
+    else if (n == "long_width") k.long_width = (value == 8) ? 8 : 32; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
+    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value);
     else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
     return GEOAC_OK;
 }
@@ -493,14 +501,17 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
     if (fixed > (size_t)max_optin) return fail(ctx, GEOAC_ERR_CUDA, "lane records do not fit in shared memory");
     const bool in_smem = !kGrid && fixed + tab_bytes <= (size_t)max_optin;
     const size_t smem = in_smem ? fixed + tab_bytes : fixed;
-    if (PATHS && !kGrid && !in_smem) return fail(ctx, GEOAC_ERR_TOO_LARGE, "raypath capture needs the profile table in shared memory");
     const void* fn;
-    if constexpr (PATHS) fn = (const void*)trace_kernel<EQ, BLOCK, !kGrid, true>;
+    if constexpr (PATHS) {            // raypath / caustic capture; a profile too large for shared memory is read through L1/L2 like in the plain trace
+        if constexpr (kGrid) fn = (const void*)trace_kernel<EQ, BLOCK, false, true>;
+        else fn = in_smem ? (const void*)trace_kernel<EQ, BLOCK, true, true> : (const void*)trace_kernel<EQ, BLOCK, false, true>;
+    }
     else fn = in_smem ? (const void*)trace_kernel<EQ, BLOCK, true> : (const void*)trace_kernel<EQ, BLOCK, false>;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, BLOCK, smem));
     if (per_sm < 1) return fail(ctx, GEOAC_ERR_CUDA, "trace kernel does not fit on an SM");
+    if (kGrid && ctx->knobs.rd_ctas > 0) per_sm = std::min(per_sm, ctx->knobs.rd_ctas);
     // persistent grid: every resident CTA slot of every SM, but never more lanes than rays
     const int64_t warps_needed = (a.n_rays + 31) / 32;
     const int64_t ctas_needed = std::max<int64_t>(1, (warps_needed + (BLOCK / 32) - 1) / (BLOCK / 32));
@@ -661,12 +672,17 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         CK(cudaEventRecord(ctx->ev_fork, st));
         CK(cudaStreamWaitEvent(ctx->stream_long, ctx->ev_fork, 0));
         void* largs[] = { (void*)&al };
+        CK(cudaEventRecord(ctx->ev_l0, ctx->stream_long));
         CK(cudaLaunchKernel(fn_long, dim3(grid_long), dim3(block_long), largs, smem_long, ctx->stream_long));
+        CK(cudaEventRecord(ctx->ev_l1, ctx->stream_long));
         CK(cudaEventRecord(ctx->ev_join, ctx->stream_long));
         ctx->last_launches += 1; ctx->last_long_ctas = grid_long;
     }
     void* args[] = { (void*)&a };
+    CK(cudaEventRecord(ctx->ev_m0, st));
     CK(cudaLaunchKernel(fn, dim3(grid), dim3(BLOCK), args, smem, st));
+    CK(cudaEventRecord(ctx->ev_m1, st));
+    ctx->timed_launches = true;
     if (grid_long > 0) CK(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     ctx->last_launches += 1;
     return GEOAC_OK;
@@ -717,6 +733,8 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
             const int blk = ctx->knobs.block3d;
             if (blk == 256) return launch_trace<Eq3D<true>, 256>(ctx, a, st);
             if (blk == 512) return launch_trace<Eq3D<true>, 512>(ctx, a, st);
+            if (blk == 448) return launch_trace<Eq3D<true>, 448>(ctx, a, st);
+            if (blk == 416) return launch_trace<Eq3D<true>, 416>(ctx, a, st);
             return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 158 registers, no spills: 420 ms per config-2 pass vs 491 (256) / 494 (512); 416 / 448 lanes compile to 128 registers with spills
         }
 #ifdef GEOAC_HAVE_GLOBAL
@@ -849,6 +867,19 @@ extern "C" int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* t
 extern "C" int geoac_last_schedule(geoac_ctx* ctx, int64_t* out4) {
     if (!ctx || !out4) return GEOAC_ERR_BAD_ARG;
     out4[0] = ctx->last_rd_group; out4[1] = ctx->last_long_packets; out4[2] = ctx->last_long_ctas; out4[3] = ctx->last_launches;
+    return GEOAC_OK;
+}
+// Durations [ms] of the trace kernel launch(es) of the last trace, valid once the trace has completed: ms2[0] the main launch,
+// ms2[1] the concurrent long-region launch (0 if there was none).
+extern "C" int geoac_last_launch_ms(geoac_ctx* ctx, double* ms2) {
+    if (!ctx || !ms2) return GEOAC_ERR_BAD_ARG;
+    ms2[0] = ms2[1] = 0.0;
+    if (!ctx->timed_launches) return GEOAC_OK;
+    cudaSetDevice(ctx->device);
+    float a = 0.f, b = 0.f;
+    if (cudaEventElapsedTime(&a, ctx->ev_m0, ctx->ev_m1) == cudaSuccess) ms2[0] = a;
+    if (ctx->last_long_ctas > 0 && cudaEventElapsedTime(&b, ctx->ev_l0, ctx->ev_l1) == cudaSuccess) ms2[1] = b;
+    cudaGetLastError();
     return GEOAC_OK;
 }
 

@@ -274,6 +274,15 @@ struct LaunchConsts {
     double sbx3[2][6], sbx4[2][4], sbx6[2][6];
 };
 
+// GeoAc_Set_ds (3DStratified.cpp:191-198 and siblings): ds = clamp(0.05 - 0.049 exp(-h / 0.75), ds_min, ds_max), h = height above
+// ground.  Above 30 km the exponential term is below 2^-58, half an ulp of 0.05, so the rounded difference IS 0.05: the
+// polynomial is skipped there (a warp's rays have near-equal altitudes, so the branch rarely diverges) without changing a bit.
+GEOAC_HD double step_size_z(const LaunchConsts& L, double h) {
+    double r = 0.05;
+    if (h < 30.0) r = 0.05 - 0.049 * g_exp(-h * (1.0 / 0.75));
+    return fmax(fmin(r, L.ds_max), L.ds_min);
+}
+
 // log10 of the gas fractions as polynomials in altitude [km] (Atmo_State.Absorption.cpp:55-99); [0] = low branch, [1] = high branch
 GEOAC_CONST_TABLE double kSBX0[6] = { 49.296, -1.5524, 1.8714E-2, -1.1069E-4, 3.199E-7, -3.6211E-10 };                    // O2, z > 90
 GEOAC_CONST_TABLE double kSBX1[4] = { 1.3972E-1, -5.6269E-3, 3.9407E-5, -1.0737E-7 };                                       // N2, z > 76
@@ -287,8 +296,8 @@ GEOAC_CONST_TABLE double kSBX5[6] = { -53.746, 1.5439, -1.8824E-2, 1.1587E-4, -3
 //   * the remaining exponentials (gas fractions 10^poly(z), rotational collision numbers, vibrational Boltzmann factors)
 //     are evaluated in lock step by the branch-free g_exp_n; the polynomials in z are Horner forms;
 //   * every quotient is a product with one of five reciprocals (two of them batched inversions).
-// `parts` (table builder only): [0] = G2 with (a_cl + a_diff) * scale = sqrt(s1m1 * G2), [1] = (a_rot + a_vib) * scale, where
-// scale = tweak_abs * 8.685889 and s1m1 = sqrt(1 + nu^2) - 1 is the one non-smooth factor of the model (see below).
+// `parts` (table builder only): [0] = G2 with (a_cl + a_diff) * scale = sqrt(s1m1 * G2), [1] = (a_rot + a_vib) * scale, [2] = nu^2,
+// where scale = tweak_abs * 8.685889 and s1m1 = sqrt(1 + nu^2) - 1 is the one non-smooth factor of the model (see below).
 GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, double c, double inv_c, double rho, double* parts = nullptr) {
     const double mu_o = 18.192E-6, S = 117.0;
     const double inv_c2 = inv_c * inv_c;
@@ -428,6 +437,7 @@ GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, 
         const double sc2 = 1.003 * L.tweak_abs * 8.685889;
         parts[0] = (w_c * w_c) * (0.5 * cchi2p1 * (rq * q2)) * (sc2 * sc2);
         parts[1] = (a_rot + a_vib) * L.tweak_abs * 8.685889;
+        parts[2] = nu * nu;
     }
     return (a_cl + a_rot + a_diff + a_vib) * L.tweak_abs * 8.685889;
 }
@@ -442,7 +452,7 @@ GEOAC_HD double suthbass_alpha(const LaunchConsts& L, const SBRef& R, double z, 
 // An interval whose interpolants miss the exact function by more than 1e-12 relative at eight check points (a gas-fraction
 // threshold inside it, a coarse user profile) is flagged and evaluated exactly, as are queries outside the table.
 constexpr int SBP_DEG = 6;
-constexpr int SBP_STRIDE = 16;      // [0..6] G2 (monomials in s = 2X - 1), [7] flag (0 = valid), [8..14] S, [15] unused
+constexpr int SBP_STRIDE = 24;      // [0..6] G2 (monomials in s = 2X - 1), [7] flag (0 = valid), [8..14] S, [16..22] nu^2, [15], [23] unused
 
 #if defined(__CUDA_ARCH__)
 GEOAC_HD Pair ldg_pair(const double* p) { const double2 v = __ldg(reinterpret_cast<const double2*>(p)); Pair r; r.a = v.x; r.b = v.y; return r; }
@@ -457,42 +467,34 @@ __device__ __noinline__ double suthbass_alpha_cold(const LaunchConsts& L, double
 inline double suthbass_alpha_cold(const LaunchConsts& L, double z, double c, double inv_c, double rho) { return suthbass_alpha(L, L.sb, z, c, inv_c, rho); }
 #endif
 
-// absorption [dB/km] at the point seg_locate(T, zq, k) found (interval k, offset sp.X); z_eff = altitude the model sees
+// absorption [dB/km] at the point seg_locate(T, zq, k) found (interval k, offset sp.X); z_eff = altitude the model sees.
+// nu^2 (the viscous-to-pressure ratio squared: a smooth function of c and rho, hence of z) comes from its own interpolant; the
+// cancelling difference sqrt(1 + nu^2) - 1 is then formed exactly as the reference forms it, so its quantisation staircase
+// stays (a rounding-level change of nu^2 moves a step of the staircase by the same relative amount, nothing else).
 GEOAC_HD double sb_alpha_1d(const LaunchConsts& L, const Table1D& T, const SegPos& sp, int k, double zq, double z_eff, double c, double inv_c) {
-    const double rho = spl_f(T, TAB_RHO, sp);
     if (T.sbpoly != nullptr && zq >= T.xmin && zq <= T.xmax) {
         const double* q = T.sbpoly + (size_t)k * SBP_STRIDE;
-        const Pair g01 = ldg_pair(q), g23 = ldg_pair(q + 2), g45 = ldg_pair(q + 4), g67 = ldg_pair(q + 6);
-        const Pair s01 = ldg_pair(q + 8), s23 = ldg_pair(q + 10), s45 = ldg_pair(q + 12), s67 = ldg_pair(q + 14);
+        const Pair g67 = ldg_pair(q + 6);
         if (g67.b == 0.0) {
-            // nu exactly as suthbass_alpha computes it
-            const double S = 117.0, mu_o = 18.192E-6;
-            const double inv_c2 = inv_c * inv_c;
-            const double c2 = (c * c) * 1.0e6;
-            const double T_z = c2 * (1.0 / (kR * kGam));
-            const double inv_Tz = inv_c2 * (kR * kGam * 1.0e-6);
-            const double den1 = 1.0 + S * inv_Tz;
-            const double r1 = g_rcp(rho * den1);
-            const double inv_rho = r1 * den1, inv_den1 = r1 * rho;
-            const double inv_Pz = inv_rho * inv_c2 * (kGam * 1.0e-9);
-            const double sq = g_sqrt(T_z * L.sb.invTo);
-            const double mu_ratio = sq * (L.sb.visc_num * inv_den1);
-            const double nu = (8.0 * kPi * L.freq * mu_o * (1.0 / 3.0)) * mu_ratio * inv_Pz;
-            const double s1m1 = g_sqrt(1.0 + nu * nu) - 1.0;
+            const Pair g01 = ldg_pair(q), g23 = ldg_pair(q + 2), g45 = ldg_pair(q + 4);
+            const Pair s01 = ldg_pair(q + 8), s23 = ldg_pair(q + 10), s45 = ldg_pair(q + 12), s67 = ldg_pair(q + 14);
+            const Pair n01 = ldg_pair(q + 16), n23 = ldg_pair(q + 18), n45 = ldg_pair(q + 20), n67 = ldg_pair(q + 22);
             const double s = fma(2.0, sp.X, -1.0);
+            const double nu2 = fma(fma(fma(fma(fma(fma(n67.a, s, n45.b), s, n45.a), s, n23.b), s, n23.a), s, n01.b), s, n01.a);
             const double G2 = fma(fma(fma(fma(fma(fma(g67.a, s, g45.b), s, g45.a), s, g23.b), s, g23.a), s, g01.b), s, g01.a);
             const double Sm = fma(fma(fma(fma(fma(fma(s67.a, s, s45.b), s, s45.a), s, s23.b), s, s23.a), s, s01.b), s, s01.a);
+            const double s1m1 = g_sqrt(1.0 + nu2) - 1.0;
             return g_sqrt(fmax(s1m1 * G2, 1e-290)) + Sm;
         }
     }
-    return suthbass_alpha_cold(L, z_eff, c, inv_c, rho);
+    return suthbass_alpha_cold(L, z_eff, c, inv_c, spl_f(T, TAB_RHO, sp));
 }
 
 // Builds the SBP_STRIDE coefficients of interval k of a 1-D table (one thread per interval on the device).
 GEOAC_HD void sbpoly_build_interval(const LaunchConsts& L, const Table1D& T, bool glob, int k, double* out) {
     const double x0 = T.lvl(k)[TAB_X], x1 = T.lvl(k + 1)[TAB_X], h = x1 - x0;
-    double f[2][SBP_DEG + 1], a[2][SBP_DEG + 1];
-    auto eval = [&](double s, double* g2, double* sm) {
+    double f[3][SBP_DEG + 1], a[3][SBP_DEG + 1];
+    auto eval = [&](double s, double* g2, double* sm, double* n2) {
         double z = x0 + (0.5 * (s + 1.0)) * h;
         z = (z < x0) ? x0 : ((z > x1) ? x1 : z);
         int cur = k;
@@ -500,13 +502,13 @@ GEOAC_HD void sbpoly_build_interval(const LaunchConsts& L, const Table1D& T, boo
         const double Tv = spl_f(T, TAB_T, sp), rho = spl_f(T, TAB_RHO, sp);
         const double gT = kGamR * Tv;
         const double inv_c = g_rsqrt(gT), c = gT * inv_c;
-        double parts[2];
+        double parts[3];
         suthbass_alpha(L, L.sb, glob ? z - kREarth : z, c, inv_c, rho, parts);
-        *g2 = parts[0]; *sm = parts[1];
+        *g2 = parts[0]; *sm = parts[1]; *n2 = parts[2];
     };
     const int N = SBP_DEG + 1;
-    for (int j = 0; j < N; j++) eval(cos((2 * j + 1) * (kPi / (2.0 * N))), &f[0][j], &f[1][j]);
-    for (int w = 0; w < 2; w++) {
+    for (int j = 0; j < N; j++) eval(cos((2 * j + 1) * (kPi / (2.0 * N))), &f[0][j], &f[1][j], &f[2][j]);
+    for (int w = 0; w < 3; w++) {
         for (int m = 0; m < N; m++) {
             double acc = 0.0;
             for (int j = 0; j < N; j++) acc += f[w][j] * cos((double)(m * (2 * j + 1)) * (kPi / (2.0 * N)));
@@ -524,14 +526,14 @@ GEOAC_HD void sbpoly_build_interval(const LaunchConsts& L, const Table1D& T, boo
     bool bad = false;
     const double chk[8] = { -0.97, -0.75, -0.45, -0.15, 0.15, 0.45, 0.75, 0.97 };
     for (int j = 0; j < 8; j++) {
-        double e[2]; eval(chk[j], &e[0], &e[1]);
-        for (int w = 0; w < 2; w++) {
+        double e[3]; eval(chk[j], &e[0], &e[1], &e[2]);
+        for (int w = 0; w < 3; w++) {
             const double* o = out + 8 * w; const double s = chk[j];
             const double pv = o[0] + s * (o[1] + s * (o[2] + s * (o[3] + s * (o[4] + s * (o[5] + s * o[6])))));
             if (!(fabs(pv - e[w]) <= 1e-12 * fabs(e[w])) || !(e[w] > 0.0)) bad = true;
         }
     }
-    out[7] = bad ? 1.0 : 0.0; out[15] = 0.0;
+    out[7] = bad ? 1.0 : 0.0; out[15] = 0.0; out[23] = 0.0;
 }
 
 // fill the Sutherland-Bass invariants from the reference state (c, rho at the reference level)

@@ -53,13 +53,10 @@ struct Eq3D {
     }
 
     // GeoAc_Set_ds, 3DStratified.cpp:191-198
-    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {
-        double r = 0.05 - 0.049 * g_exp(-(y[2] - L.z_grnd) * (1.0 / 0.75));
-        return fmax(fmin(r, L.ds_max), L.ds_min);
-    }
+    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) { return step_size_z(L, y[2] - L.z_grnd); }
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, 3DStratified.cpp:203-310: all NEQ right-hand sides from ONE atmosphere sample
-    GEOAC_HD static void rhs(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* p, double* f, int& cur) {
+    GEOAC_HD static double rhs(const LaunchConsts& L, const Table1D& T, const RayC& rc, const double* p, double* f, int& cur) {
         const SegPos sp = seg_locate(T, p[2], cur);
         double Tv, dT, ddT, u, du, ddu, v, dv, ddv;
         if (AMP) {
@@ -82,10 +79,17 @@ struct Eq3D {
         const double inv_cpm = nu_mag * inv_q;
         const double cn = s.c * inv_nm;
         const double cp0 = q0 * inv_nm, cp1 = q1 * inv_nm, cp2 = q2 * inv_nm;
-        f[0] = q0 * inv_q; f[1] = q1 * inv_q; f[2] = q2 * inv_q;                   // dx/ds
         const double G = nu_mag * s.dc + rc.nx * du + rc.ny * dv;
-        f[3] = -G * inv_cpm;
-        if (AMP) {
+        if (!AMP) {
+            // every right-hand side carries 1/|q|: it is returned as the common factor and folded into the RK4 step factors
+            f[0] = q0; f[1] = q1; f[2] = q2;                                         // dx/ds = q / |q|
+            f[3] = -G * nu_mag;                                                       // -G / |c_prop|,  1/|c_prop| = nu_mag / |q|
+            return inv_q;
+        }
+        // with the auxiliary set the common factor is 1/|c_prop| (twelve multiplications per stage less)
+        f[0] = cp0; f[1] = cp1; f[2] = cp2;                                          // dx/ds = c_prop / |c_prop|
+        f[3] = -G;
+        {
             const double H = nu_mag * s.ddc + rc.nx * ddu + rc.ny * ddv;
 #pragma unroll
             for (int a = 0; a < 2; a++) {
@@ -98,12 +102,13 @@ struct Eq3D {
                 const double d2 = nz * q + cn * mz;
                 const double dcpm = cp0 * d0 + cp1 * d1 + cp2 * d2;                 // times inv_cpm below
                 const double g = dcpm * inv_cpm * inv_cpm;                          // d|cp| / |cp|
-                f[4 + 4 * a] = (d0 - cp0 * g) * inv_cpm;
-                f[5 + 4 * a] = (d1 - cp1 * g) * inv_cpm;
-                f[6 + 4 * a] = (d2 - cp2 * g) * inv_cpm;
-                f[7 + 4 * a] = (G * g - (dnm * s.dc + mx * du + my * dv + H * Z)) * inv_cpm;
+                f[4 + 4 * a] = d0 - cp0 * g;
+                f[5 + 4 * a] = d1 - cp1 * g;
+                f[6 + 4 * a] = d2 - cp2 * g;
+                f[7 + 4 * a] = G * g - (dnm * s.dc + mx * du + my * dv + H * Z);
             }
         }
+        return inv_cpm;
     }
 
     // BreakCheck / GroundCheck, 3DStratified.cpp:327-343 (strict inequalities on the unclamped state)
@@ -231,13 +236,10 @@ struct Eq2D {
         if (AMP) { y[3] = 0.0; y[4] = 0.0; y[5] = rc.costh; }
     }
 
-    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {   // 2DStratified.cpp:123-130
-        double r = 0.05 - 0.049 * g_exp(-(y[1] - L.z_grnd) * (1.0 / 0.75));
-        return fmax(fmin(r, L.ds_max), L.ds_min);
-    }
+    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) { return step_size_z(L, y[1] - L.z_grnd); }   // 2DStratified.cpp:123-130
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, 2DStratified.cpp:135-181
-    GEOAC_HD static void rhs(const LaunchConsts&, const Table1D& T, const RayC& rc, const double* p, double* f, int& cur) {
+    GEOAC_HD static double rhs(const LaunchConsts&, const Table1D& T, const RayC& rc, const double* p, double* f, int& cur) {
         const SegPos sp = seg_locate(T, p[1], cur);
         double Tv, dT, ddT, u, du, ddu, v, dv, ddv;
         if (AMP) {
@@ -266,6 +268,7 @@ struct Eq2D {
             const double dcc = dc * inv_c;
             f[5] = (2.0 * dcc * dcc - ddc * inv_c) * rc.ceff0 * inv_c * dzt;
         }
+        return 1.0;
     }
 
     GEOAC_HD static bool left_region(const LaunchConsts& L, const RayC&, const double* y) {   // 2DStratified.cpp:194-203

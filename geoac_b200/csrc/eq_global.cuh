@@ -55,13 +55,10 @@ struct EqGlobal {
     }
 
     // GeoAc_Set_ds, Global.cpp:210-217
-    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {
-        double r = 0.05 - 0.049 * g_exp(-(y[0] - L.ground) * (1.0 / 0.75));
-        return fmax(fmin(r, L.ds_max), L.ds_min);
-    }
+    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) { return step_size_z(L, y[0] - L.ground); }
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, Global.cpp:222-442
-    GEOAC_HD static void rhs(const LaunchConsts&, const Table1D& T, const RayC&, const double* p, double* f, int& cur) {
+    GEOAC_HD static double rhs(const LaunchConsts&, const Table1D& T, const RayC&, const double* p, double* f, int& cur) {
         const double r = p[0];
         const SegPos sp = seg_locate(T, r, cur);
         double Tv, dT, ddT, u, du, ddu, v, dv, ddv;
@@ -90,11 +87,12 @@ struct EqGlobal {
         const double GT0 = inv_r * nug;
         const double GT1 = nu0 * v - nu0 * g1 + nu2 * g2 * tant;
         const double GT2 = nu0 * u * ct + B * st - g2 * A;
-        f[0] = g0 * inv_cgm; f[1] = GC1 * g1 * inv_cgm; f[2] = GC2 * g2 * inv_cgm;
+        // every right-hand side carries 1/|c_g|: returned as the common factor and folded into the RK4 step factors
+        f[0] = g0; f[1] = GC1 * g1; f[2] = GC2 * g2;
         const double E0 = nm * s.dc + nu1 * dv + nu2 * du;
-        f[3] = -inv_cgm * (E0 + GT0);
-        f[4] = -inv_cgm * GC1 * GT1;
-        f[5] = -inv_cgm * GC2 * GT2;
+        f[3] = -(E0 + GT0);
+        f[4] = -GC1 * GT1;
+        f[5] = -GC2 * GT2;
         if (AMP) {
             const double inv_r2 = inv_r * inv_r, inv_ct2 = inv_ct * inv_ct;
 #pragma unroll
@@ -114,14 +112,15 @@ struct EqGlobal {
                 const double dGT1 = m0 * v + nu0 * dv_a - m0 * g1 - nu0 * d1 + (m2 * g2 + nu2 * d2) * tant + nu2 * g2 * R1 * inv_ct2;
                 const double dGT2 = (m0 * u + nu0 * du_a) * ct - nu0 * u * R1 * st + (m1 * u + nu1 * du_a - m2 * v - nu2 * dv_a) * st + B * R1 * ct
                                   - d2 * A - g2 * (m0 * ct - nu0 * R1 * st + m1 * st + nu1 * R1 * ct);
-                f[6 + 6 * a] = (d0 - g0 * gg) * inv_cgm;
-                f[7 + 6 * a] = (dGC1 * g1 + GC1 * (d1 - g1 * gg)) * inv_cgm;
-                f[8 + 6 * a] = (dGC2 * g2 + GC2 * (d2 - g2 * gg)) * inv_cgm;
-                f[9 + 6 * a]  = inv_cgm * (gg * E0 - (dnm * s.dc + nm * (R0 * s.ddc) + m1 * dv + m2 * du + nu1 * (R0 * ddv) + nu2 * (R0 * ddu) + dGT0));
-                f[10 + 6 * a] = -inv_cgm * (dGC1 * GT1 + GC1 * dGT1);
-                f[11 + 6 * a] = -inv_cgm * (dGC2 * GT2 + GC2 * dGT2);
+                f[6 + 6 * a] = d0 - g0 * gg;
+                f[7 + 6 * a] = dGC1 * g1 + GC1 * (d1 - g1 * gg);
+                f[8 + 6 * a] = dGC2 * g2 + GC2 * (d2 - g2 * gg);
+                f[9 + 6 * a]  = (gg * E0 - (dnm * s.dc + nm * (R0 * s.ddc) + m1 * dv + m2 * du + nu1 * (R0 * ddv) + nu2 * (R0 * ddu) + dGT0));
+                f[10 + 6 * a] = -(dGC1 * GT1 + GC1 * dGT1);
+                f[11 + 6 * a] = -(dGC2 * GT2 + GC2 * dGT2);
             }
         }
+        return inv_cgm;
     }
 
     // GeoAc_BreakCheck, Global.cpp:500-514: altitude limit and great-circle range from the source.

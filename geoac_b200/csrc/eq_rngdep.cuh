@@ -60,13 +60,10 @@ struct Eq3DRD {
         cur.kz = ms_find_cold(G.axz, G.nz, clampd(y[2], G.zmin, G.zmax));
     }
 
-    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {       // 3DRngDep.cpp:206-213
-        double r = 0.05 - 0.049 * g_exp(-(y[2] - L.z_grnd) * (1.0 / 0.75));
-        return fmax(fmin(r, L.ds_max), L.ds_min);
-    }
+    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) { return step_size_z(L, y[2] - L.z_grnd); }       // 3DRngDep.cpp:206-213
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, 3DRngDep.cpp:218-393
-    GEOAC_HD static void rhs(const LaunchConsts&, const Grid3D& G, const RayC&, const double* p, double* f, Cur3& cur) {
+    GEOAC_HD static double rhs(const LaunchConsts&, const Grid3D& G, const RayC&, const double* p, double* f, Cur3& cur) {
         double (&S)[3][10] = *reinterpret_cast<double (*)[3][10]>(G.scratch);      // per-thread block (shared memory on the device)
         ms_sample_tuv<false, AMP>(G, p[0], p[1], p[2], cur, S);
         const double* Tt = S[0]; const double* U = S[1]; const double* V = S[2];
@@ -78,10 +75,10 @@ struct Eq3DRD {
         const double cn = s.c * inv_nm;
         const double g0 = cn * nu0 + U[0], g1 = cn * nu1 + V[0], g2 = cn * nu2;
         const double inv_cgm = g_rsqrt(g0 * g0 + g1 * g1 + g2 * g2);
-        f[0] = g0 * inv_cgm; f[1] = g1 * inv_cgm; f[2] = g2 * inv_cgm;
+        f[0] = g0; f[1] = g1; f[2] = g2;          // every right-hand side carries 1/|c_g|: returned as the common factor
         double E[3];
 #pragma unroll
-        for (int n = 0; n < 3; n++) { E[n] = nm * dc[n] + nu0 * U[1 + n] + nu1 * V[1 + n]; f[3 + n] = -E[n] * inv_cgm; }
+        for (int n = 0; n < 3; n++) { E[n] = nm * dc[n] + nu0 * U[1 + n] + nu1 * V[1 + n]; f[3 + n] = -E[n]; }
         if (AMP) {
             // symmetric second-derivative index: (n,m) -> slot in the sampler's output
             // 0 f, 1 a, 2 b, 3 z, 4 aa, 5 bb, 6 zz, 7 ab, 8 az, 9 bz
@@ -98,18 +95,19 @@ struct Eq3DRD {
                 const double q = inv_nm * (dck - cn * dnm);
                 const double d0 = nu0 * q + cn * m0 + duk, d1 = nu1 * q + cn * m1 + dvk, d2 = nu2 * q + cn * m2;
                 const double gg = (g0 * d0 + g1 * d1 + g2 * d2) * inv_cgm * inv_cgm;
-                f[6 + 6 * k] = (d0 - g0 * gg) * inv_cgm;
-                f[7 + 6 * k] = (d1 - g1 * gg) * inv_cgm;
-                f[8 + 6 * k] = (d2 - g2 * gg) * inv_cgm;
+                f[6 + 6 * k] = d0 - g0 * gg;
+                f[7 + 6 * k] = d1 - g1 * gg;
+                f[8 + 6 * k] = d2 - g2 * gg;
 #pragma unroll
                 for (int n = 0; n < 3; n++) {
                     const double ddc = s.hg * (X0 * Tt[H[n][0]] + X1 * Tt[H[n][1]] + X2 * Tt[H[n][2]]) - s.hg2 * Tt[1 + n] * XdT;
                     const double ddu = X0 * U[H[n][0]] + X1 * U[H[n][1]] + X2 * U[H[n][2]];
                     const double ddv = X0 * V[H[n][0]] + X1 * V[H[n][1]] + X2 * V[H[n][2]];
-                    f[9 + 6 * k + n] = inv_cgm * (gg * E[n] - (dnm * dc[n] + nm * ddc + m0 * U[1 + n] + m1 * V[1 + n] + nu0 * ddu + nu1 * ddv));
+                    f[9 + 6 * k + n] = gg * E[n] - (dnm * dc[n] + nm * ddc + m0 * U[1 + n] + m1 * V[1 + n] + nu0 * ddu + nu1 * ddv);
                 }
             }
         }
+        return inv_cgm;
     }
 
     // GeoAc_BreakCheck / GeoAc_GroundCheck, 3DRngDep.cpp:451-472 (box from GeoAc_SetPropRegion)
@@ -265,13 +263,10 @@ struct EqGlobalRD {
         cur.kz = ms_find_cold(G.axz, G.nz, clampd(y[0], G.zmin, G.zmax));
     }
 
-    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) {       // GlobalRngDep.cpp:214-221
-        double r = 0.05 - 0.049 * g_exp(-(y[0] - L.ground) * (1.0 / 0.75));
-        return fmax(fmin(r, L.ds_max), L.ds_min);
-    }
+    GEOAC_HD static double step_size(const LaunchConsts& L, const double* y) { return step_size_z(L, y[0] - L.ground); }       // GlobalRngDep.cpp:214-221
 
     // GeoAc_UpdateSources + GeoAc_EvalSrcEq, GlobalRngDep.cpp:226-460
-    GEOAC_HD static void rhs(const LaunchConsts&, const Grid3D& G, const RayC&, const double* p, double* f, Cur3& cur) {
+    GEOAC_HD static double rhs(const LaunchConsts&, const Grid3D& G, const RayC&, const double* p, double* f, Cur3& cur) {
         double (&S)[3][10] = *reinterpret_cast<double (*)[3][10]>(G.scratch);      // per-thread block (shared memory on the device)
         ms_sample_tuv<true, AMP>(G, p[1], p[2], p[0], cur, S);
         const double* Tt = S[0]; const double* U = S[1]; const double* V = S[2];
@@ -295,10 +290,10 @@ struct EqGlobalRD {
         const double A = nu0 * ct + nu1 * st;
         const double B = nu1 * u - nu2 * v;
         const double GT[3] = { inv_r * nug, nu0 * v - nu0 * g1 + nu2 * g2 * tant, nu0 * u * ct + B * st - g2 * A };
-        f[0] = g0 * inv_cgm; f[1] = GC[1] * g1 * inv_cgm; f[2] = GC[2] * g2 * inv_cgm;
+        f[0] = g0; f[1] = GC[1] * g1; f[2] = GC[2] * g2;     // every right-hand side carries 1/|c_g|: returned as the common factor
         double E[3];
 #pragma unroll
-        for (int n = 0; n < 3; n++) { E[n] = nm * dc[n] + nu1 * dv[n] + nu2 * du[n]; f[3 + n] = -GC[n] * inv_cgm * (E[n] + GT[n]); }
+        for (int n = 0; n < 3; n++) { E[n] = nm * dc[n] + nu1 * dv[n] + nu2 * du[n]; f[3 + n] = -GC[n] * (E[n] + GT[n]); }
         if (AMP) {
             // second derivatives in (r, lat, lon) order from the sampler's (a = lat, b = lon, z = r) slots
             const int H[3][3] = { { 6, 8, 9 }, { 8, 4, 7 }, { 9, 7, 5 } };
@@ -321,20 +316,21 @@ struct EqGlobalRD {
                     m0 * v + nu0 * dvk - m0 * g1 - nu0 * d1 + (m2 * g2 + nu2 * d2) * tant + nu2 * g2 * R1 * inv_ct2,
                     (m0 * u + nu0 * duk) * ct - nu0 * u * R1 * st + (m1 * u + nu1 * duk - m2 * v - nu2 * dvk) * st + B * R1 * ct
                         - d2 * A - g2 * (m0 * ct - nu0 * R1 * st + m1 * st + nu1 * R1 * ct) };
-                f[6 + 6 * k] = (d0 - g0 * gg) * inv_cgm;
-                f[7 + 6 * k] = (dGC[1] * g1 + GC[1] * (d1 - g1 * gg)) * inv_cgm;
-                f[8 + 6 * k] = (dGC[2] * g2 + GC[2] * (d2 - g2 * gg)) * inv_cgm;
+                f[6 + 6 * k] = d0 - g0 * gg;
+                f[7 + 6 * k] = dGC[1] * g1 + GC[1] * (d1 - g1 * gg);
+                f[8 + 6 * k] = dGC[2] * g2 + GC[2] * (d2 - g2 * gg);
 #pragma unroll
                 for (int n = 0; n < 3; n++) {
                     const double ddc = s.hg * (R0 * Tt[H[n][0]] + R1 * Tt[H[n][1]] + R2 * Tt[H[n][2]]) - s.hg2 * Tt[D1[n]] * RdT;
                     const double ddu = R0 * U[H[n][0]] + R1 * U[H[n][1]] + R2 * U[H[n][2]];
                     const double ddv = R0 * V[H[n][0]] + R1 * V[H[n][1]] + R2 * V[H[n][2]];
                     // the second term carries E without GeoTerms, like the reference (GlobalRngDep.cpp EvalSrcEq)
-                    f[9 + 6 * k + n] = inv_cgm * (GC[n] * gg * E[n] - dGC[n] * (E[n] + GT[n])
-                                                  - GC[n] * (dnm * dc[n] + nm * ddc + m1 * dv[n] + m2 * du[n] + nu1 * ddv + nu2 * ddu + dGT[n]));
+                    f[9 + 6 * k + n] = GC[n] * gg * E[n] - dGC[n] * (E[n] + GT[n])
+                                   - GC[n] * (dnm * dc[n] + nm * ddc + m1 * dv[n] + m2 * du[n] + nu1 * ddv + nu2 * ddu + dGT[n]);
                 }
             }
         }
+        return inv_cgm;
     }
 
     // GeoAc_BreakCheck, GlobalRngDep.cpp:523-535 (altitude + lat/lon box); GroundCheck :537-545

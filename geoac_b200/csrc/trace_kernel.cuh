@@ -173,9 +173,9 @@ GEOAC_HD bool lane_advance(LaneD<EQ>& d, LaneI<EQ>& n, const LaunchConsts& L, co
     constexpr int kStageUnroll = (MEM || NEQ > 12) ? 1 : GEOAC_STAGE_UNROLL;
 #pragma unroll(kStageUnroll)
     for (int s = 0; s < 4; s++) {
-        EQ::rhs(L, T, d.rc, p, f, n.cur);
-        const double dsa = ds * ((s == 2) ? 1.0 : 0.5);
-        const double dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+        const double sc = EQ::rhs(L, T, d.rc, p, f, n.cur);     // right-hand sides up to their common factor (1 / |c_prop|)
+        const double dsa = (ds * ((s == 2) ? 1.0 : 0.5)) * sc;
+        const double dsb = (ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0))) * sc;
         if (MEM) {                                             // the record is shared by the lanes of a cooperative group
             double a_new[NEQ];
 #pragma unroll
@@ -326,8 +326,11 @@ template <class EQ> struct LaneLayout {
     static constexpr int STRIDE = (WORK + EXTRA) | 1;
 };
 
+// registers per lane: what one resident CTA of BLOCK lanes leaves (allocation granularity 8), stated explicitly because ptxas
+// otherwise settles on 128 for the 416 / 448-lane variants
+constexpr int lane_regs(int block) { return (65536 / block / 8) * 8 > 255 ? 255 : (65536 / block / 8) * 8; }
 template <class EQ, int BLOCK, bool TABLE_IN_SMEM, bool PATHS = false>
-__global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK) __maxnreg__(lane_regs(BLOCK)) trace_kernel(const __grid_constant__ TraceArgs a) {
     constexpr int NEQ = EQ::NEQ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [LaunchConsts][mbarrier][lane records: BLOCK x STRIDE doubles][table]
@@ -669,8 +672,8 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
         for (int i = 0; i < NEQ; i++) { acc[i] = y[i]; p[i] = y[i]; }
 #pragma unroll 1
         for (int s = 0; s < 4; s++) {
-            EQ::rhs(L, T, rc, p, f, cur);
-            const double dsa = ds * ((s == 2) ? 1.0 : 0.5), dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0));
+            const double sc = EQ::rhs(L, T, rc, p, f, cur);
+            const double dsa = ds * ((s == 2) ? 1.0 : 0.5) * sc, dsb = ds * ((s == 0 || s == 3) ? (1.0 / 6.0) : (1.0 / 3.0)) * sc;
 #pragma unroll
             for (int i = 0; i < NEQ; i++) { acc[i] = fma(f[i], dsb, acc[i]); p[i] = fma(f[i], dsa, y[i]); }
         }

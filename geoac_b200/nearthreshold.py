@@ -201,7 +201,9 @@ def check_against(got, want, variant, calc_amp, tainted, cond, rtol=1e-9, cond_f
             allow = np.full(rel.shape, rtol)
             r_f = np.zeros(rel.shape)
         else:
-            r_f = np.maximum(cond["resp"][f], cond["jac"]) if f == abi.F_AMPLITUDE else cond["resp"][f]
+            # the auxiliary states of an arrival are one coupled linear system: if any of them (or D, or the amplitude built from
+            # them) responds to the perturbation, the whole set is ill-conditioned there
+            r_f = np.maximum(np.maximum(cond["aux"], cond["amp"]), cond["jac"]) if f in auxf else cond["resp"][f]
             allow = np.maximum(rtol, cond_factor * r_f)
         over = rel > allow
         name = "amplitude" if f == abi.F_AMPLITUDE else (f"aux state {f}" if f in auxf else f"field {f}")

@@ -276,6 +276,8 @@ int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kern
  * 1 = equal inclination / neighbouring azimuth), out4[1] packets in the long region (predicted to outlast the pass on a loaded
  * SM), out4[2] CTAs of the concurrent launch that traced them on SMs of their own, out4[3] kernels enqueued. */
 int geoac_last_schedule(geoac_ctx* ctx, int64_t* out4);
+/* Durations [ms] of the trace kernel launch(es) of the last completed trace: ms2[0] main launch, ms2[1] long-region launch (or 0). */
+int geoac_last_launch_ms(geoac_ctx* ctx, double* ms2);
 
 /* Device self-test of the kernel's branch-free FP64 primitives against the CUDA math library on n_per_thread random
  * operands per thread: max_err[7] = maximum relative error of reciprocal, reciprocal square root, square root, exp, 10^x

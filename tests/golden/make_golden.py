@@ -77,6 +77,8 @@ CASES = {
                                                              x_src=13.7, y_src=-21.3, accum_mode=1, path_stride=25, caustics=1)),
     "globalrngdep_path": (abi.GEOAC_GLOBAL_RNGDEP, "grid_glob", dict(theta_min=12, theta_max=33, theta_step=20, phi_min=70, phi_max=70, phi_step=1, bounces=1,
                                                                      lat_src=33.3, lon_src=1.7, accum_mode=1, path_stride=25, caustics=1)),
+    # -interactive of GeoAc3D plots one ray with a row every 10 steps (Code/GeoAc3D_main.cpp:409)
+    "3d_interactive_path": (abi.GEOAC_3D, [TOY], dict(theta_min=40, theta_max=40, theta_step=1, phi_min=-45, phi_max=-45, phi_step=1, bounces=1, accum_mode=1, path_stride=10, caustics=1)),
     "3d_elevated": (abi.GEOAC_3D, [TOY], dict(theta_min=-10, theta_max=40, theta_step=10, azimuth=-60, bounces=2, z_src=12.5, z_grnd=1.2, freq=0.5, rng_max=600, alt_max=120)),
 }
 

@@ -130,6 +130,16 @@ def test_table_too_large_for_shared_memory_still_traces():
     m = a["status"] == abi.ST_ARRIVAL
     # the natural spline's end condition moves to the new top, which perturbs the slopes of the last original levels a little
     assert np.allclose(a["rec"][abi.F_TRAVELTIME][m], b["rec"][abi.F_TRAVELTIME][m], rtol=1e-6)
+    # raypath / caustic capture works for such a profile too (the reference's WriteRays mode has no size limit)
+    for t in (tr, big):
+        q = t.params
+        q.accum_per_segment = 1
+        t.params = q
+    pa, pb = tr.trace_paths(th, ph, 25, 2000, caustic_cap=16), big.trace_paths(th, ph, 25, 2000, caustic_cap=16)
+    assert (np.abs(pa["path_rows"] - pb["path_rows"]) <= 1).all() and pa["path_rows"].min() > 50
+    n0 = int(min(pa["path_rows"][0], pb["path_rows"][0])) - 2
+    assert np.allclose(pa["path"][0, :n0, :3], pb["path"][0, :n0, :3], rtol=1e-5, atol=1e-6)
+    assert np.array_equal(pa["caustic_rows"], pb["caustic_rows"])
 
 
 @pytest.mark.parametrize("glob", [False, True])
