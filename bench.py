@@ -43,7 +43,10 @@ KERNEL_NAMES = {V2D: "geoac::trace_kernel<Eq2D<true>,512,true>", V3D: "geoac::tr
 #  * SURVEY_FLOPS_PER_STEP: SURVEY 8d's provisional hand de-duplication of the REFERENCE's formulation (+-25 %); reported
 #    next to it as `achieved_survey_figure`.  The range-dependent figures differ most: the tensor-product sampler needs
 #    17-19 k operations where the reference's five-bicubic-patch scheme, de-duplicated, needs ~39 k.
-ALGO_FLOPS_PER_STEP = {V2D: 766.0, V3D: 1295.0, VGLOBAL: 2225.2, V3DRD: 16988.7, VGLOBALRD: 18613.4}
+ALGO_FLOPS_PER_STEP = {V2D: 739.6, V3D: 1220.2, VGLOBAL: 2126.3, V3DRD: 16922.0, VGLOBALRD: 18202.6}
+# the same count on the round-1 formulation (before the common factor of the right-hand sides moved into the step factors, the
+# nu^2 interpolant and the step-size shortcut removed ~6 % of the operations): reported next to it so that rounds stay comparable
+ALGO_FLOPS_PER_STEP_R1 = {V2D: 766.0, V3D: 1295.0, VGLOBAL: 2225.2, V3DRD: 16988.7, VGLOBALRD: 18613.4}
 NCU_DRAM_BYTES_PER_RAY = {"config2": 502.0}       # measured with ncu --set full, see roofline.traffic_source
 SURVEY_FLOPS_PER_STEP = {V2D: 1400.0, V3D: 2200.0, VGLOBAL: 2800.0, V3DRD: 39000.0, VGLOBALRD: 40000.0}
 
@@ -455,6 +458,8 @@ def run_ours(args):
                                             if args.workload in NCU_DRAM_BYTES_PER_RAY else None),
                          "kernel": KERNEL_NAMES[variant], "kernel_ms_per_launch": kern_ms,
                          "algorithmic_flops_per_rk4_step": flops_step,
+                         "frac_with_round1_flop_count": (ALGO_FLOPS_PER_STEP_R1[variant] * total_steps / (kern_ms * 1e-3) / 1e12 / peak_tf) if peak_tf > 0 else None,
+                         "round1_flops_per_rk4_step": ALGO_FLOPS_PER_STEP_R1[variant],
                          "achieved_survey_figure": SURVEY_FLOPS_PER_STEP[variant] * total_steps / (kern_ms * 1e-3) / 1e12,
                          "survey_flops_per_rk4_step": SURVEY_FLOPS_PER_STEP[variant],
                          "peak_source": "DFMA micro-benchmark run in this process (MEASURED_PEAKS.json has no FP64 entry); "

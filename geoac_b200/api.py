@@ -48,6 +48,9 @@ def lib():
         L.geoac_set_params.argtypes = [C.c_void_p, C.POINTER(GeoacParams)]
         L.geoac_trace.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip]
         L.geoac_trace_paths.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int64, _dp, _ip, C.c_int64, _dp, _ip]
+        _lp = C.POINTER(C.c_int64)
+        L.geoac_trace_paths_compact.argtypes = [C.c_void_p, C.c_int64, _dp, _dp, _dp, _ip, _ip, C.c_int, C.c_int64, C.c_int64, _dp, _lp,
+                                                C.c_int64, C.c_int64, _dp, _lp]
         L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.geoac_reserve.argtypes = [C.c_void_p, C.c_int64]
         L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
@@ -84,7 +87,7 @@ EXPORTED_SYMBOLS = [
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
     "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_eigenray_direct", "geoac_get_variant", "geoac_source_state",
-    "geoac_set_knob", "geoac_last_schedule", "geoac_last_launch_ms",
+    "geoac_set_knob", "geoac_last_schedule", "geoac_last_launch_ms", "geoac_trace_paths_compact",
     "geoac_create_multi", "geoac_multi_set_atmosphere_1d", "geoac_multi_set_atmosphere_3d", "geoac_multi_set_params", "geoac_trace_multi",
 ]
 
@@ -275,6 +278,31 @@ class Tracer:
                                             out["n_steps"].ctypes.data_as(_ip), stride, cap, _p(out["path"]),
                                             out["path_rows"].ctypes.data_as(_ip), caustic_cap, _p(out["caustic"]),
                                             out["caustic_rows"].ctypes.data_as(_ip)), "geoac_trace_paths")
+        return out
+
+    def trace_paths_compact(self, theta, phi, stride=25, cap=2400, caustic_cap=0, total_rows=None, total_events=None):
+        """trace_paths() with compacted rows: path [total][PATH_NF] + path_offset [n + 1] (ray i owns rows offset[i]:offset[i+1]),
+        likewise caustic / caustic_offset.  total_rows / total_events: output capacities in rows (default: generous estimates;
+        grown and retried once if the library reports they were too small)."""
+        theta = np.ascontiguousarray(theta, dtype=np.float64)
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
+        n = len(theta)
+        n_rec = self.params.bounces + 1
+        out = {"rec": np.empty((abi.NFIELDS, n, n_rec)), "status": np.empty((n, n_rec), dtype=np.int32), "n_steps": np.empty((n, n_rec), dtype=np.int32)}
+        total_rows = total_rows if total_rows is not None else max(1, n * min(cap, 1024)) if stride > 0 else 1
+        total_events = total_events if total_events is not None else max(1, n * min(max(caustic_cap, 1), 8))
+        for attempt in range(2):
+            path = np.zeros((max(total_rows, 1), abi.PATH_NF)); poff = np.zeros(n + 1, dtype=np.int64)
+            caus = np.zeros((max(total_events, 1), abi.CAUSTIC_NF)); coff = np.zeros(n + 1, dtype=np.int64)
+            rc = lib().geoac_trace_paths_compact(self._h, n, _p(theta), _p(phi), _p(out["rec"]), out["status"].ctypes.data_as(_ip), out["n_steps"].ctypes.data_as(_ip),
+                                                 stride, cap, total_rows, _p(path), poff.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                 caustic_cap, total_events, _p(caus), coff.ctypes.data_as(C.POINTER(C.c_int64)))
+            if rc == abi.GEOAC_ERR_TOO_LARGE and attempt == 0:
+                total_rows, total_events = max(total_rows, int(poff[-1])), max(total_events, int(coff[-1]))
+                continue
+            self._check(rc, "geoac_trace_paths_compact")
+            break
+        out.update(path=path[: poff[-1]], path_offset=poff, caustic=caus[: coff[-1]], caustic_offset=coff)
         return out
 
     def reserve(self, n_rays):

@@ -47,6 +47,7 @@ struct Knobs {
     int long_sm_pct = 50;   // at most this share of the SMs is given to the long-region launch
     int exclusive = 1;      // long-region launch keeps its SMs to itself (0: one launch, long packets first)
     int rd_ctas = 0;        // range-dependent sets: CTAs per SM of the main launch (0 = as many as fit)
+    int scout_stride = 0;   // the cost scout traces every N-th ray of the batch (0 = default: every ray; measured on config 2: every 4th ray costs 24 % -- the warps' rays stop ending together)
 };
 static int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
 static Knobs knobs_from_env() {
@@ -60,6 +61,7 @@ static Knobs knobs_from_env() {
     k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 8 ? 8 : 32;
     k.long_sm_pct = std::min(90, std::max(1, env_int("GEOAC_B200_LONG_SM_PCT", k.long_sm_pct))); k.exclusive = env_int("GEOAC_B200_EXCLUSIVE", k.exclusive);
     k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas));
+    k.scout_stride = std::max(0, env_int("GEOAC_B200_SCOUT_STRIDE", k.scout_stride));
     return k;
 }
 
@@ -199,6 +201,7 @@ extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
     else if (n == "rd_group") k.rd_group = value; else if (n == "long_alpha") k.long_alpha = std::max(1, value);
     else if (n == "long_width") k.long_width = (value == 8) ? 8 : 32; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
     else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value);
+    else if (n == "scout_stride") k.scout_stride = std::max(0, value);
     else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
     return GEOAC_OK;
 }
@@ -557,11 +560,12 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             CK(cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s_smem));
             int s_per_sm = 1;
             CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&s_per_sm, sfn, kScoutBlock, s_smem));
-            const int64_t s_need = (a.n_rays + kScoutBlock - 1) / kScoutBlock;
+            int stride = ctx->knobs.scout_stride > 0 ? ctx->knobs.scout_stride : 1;
+            const int64_t s_need = ((a.n_rays + stride - 1) / stride + kScoutBlock - 1) / kScoutBlock;
             const int sblocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * std::max(1, s_per_sm), s_need);
             unsigned long long* scounter = ctx->d_counters + 3;
             int coarse = ctx->knobs.scout_coarse > 0 ? ctx->knobs.scout_coarse : (kGrid ? kScoutCoarse : 2 * kScoutCoarse);   // stratified: 32x measured best (404.8 vs 421.0 / 443.3 ms at 16x / 64x)
-            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse };
+            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse, (void*)&stride };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
         }
         // Range-dependent sets: which 32 rays make a packet (trace_kernel.cuh: grid_shape_kernel).  The choice only schedules.
@@ -733,9 +737,11 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
             const int blk = ctx->knobs.block3d;
             if (blk == 256) return launch_trace<Eq3D<true>, 256>(ctx, a, st);
             if (blk == 512) return launch_trace<Eq3D<true>, 512>(ctx, a, st);
-            if (blk == 448) return launch_trace<Eq3D<true>, 448>(ctx, a, st);
-            if (blk == 416) return launch_trace<Eq3D<true>, 416>(ctx, a, st);
-            return launch_trace<Eq3D<true>, 384>(ctx, a, st);      // 158 registers, no spills: 420 ms per config-2 pass vs 491 (256) / 494 (512); 416 / 448 lanes compile to 128 registers with spills
+            // 384 lanes = 3 warps per scheduler at <= 168 registers, no spills (420 ms per config-2 pass vs 491 (256) / 494 (512) in round 1).
+            // Nothing in between exists: the register file is four 16 K-register banks, one per scheduler, so 13 or 14 warps put 4
+            // on some scheduler and cap every lane at 128 registers -- the 512-lane case, which spills (measured on B200: 416 / 448
+            // lanes at 152 / 144 registers compile without spills but do not fit on an SM).
+            return launch_trace<Eq3D<true>, 384>(ctx, a, st);
         }
 #ifdef GEOAC_HAVE_GLOBAL
         case GEOAC_GLOBAL: return amp ? launch_trace<EqGlobal<true>, 384>(ctx, a, st) : launch_trace<EqGlobal<false>, 512>(ctx, a, st);
@@ -859,6 +865,100 @@ extern "C" int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* t
     if (path_stride < 0 || caustic_cap < 0 || (path_stride == 0 && caustic_cap == 0))
         return ctx ? fail(ctx, GEOAC_ERR_BAD_ARG, "ask for raypath rows (path_stride > 0) and / or caustic events (caustic_cap > 0)") : GEOAC_ERR_BAD_ARG;
     return trace_host(ctx, n_rays, theta, phi, rec, status, n_steps, path_stride, path_cap, path, path_rows, caustic_cap, caustic, caustic_rows);
+}
+
+// ---- compacted raypath / caustic rows: only the rows produced cross PCIe ----
+__global__ void compact_rows_kernel(const double* dense, const int32_t* rows, const int64_t* offs, int64_t n, int64_t cap, int nf, double* out) {
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int64_t r = warp; r < n; r += nwarps) {
+        const int64_t m = (rows[r] < cap ? rows[r] : cap) * nf;
+        const double* src = dense + r * cap * nf;
+        double* dst = out + offs[r] * nf;
+        for (int64_t i = lane; i < m; i += 32) dst[i] = src[i];
+    }
+}
+
+extern "C" int geoac_trace_paths_compact(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                                         double* rec, int32_t* status, int32_t* n_steps,
+                                         int path_stride, int64_t path_cap, int64_t path_total_cap, double* path, int64_t* path_offset,
+                                         int64_t caustic_cap, int64_t caustic_total_cap, double* caustic, int64_t* caustic_offset) {
+    if (!ctx || n_rays < 0) return GEOAC_ERR_BAD_ARG;
+    if (path_stride < 0 || caustic_cap < 0 || (path_stride == 0 && caustic_cap == 0))
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "ask for raypath rows (path_stride > 0) and / or caustic events (caustic_cap > 0)");
+    if (path_stride > 0 && (path_cap <= 0 || !path || !path_offset)) return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath capture needs its buffers and a positive per-ray capacity");
+    if (caustic_cap > 0 && (!caustic || !caustic_offset)) return fail(ctx, GEOAC_ERR_BAD_ARG, "caustic capture needs its buffers");
+    if (n_rays > 0 && (!theta || !phi || !rec || !status || !n_steps)) return GEOAC_ERR_BAD_ARG;
+    if (caustic_cap > 0 && !ctx->prm.calc_amp) return fail(ctx, GEOAC_ERR_BAD_ARG, "caustic capture needs calc_amp = 1 (the Jacobian uses the auxiliary equations)");
+    if (ctx->variant != GEOAC_2D && !ctx->prm.accum_per_segment)
+        return fail(ctx, GEOAC_ERR_BAD_ARG, "raypath / caustic rows need accum_per_segment = 1 (the mains' WriteRays accumulation, SURVEY App. A-2)");
+    if (path_stride > 0) path_offset[0] = 0;
+    if (caustic_cap > 0) caustic_offset[0] = 0;
+    if (n_rays == 0) return GEOAC_OK;
+    if (!ctx->have_atmo) return fail(ctx, GEOAC_ERR_NO_ATMO, "set an atmosphere first");
+    cudaSetDevice(ctx->device);
+    const int n_rec = ctx->prm.bounces + 1;
+    const int64_t n_slots = n_rays * n_rec;
+    int rsv = reserve_staging(ctx, n_rays);
+    if (rsv) return rsv;
+    PathArgs pa;
+    cudaStream_t st = ctx->stream;
+    if (path_stride > 0) {
+        const size_t need = (size_t)n_rays * path_cap * GEOAC_PATH_NF * sizeof(double);
+        int g1 = grow(ctx, (void**)&ctx->d_path, &ctx->cap_path, need); if (g1) return g1;
+        int g2 = grow(ctx, (void**)&ctx->d_path_rows, &ctx->cap_path_rows, sizeof(int32_t) * n_rays); if (g2) return g2;
+        CK(cudaMemsetAsync(ctx->d_path_rows, 0, sizeof(int32_t) * n_rays, st));
+        pa.path = ctx->d_path; pa.rows = ctx->d_path_rows; pa.stride = path_stride; pa.cap = path_cap;
+    }
+    if (caustic_cap > 0) {
+        const size_t need = (size_t)n_rays * caustic_cap * GEOAC_CAUSTIC_NF * sizeof(double);
+        int g1 = grow(ctx, (void**)&ctx->d_caus, &ctx->cap_caus, need); if (g1) return g1;
+        int g2 = grow(ctx, (void**)&ctx->d_caus_rows, &ctx->cap_caus_rows, sizeof(int32_t) * n_rays); if (g2) return g2;
+        CK(cudaMemsetAsync(ctx->d_caus_rows, 0, sizeof(int32_t) * n_rays, st));
+        pa.caus = ctx->d_caus; pa.caus_rows = ctx->d_caus_rows; pa.caus_cap = caustic_cap;
+    }
+    CK(cudaMemcpyAsync(ctx->d_theta, theta, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->d_phi, phi, sizeof(double) * n_rays, cudaMemcpyHostToDevice, st));
+    int rc = refresh_consts(ctx);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev0, st));
+    rc = enqueue_trace(ctx, n_rays, ctx->d_theta, ctx->d_phi, ctx->d_rec, ctx->d_status, ctx->d_nsteps, st, pa);
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev1, st));
+    CK(cudaMemcpyAsync(rec, ctx->d_rec, sizeof(double) * GEOAC_NFIELDS * n_slots, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, ctx->d_status, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(n_steps, ctx->d_nsteps, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToHost, st));
+    // per-ray row counts -> offsets on the host (n_rays integers), rows gathered on the device, only those copied out
+    std::vector<int32_t> h_rows((size_t)n_rays);
+    int64_t* d_offs = nullptr; double* d_out = nullptr;
+    auto cleanup = [&]() { cudaFree(d_offs); cudaFree(d_out); };
+    auto compact = [&](const int32_t* d_rows, const double* d_dense, int64_t cap, int nf, int64_t total_cap, double* out, int64_t* offs, const char* what) -> int {
+        if (cudaMemcpyAsync(h_rows.data(), d_rows, sizeof(int32_t) * n_rays, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            return fail(ctx, GEOAC_ERR_CUDA, std::string(what) + ": row counts: " + cudaGetErrorString(cudaGetLastError()));
+        offs[0] = 0;
+        for (int64_t i = 0; i < n_rays; i++) offs[i + 1] = offs[i] + std::min<int64_t>(h_rows[(size_t)i], cap);
+        const int64_t total = offs[n_rays];
+        if (total > total_cap) return fail(ctx, GEOAC_ERR_TOO_LARGE, std::string(what) + ": " + std::to_string(total) + " rows produced, buffer holds " + std::to_string(total_cap)
+                                                                     + " (the offsets are filled in: the last one is the size to allocate)");
+        if (total == 0) return GEOAC_OK;
+        cudaFree(d_offs); cudaFree(d_out); d_offs = nullptr; d_out = nullptr;
+        if (cudaMalloc(&d_offs, sizeof(int64_t) * (n_rays + 1)) != cudaSuccess || cudaMalloc(&d_out, sizeof(double) * total * nf) != cudaSuccess)
+            return fail(ctx, GEOAC_ERR_CUDA, std::string(what) + ": out of device memory");
+        if (cudaMemcpyAsync(d_offs, offs, sizeof(int64_t) * (n_rays + 1), cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(ctx, GEOAC_ERR_CUDA, "offset upload");
+        compact_rows_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(d_dense, d_rows, d_offs, n_rays, cap, nf, d_out);
+        if (cudaMemcpyAsync(out, d_out, sizeof(double) * total * nf, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            return fail(ctx, GEOAC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()));
+        return GEOAC_OK;
+    };
+    if (path_stride > 0) { rc = compact(ctx->d_path_rows, ctx->d_path, path_cap, GEOAC_PATH_NF, path_total_cap, path, path_offset, "raypath rows"); if (rc) { cleanup(); return rc; } }
+    if (caustic_cap > 0) { rc = compact(ctx->d_caus_rows, ctx->d_caus, caustic_cap, GEOAC_CAUSTIC_NF, caustic_total_cap, caustic, caustic_offset, "caustic rows"); if (rc) { cleanup(); return rc; } }
+    unsigned long long cnt[2] = { 0, 0 };
+    cudaMemcpyAsync(cnt, ctx->d_counters, sizeof cnt, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cleanup();
+    float ms = 0.f; cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    ctx->last_ms = ms; ctx->last_steps = (int64_t)cnt[1];
+    return GEOAC_OK;
 }
 
 // Scheduling facts of the last trace (range-dependent sets): out[0] packet grouping used (0 = consecutive rays, 1 = equal

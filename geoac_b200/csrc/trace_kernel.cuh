@@ -326,11 +326,8 @@ template <class EQ> struct LaneLayout {
     static constexpr int STRIDE = (WORK + EXTRA) | 1;
 };
 
-// registers per lane: what one resident CTA of BLOCK lanes leaves (allocation granularity 8), stated explicitly because ptxas
-// otherwise settles on 128 for the 416 / 448-lane variants
-constexpr int lane_regs(int block) { return (65536 / block / 8) * 8 > 255 ? 255 : (65536 / block / 8) * 8; }
 template <class EQ, int BLOCK, bool TABLE_IN_SMEM, bool PATHS = false>
-__global__ void __launch_bounds__(BLOCK) __maxnreg__(lane_regs(BLOCK)) trace_kernel(const __grid_constant__ TraceArgs a) {
+__global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__ TraceArgs a) {
     constexpr int NEQ = EQ::NEQ;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     // layout: [LaunchConsts][mbarrier][lane records: BLOCK x STRIDE doubles][table]
@@ -622,7 +619,7 @@ template <class EQ> struct ScoutBlock { static constexpr int value = std::is_sam
 // in registers.
 template <class EQ, bool TABLE_IN_SMEM>
 __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const __grid_constant__ TraceArgs a, uint32_t* cost, uint32_t* cost_max,
-                                                               unsigned long long* cost_sum, unsigned long long* counter, int coarse) {
+                                                               unsigned long long* cost_sum, unsigned long long* counter, int coarse, int stride) {
     constexpr int NEQ = EQ::NEQ;
     constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -654,7 +651,9 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
             if ((int)lane == leader) base = atomicAdd(counter, (unsigned long long)__popc(wmask));
             base = __shfl_sync(0xffffffffu, base, leader);
             if (want) {
-                ray = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
+                // every `stride`-th ray is scouted; its neighbours in the batch (neighbouring launch angles) inherit the estimate --
+                // the cost only orders the claims, and it varies smoothly along the launch grid
+                ray = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u))) * stride;
                 if (ray < a.n_rays) {
                     cur = typename EQ::Cursor{};
                     EQ::init(L, T, a.theta[ray], a.phi[ray], rc, y, cur);
@@ -689,7 +688,10 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
                 bounce++; seg = 0;
             }
         }
-        if (done) { cost[ray] = est; worst = max(worst, est); total += est; have_ray = false; }
+        if (done) {
+            for (int j = 0; j < stride && ray + j < a.n_rays; j++) { cost[ray + j] = est; total += est; }
+            worst = max(worst, est); have_ray = false;
+        }
         else {
 #pragma unroll
             for (int i = 0; i < NEQ; i++) { ym1[i] = y[i]; y[i] = acc[i]; }

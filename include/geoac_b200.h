@@ -166,6 +166,17 @@ int geoac_trace_paths(geoac_ctx* ctx, int64_t n_rays, const double* theta, const
                       int path_stride, int64_t path_cap, double* path, int32_t* path_rows,
                       int64_t caustic_cap, double* caustic, int32_t* caustic_rows);
 
+/* geoac_trace_paths with COMPACTED rows: ray i's raypath rows are path[path_offset[i] .. path_offset[i+1]) (rows of
+ * GEOAC_PATH_NF doubles), its caustic events caustic[caustic_offset[i] .. caustic_offset[i+1]) (GEOAC_CAUSTIC_NF doubles);
+ * path_offset / caustic_offset hold n_rays + 1 entries.  The rows are gathered on the device, so only rows that exist cross
+ * PCIe (WriteRays=True on a config-2-size batch: 1.2 GB instead of the 3.3 GB of the dense [ray][cap] layout).  path_cap /
+ * caustic_cap still bound the rows kept PER RAY; *_total_cap are the capacities of the output buffers in rows -- if one is too
+ * small the call returns GEOAC_ERR_TOO_LARGE with the offsets filled in (the last offset is the number of rows to allocate). */
+int geoac_trace_paths_compact(geoac_ctx* ctx, int64_t n_rays, const double* theta, const double* phi,
+                              double* rec, int32_t* status, int32_t* n_steps,
+                              int path_stride, int64_t path_cap, int64_t path_total_cap, double* path, int64_t* path_offset,
+                              int64_t caustic_cap, int64_t caustic_total_cap, double* caustic, int64_t* caustic_offset);
+
 /* ---- several devices behind one call (the data-parallel axis is the launch-angle loop, Code/GeoAc3D_main.cpp:226-227) ----
  * A front end creates one context per device (geoac_create_multi, or geoac_create in a loop), gives every context the same
  * atmosphere and parameters (the geoac_multi_set_* helpers do that from one host thread per context) and traces with
@@ -294,7 +305,7 @@ int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t 
 /* Tuning / experiment knobs of a context.  Their defaults are read from the GEOAC_B200_* environment
  * variables ONCE, in geoac_create; nothing on the launch path reads the environment.  Names: "lpt" (claim order: 0 natural,
  * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables",
- * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive".
+ * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride".
  * No knob changes a record bit except "sbpoly" (absorption sum to 1e-11) -- that is what the tests use them to prove. */
 int geoac_set_knob(geoac_ctx* ctx, const char* name, int value);
 

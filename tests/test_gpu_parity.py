@@ -76,6 +76,13 @@ def test_cuda_raypath_rows_match_reference(name):
     want = {"rec": d["rec"], "status": d["status"], "n_steps": d["n_steps"]}
     rp, _, _, _ = _verdict(tr, variant, th, ph, out, want, name)
     assert not (problems + rp), "\n".join((problems + rp)[:10])
+    # compacted rows (geoac_trace_paths_compact): the same rows, ray after ray, with offsets; a too-small buffer is reported and retried
+    cp = tr.trace_paths_compact(th, ph, int(kv["path_stride"]), cap, caustic_cap=32, total_rows=7)
+    assert np.array_equal(np.diff(cp["path_offset"]), out["path_rows"]) and np.array_equal(np.diff(cp["caustic_offset"]), out["caustic_rows"])
+    for i in range(len(th)):
+        assert np.array_equal(cp["path"][cp["path_offset"][i]:cp["path_offset"][i + 1]], out["path"][i, :out["path_rows"][i]])
+        assert np.array_equal(cp["caustic"][cp["caustic_offset"][i]:cp["caustic_offset"][i + 1]], out["caustic"][i, :out["caustic_rows"][i]])
+    assert np.array_equal(cp["rec"], out["rec"]) and np.array_equal(cp["status"], out["status"])
     # a row capacity that is too small drops the surplus rows but still reports how many were produced
     small = tr.trace_paths(th, ph, int(kv["path_stride"]), 5)
     assert np.array_equal(small["path_rows"], want_rows) and np.array_equal(small["path"][:, :5], out["path"][:, :5])
