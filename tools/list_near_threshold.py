@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--every", type=int, default=100, help="trace every N-th ray of the launch grid")
     ap.add_argument("--eps", type=float, default=1e-6)
     ap.add_argument("--delta", type=float, default=1e-10)
-    ap.add_argument("--sens", type=float, default=1e-9)
+    ap.add_argument("--sens", type=float, default=1e-7, help="list arrivals whose amplitude or auxiliary states move by more than this (relative) under the perturbation")
     ap.add_argument("--limit", type=int, default=200)
     a = ap.parse_args()
     variant = bench.WORKLOADS[a.workload][0]
