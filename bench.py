@@ -309,8 +309,10 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a B200: the product has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        cpu_group = dist.new_group(backend="gloo")                    # host-side barrier: an NCCL barrier spins ON the waiting ranks' GPUs
     dev = torch.device("cuda", local)
 
     variant = WORKLOADS[args.workload][0]
@@ -421,11 +423,12 @@ def run_ours(args):
     multi = None
     if world > 1 and args.workload in ("config1", "config2") and not args.rays_cap:
         barrier()
-        if rank == 0:
+        if rank == 0:                                                    # the other ranks wait on the HOST (gloo): their GPUs stay idle for rank 0
             try:
                 multi = single_process_multi_record(args, world)
             except Exception as e:                                       # reported, never fatal for the bench line
                 multi = {"error": str(e)}
+        dist.barrier(group=cpu_group)
         barrier()
     strong = None
     if not args.no_strong and args.workload == "config2" and not args.rays_cap:

@@ -86,6 +86,37 @@ def config5_grid(nlat=181, nlon=361, nr=300, lat_deg=None, lon_deg=None):
     return lat, lon, z, np.ascontiguousarray(T), np.ascontiguousarray(u), np.ascontiguousarray(v), np.ascontiguousarray(rho)
 
 
+def _roundtrip(vals, fmt):
+    """What strtod returns for the text `fmt % value` -- exactly (a few hundred values: node coordinates, levels, density)."""
+    return np.array([float(fmt % v) for v in np.asarray(vals, dtype=np.float64)])
+
+
+def config4_grid_from_files(nx=200, ny=200, nz=300):
+    """The config-4 grid EXACTLY as the reference's loader hands it to the spline builder when it reads the node files that
+    write_config4_files() writes: node fields rounded to the files' six decimals, node coordinates / levels / density through the
+    text round trip, winds converted to km/s with the loader's ground taper (Code/Atmo/G2S_MultiDimSpline3D.cpp:139-189).
+    Bit-identical to load_met_grid() on those 40 000 files (checked when the golden vector was made, tests/golden/make_golden.py),
+    without writing them: this is the grid the full-size reference golden `3drngdep_c4full` was traced on."""
+    import math
+    xs, ys = np.linspace(-500.0, 500.0, nx), np.linspace(-500.0, 500.0, ny)
+    z = np.arange(nz) * 0.5
+    T0, u0, v0, rho0, _ = base_profile(z)
+    # per-node factors with the SAME scalar calls the file writer makes (_raw_cart)
+    fT = np.array([[1.0 + 0.02 * np.sin(2 * np.pi * x / 700.0) * np.cos(2 * np.pi * y / 900.0) for y in ys] for x in xs])
+    fu = np.array([1.0 + 0.2 * np.cos(2 * np.pi * x / 600.0) for x in xs])
+    sv = np.array([8.0 * np.sin(2 * np.pi * y / 800.0) for y in ys])
+    gz = np.exp(-(((z - 50.0) / 20.0) ** 2))
+    T = T0[None, None, :] * fT[:, :, None]
+    u = np.broadcast_to((u0[None, :] * fu[:, None])[:, None, :], T.shape)
+    v = np.broadcast_to((v0[None, :] + sv[:, None] * gz[None, :])[None, :, :], T.shape)
+    q = lambda a: np.rint(a * 1e6) / 1e6                                  # "%.6f" and back
+    zq = _roundtrip(z, "%.1f")
+    tap = np.array([(2.0 / (1.0 + math.exp(-(zz - 0.0) / 0.05)) - 1.0) / 1000.0 for zz in zq])
+    rho = np.broadcast_to(_roundtrip(rho0 / 1.0, "%.6e")[None, None, :], T.shape)
+    return (_roundtrip(xs, "%.6f"), _roundtrip(ys, "%.6f"), zq, np.ascontiguousarray(q(T)),
+            np.ascontiguousarray(q(u) * tap[None, None, :]), np.ascontiguousarray(q(v) * tap[None, None, :]), np.ascontiguousarray(rho))
+
+
 # ---- the same atmospheres as .met node files (file units: m/s, g/cm^3, mbar), for the reference binaries / golden vectors ----
 def _raw_cart(x, y, z):
     T0, u0, v0, rho0, p0 = base_profile(z)

@@ -83,6 +83,14 @@ CASES = {
 }
 
 
+# The full-size config-4 golden (`3drngdep_c4full`: the unmodified reference on the 200 x 200 x 300 node grid of BASELINE config 4) is
+# not made by main(): write the 40 000 node files with synth.write_config4_files("/tmp/c4", linspace(-500, 500, 200) twice, 300), check
+# that oracle.load_met_grid on them equals synth.config4_grid_from_files() bit for bit (it does: all seven arrays), run
+#   (ulimit -s unlimited; oracle/_ref/ref_3drngdep /tmp/c4full.bin /tmp/c4/p /tmp/c4/x.loc /tmp/c4/y.loc theta_min=6 theta_max=46
+#    theta_step=10 phi_min=20 phi_max=200 phi_step=140 bounces=2 x_src=0 y_src=0)
+# (24 s load, 12 s for the 10 rays) and store pyoracle.read_ref_bin("/tmp/c4full.bin") with grid = "synth:config4_grid_from_files".
+
+
 def main(names):
     for name in names:
         variant, prof, kv = CASES[name]

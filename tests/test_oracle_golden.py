@@ -94,7 +94,7 @@ def test_golden_has_reference_invariants():
 
 
 @pytest.mark.parametrize("name", ["3d_elevated", "2d_noamp", "3d_noamp", "global_segmode", "3drngdep_sub", "globalrngdep_sub",
-                                  "global_c3", "3drngdep_c4", "globalrngdep_c5"])
+                                  "global_c3", "3drngdep_c4", "globalrngdep_c5", "3drngdep_c4full"])
 def test_device_math_host_emulation(oracle, name):
     """The per-ray device code (geoac_b200/csrc/*.cuh, GEOAC_HD) compiled with g++ -mfma must agree with the reference
     golden vectors to the GPU tolerance.  This is a build-container debugging aid, not a product path; the real gate

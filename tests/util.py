@@ -27,7 +27,13 @@ def is_rngdep(variant):
 
 def load_grid(d):
     """The synthetic range-dependent grid a golden case was traced on: ax0, ax1, axz, T, u, v, rho (as the loader returns them)."""
-    g = np.load(os.path.join(GOLD, str(d["grid"]) + ".npz"))
+    name = str(d["grid"])
+    if name.startswith("synth:"):
+        # a full-size grid regenerated in memory, bit-identical to what the reference's loader reads from the node files the golden
+        # vector was traced on (geoac_b200/synth.py: checked against load_met_grid on those 40 000 files when the vector was made)
+        from geoac_b200 import synth
+        return list(getattr(synth, name.split(":", 1)[1])())
+    g = np.load(os.path.join(GOLD, name + ".npz"))
     return [g[k] for k in ("ax0", "ax1", "axz", "T", "u", "v", "rho")]
 
 
