@@ -334,11 +334,11 @@ class Tracer:
 
     def last_schedule(self):
         """Scheduling facts of the last trace: packet grouping, long-region packets, exclusive long-region CTAs, kernels."""
-        o = (C.c_int64 * 4)()
+        o = (C.c_int64 * 8)()
         self._check(lib().geoac_last_schedule(self._h, o), "geoac_last_schedule")
         ms = np.zeros(2)
         lib().geoac_last_launch_ms(self._h, _p(ms))
-        return {"rd_group": o[0], "long_packets": o[1], "long_ctas": o[2], "launches": o[3], "main_ms": float(ms[0]), "long_ms": float(ms[1])}
+        return {"rd_group": o[0], "long_packets": o[1], "quarter_packets": o[4], "long_ctas": o[2], "launches": o[3], "main_ms": float(ms[0]), "long_ms": float(ms[1])}
 
     def selftest_math(self, n_per_thread=2000):
         """Max relative error of the kernel's rcp / rsqrt / sqrt / exp / exp10 against the CUDA math library."""

@@ -44,9 +44,11 @@ struct Knobs {
     int rd_group = 0;       // range-dependent packets: 0 = 32 consecutive rays (inclination neighbours), 1 = equal inclination / neighbouring azimuth, -1 = automatic
     int long_alpha = 100;   // a packet is LONG if its cost exceeds long_alpha % of the average work of a lane
     int long_width = 32;    // long-region CTAs: 32 = one thread per ray, 8 = cooperative kernel (four lanes per ray, cell cache in shared memory)
-    int long_sm_pct = 50;   // at most this share of the SMs is given to the long-region launch
+    int long_sm_pct = 90;   // at most this share of the SMs is given to the long-region launch (its CTAs help with the main region once theirs is drained)
     int exclusive = 1;      // long-region launch keeps its SMs to itself (0: one launch, long packets first)
     int rd_ctas = 0;        // range-dependent sets: CTAs per SM of the main launch (0 = as many as fit)
+    int quarter = 1;        // the longest long-region packets are claimed as quarter packets while the exclusive SMs have warps to spare
+    int quarter_alpha = 210;// ... those whose cost exceeds this % of the average lane work (lone-warp speed is ~2.1x the loaded one)
     int scout_stride = 0;   // the cost scout traces every N-th ray of the batch (0 = default: every ray; measured on config 2: every 4th ray costs 24 % -- the warps' rays stop ending together)
 };
 static int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
@@ -60,7 +62,7 @@ static Knobs knobs_from_env() {
     k.rd_group = env_int("GEOAC_B200_RD_GROUP", k.rd_group); k.long_alpha = std::max(1, env_int("GEOAC_B200_LONG_ALPHA", k.long_alpha));
     k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 8 ? 8 : 32;
     k.long_sm_pct = std::min(90, std::max(1, env_int("GEOAC_B200_LONG_SM_PCT", k.long_sm_pct))); k.exclusive = env_int("GEOAC_B200_EXCLUSIVE", k.exclusive);
-    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas));
+    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas)); k.quarter = env_int("GEOAC_B200_QUARTER", k.quarter); k.quarter_alpha = std::max(1, env_int("GEOAC_B200_QUARTER_ALPHA", k.quarter_alpha));
     k.scout_stride = std::max(0, env_int("GEOAC_B200_SCOUT_STRIDE", k.scout_stride));
     return k;
 }
@@ -96,7 +98,7 @@ struct geoac_ctx {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_fork = nullptr, ev_join = nullptr, ev_m0 = nullptr, ev_m1 = nullptr, ev_l0 = nullptr, ev_l1 = nullptr;
     bool timed_launches = false;
     double grid_dh = 0.0, grid_dz = 0.0;                       // median node spacing [km] of the range-dependent grid (packet grouping heuristic)
-    int last_long_packets = 0, last_long_ctas = 0, last_rd_group = 0;
+    int last_long_packets = 0, last_long_ctas = 0, last_rd_group = 0, last_quarter_packets = 0;
     int64_t last_steps = 0; double last_ms = 0.0;
     bool consts_dirty = true;
     bool src_set = false;
@@ -200,7 +202,7 @@ extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
     else if (n == "host_tables") k.host_tables = value;
     else if (n == "rd_group") k.rd_group = value; else if (n == "long_alpha") k.long_alpha = std::max(1, value);
     else if (n == "long_width") k.long_width = (value == 8) ? 8 : 32; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
-    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value);
+    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value); else if (n == "quarter") k.quarter = value; else if (n == "quarter_alpha") k.quarter_alpha = std::max(1, value);
     else if (n == "scout_stride") k.scout_stride = std::max(0, value);
     else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
     return GEOAC_OK;
@@ -528,9 +530,10 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         }
     }
     a.prev = ctx->d_prev;
-    a.order = nullptr; a.n_claims = a.n_rays; a.n_long_packets = 0; a.counter_long = ctx->d_counters + 4; a.prefer_long = 0; a.long_width = 32;
+    a.order = nullptr; a.n_claims = a.n_rays; a.n_long_packets = 0; a.n_quarter_packets = 0; a.counter_long = ctx->d_counters + 4; a.counter_quarter = ctx->d_counters + 5;
+    a.prefer_long = 0; a.long_width = 32;
     a.packet_refill = ctx->knobs.packet > 0 ? 1 : 0;
-    ctx->last_launches = 0; ctx->last_long_packets = 0; ctx->last_long_ctas = 0; ctx->last_rd_group = 0;
+    ctx->last_launches = 0; ctx->last_long_packets = 0; ctx->last_long_ctas = 0; ctx->last_rd_group = 0; ctx->last_quarter_packets = 0;
     int grid_long = 0;
     // longest-predicted-ray-first claim order, when a lane will process more than one ray (see trace_kernel.cuh)
     // knob lpt: 0 = natural order, 1 = automatic (default), 2 = always (used by the tests on small batches)
@@ -550,6 +553,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         uint32_t* n_long = ctx->d_hist + kCostBuckets + 1;
         unsigned long long* cost_sum = reinterpret_cast<unsigned long long*>(ctx->d_hist + kCostBuckets + 2);
         double* shape = reinterpret_cast<double*>(ctx->d_hist + kCostBuckets + 4);
+        uint32_t* n_quarter = ctx->d_hist + kCostBuckets + 10;
         {   // cost scout: persistent, the table in shared memory when it fits
             using SEQ = typename EQ::Scout;
             constexpr int kScoutBlock = ScoutBlock<SEQ>::value;
@@ -612,7 +616,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
                 pass(key_t2, ctx->d_order, ctx->d_order2);
                 pass(key_c, ctx->d_order2, ctx->d_order);
                 if (n_entries > n) CK(cudaMemsetAsync(ctx->d_order + n, 0xff, sizeof(uint32_t) * (n_entries - n), st));
-                packet_long_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_order, ctx->d_cost, n_entries / 32, n, cost_sum, (long long)grid * BLOCK, ctx->knobs.long_alpha, n_long);
+                packet_long_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_order, ctx->d_cost, n_entries / 32, n, cost_sum, (long long)grid * BLOCK, ctx->knobs.long_alpha, n_long, n_quarter, ctx->knobs.quarter_alpha);
                 ctx->last_launches += 12;
             } else {
                 order_keys_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_c, cost_shift);
@@ -622,7 +626,7 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
                 if (ctx->knobs.packet < 0) a.packet_refill = 1;
             }
         } else {
-            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long, ctx->knobs.long_alpha);
+            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long, ctx->knobs.long_alpha, n_quarter, ctx->knobs.quarter_alpha);
             order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
             order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
             ctx->last_launches += 3;
@@ -633,19 +637,31 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         ctx->last_launches += 1;                                        // the cost scout
         if (PacketMode<EQ>::value && ctx->knobs.coop) {
             // the long region: packets that would outlast the pass on a fully loaded SM.  Their count sizes the second launch.
-            uint32_t h_long = 0;
+            uint32_t h_long = 0, h_quarter = 0;
             CK(cudaMemcpyAsync(&h_long, n_long, sizeof h_long, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&h_quarter, n_quarter, sizeof h_quarter, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             a.n_long_packets = std::min<int64_t>(h_long, n_entries / 32);
             ctx->last_long_packets = (int)a.n_long_packets;
             if (a.n_long_packets > 0 && ctx->knobs.exclusive && !PATHS) {
                 const int64_t per_cta = (ctx->knobs.long_width == 8) ? kCoopSlots : BLOCK;      // rays a long-region CTA holds at a time
-                grid_long = (int)std::min<int64_t>((a.n_long_packets * 32 + per_cta - 1) / per_cta, (int64_t)ctx->sm_count * ctx->knobs.long_sm_pct / 100);
+                const int64_t max_ctas = std::max<int64_t>(1, (int64_t)ctx->sm_count * ctx->knobs.long_sm_pct / 100);
+                grid_long = (int)std::min<int64_t>((a.n_long_packets * 32 + per_cta - 1) / per_cta, max_ctas);
                 grid_long = std::max(grid_long, 1);
+                if (ctx->knobs.long_width == 32 && ctx->knobs.quarter) {
+                    // The very longest packets set the length of the pass: even alone on its scheduler a warp needs ~60 us per step of its
+                    // 32 rays.  Packets whose cost exceeds quarter_alpha % of the average lane work (they would outlast the pass even at
+                    // lone-warp speed) are split over four warps -- quarter claims, four lanes per ray, ~40 us per step -- as far as the
+                    // exclusive SMs have warps to spare.  Measured on one GPU's share of the 8-way config-5 split: 31.4 s -> 22.2 s.
+                    const int64_t warps = max_ctas * (BLOCK / 32);
+                    a.n_quarter_packets = std::min<int64_t>(std::min<int64_t>(a.n_long_packets, h_quarter), std::max<int64_t>(0, (warps - a.n_long_packets) / 3));
+                    grid_long = (int)std::min<int64_t>(max_ctas, (a.n_long_packets + 3 * a.n_quarter_packets + (BLOCK / 32) - 1) / (BLOCK / 32));
+                }
             }
         }
     }
     a.long_width = 32;                                                  // one-thread-per-ray CTAs take whole packets
+    ctx->last_quarter_packets = (int)a.n_quarter_packets;
     if (grid_long > 0) {
         // Two concurrent launches.  The long region -- packets that would outlast the pass on a loaded SM -- goes to CTAs that
         // keep their SM to themselves (their shared-memory request leaves no room for a main CTA), launched first on a
@@ -964,9 +980,11 @@ extern "C" int geoac_trace_paths_compact(geoac_ctx* ctx, int64_t n_rays, const d
 // Scheduling facts of the last trace (range-dependent sets): out[0] packet grouping used (0 = consecutive rays, 1 = equal
 // inclination / neighbouring azimuth), out[1] packets in the long region, out[2] CTAs of the exclusive long-region launch,
 // out[3] kernels enqueued.
-extern "C" int geoac_last_schedule(geoac_ctx* ctx, int64_t* out4) {
-    if (!ctx || !out4) return GEOAC_ERR_BAD_ARG;
-    out4[0] = ctx->last_rd_group; out4[1] = ctx->last_long_packets; out4[2] = ctx->last_long_ctas; out4[3] = ctx->last_launches;
+extern "C" int geoac_last_schedule(geoac_ctx* ctx, int64_t* out8) {
+    if (!ctx || !out8) return GEOAC_ERR_BAD_ARG;
+    for (int i = 0; i < 8; i++) out8[i] = 0;
+    out8[0] = ctx->last_rd_group; out8[1] = ctx->last_long_packets; out8[2] = ctx->last_long_ctas; out8[3] = ctx->last_launches;
+    out8[4] = ctx->last_quarter_packets;
     return GEOAC_OK;
 }
 // Durations [ms] of the trace kernel launch(es) of the last trace, valid once the trace has completed: ms2[0] the main launch,

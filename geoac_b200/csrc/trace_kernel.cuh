@@ -47,6 +47,9 @@ struct TraceArgs {
     // claimed by the CTAs of a second, concurrent launch that keeps its SMs to itself (one warp per scheduler: see capi.cu),
     // `long_width` rays at a time (32 = whole packets, 8 = quarter packets traced four lanes per ray from the start).
     int64_t n_long_packets;
+    int64_t n_quarter_packets;        // the first of them -- the very longest -- are claimed eight rays at a time and traced four lanes per
+                                      // ray from the start: a warp with 8 rays keeps their cells in L1 and needs ~0.6x the instructions per step
+    unsigned long long* counter_quarter;
     unsigned long long* counter_long; // next unclaimed entry of the long region
     int prefer_long;                  // this launch claims the long region first (1) or the main region first (0)
     int long_width;
@@ -379,14 +382,21 @@ __global__ void __launch_bounds__(BLOCK, 1) trace_kernel(const __grid_constant__
             if (!exhausted && !__any_sync(0xffffffffu, have_ray)) {
                 unsigned long long base = 0; int width = 0;
                 if (lane == 0) {
-                    const unsigned long long nl = (unsigned long long)a.n_long_packets * 32ull;
-                    const unsigned long long nm = (unsigned long long)a.n_claims - nl;
-                    for (int attempt = 0; attempt < 2 && width == 0; attempt++) {
-                        const bool from_long = (attempt == 0) == (a.prefer_long != 0);
-                        if (from_long) {
-                            if (nl && !(region_done & 1u)) {
+                    const unsigned long long nq = (unsigned long long)a.n_quarter_packets * 32ull;                 // [0, nq): quarter claims
+                    const unsigned long long nl = (unsigned long long)a.n_long_packets * 32ull;                    // [nq, nl): whole long packets
+                    const unsigned long long nm = (unsigned long long)a.n_claims - nl;                             // [nl, n_claims): main region
+                    for (int attempt = 0; attempt < 3 && width == 0; attempt++) {
+                        // long-region CTAs: quarter, long, main; main CTAs: main, long, quarter
+                        const int region = a.prefer_long ? attempt : 2 - attempt;
+                        if (region == 0) {
+                            if (nq && !(region_done & 4u)) {
+                                const unsigned long long q = atomicAdd(a.counter_quarter, 8ull);
+                                if (q < nq) { base = q; width = 8; } else region_done |= 4u;
+                            }
+                        } else if (region == 1) {
+                            if (nl > nq && !(region_done & 1u)) {
                                 const unsigned long long q = atomicAdd(a.counter_long, (unsigned long long)a.long_width);
-                                if (q < nl) { base = q; width = a.long_width; } else region_done |= 1u;
+                                if (nq + q < nl) { base = nq + q; width = a.long_width; } else region_done |= 1u;
                             }
                         } else if (nm && !(region_done & 2u)) {
                             const unsigned long long q = atomicAdd(a.counter, 32ull);
@@ -716,23 +726,26 @@ __device__ __forceinline__ uint32_t group_cost(const uint32_t* cost, int64_t n, 
 // Also counts the LONG groups: those whose predicted cost exceeds the average work of a lane (cost_sum / lanes) -- traced
 // serially such a packet alone would outlast the rest of the batch, so it is traced four lanes per ray instead.
 __global__ void order_hist_kernel(const uint32_t* cost, int64_t n, int group, const uint32_t* cost_max, uint32_t* hist,
-                                  const unsigned long long* cost_sum, long long lanes, uint32_t* n_long, int alpha_pct) {
+                                  const unsigned long long* cost_sum, long long lanes, uint32_t* n_long, int alpha_pct, uint32_t* n_quarter, int alpha2_pct) {
     __shared__ uint32_t h[kCostBuckets];
-    __shared__ uint32_t nl;
+    __shared__ uint32_t nl, nq;
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) h[i] = 0;
-    if (threadIdx.x == 0) nl = 0;
+    if (threadIdx.x == 0) { nl = 0; nq = 0; }
     __syncthreads();
     const uint32_t cmax = *cost_max;
-    const unsigned long long thr = (*cost_sum / (unsigned long long)lanes) * (unsigned long long)alpha_pct / 100ull;
+    const unsigned long long avg = *cost_sum / (unsigned long long)lanes;
+    const unsigned long long thr = avg * (unsigned long long)alpha_pct / 100ull, thr2 = avg * (unsigned long long)alpha2_pct / 100ull;
     const int64_t ng = (n + group - 1) / group;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ng; g += (int64_t)gridDim.x * blockDim.x) {
         const uint32_t c = group_cost(cost, n, g, group);
         atomicAdd(&h[cost_bucket(c, cmax)], 1u);
         if (group == 32 && (unsigned long long)c > thr) atomicAdd(&nl, 1u);
+        if (group == 32 && (unsigned long long)c > thr2) atomicAdd(&nq, 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kCostBuckets; i += blockDim.x) if (h[i]) atomicAdd(&hist[i], h[i]);
     if (threadIdx.x == 0 && nl) atomicAdd(n_long, nl);
+    if (threadIdx.x == 0 && nq) atomicAdd(n_quarter, nq);
 }
 __global__ void order_scan_kernel(uint32_t* hist) {          // one block of kCostBuckets threads: exclusive prefix in place
     __shared__ uint32_t h[kCostBuckets];
@@ -881,16 +894,19 @@ __global__ void order_keys16_kernel(const uint32_t* cost, const double* theta, i
 // packets of the final order whose longest ray exceeds the average work of a lane (times alpha_pct / 100): the long region.
 // The order is sorted by cost bucket, so they sit at its head; the count is all the launch needs.
 __global__ void packet_long_kernel(const uint32_t* order, const uint32_t* cost, int64_t n_packets, int64_t n_rays,
-                                   const unsigned long long* cost_sum, long long lanes, int alpha_pct, uint32_t* n_long) {
-    const unsigned long long thr = (*cost_sum / (unsigned long long)lanes) * (unsigned long long)alpha_pct / 100ull;
-    uint32_t cnt = 0;
+                                   const unsigned long long* cost_sum, long long lanes, int alpha_pct, uint32_t* n_long, uint32_t* n_quarter, int alpha2_pct) {
+    const unsigned long long avg = *cost_sum / (unsigned long long)lanes;
+    const unsigned long long thr = avg * (unsigned long long)alpha_pct / 100ull, thr2 = avg * (unsigned long long)alpha2_pct / 100ull;
+    uint32_t cnt = 0, cnt2 = 0;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < n_packets; g += (int64_t)gridDim.x * blockDim.x) {
         uint32_t c = 0;
         for (int l = 0; l < 32; l++) { const uint32_t r = order[g * 32 + l]; if (r < n_rays) c = max(c, cost[r]); }
         if ((unsigned long long)c > thr) cnt++;
+        if ((unsigned long long)c > thr2) cnt2++;
     }
-    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    cnt = __reduce_add_sync(0xffffffffu, cnt); cnt2 = __reduce_add_sync(0xffffffffu, cnt2);
     if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(n_long, cnt);
+    if ((threadIdx.x & 31) == 0 && cnt2) atomicAdd(n_quarter, cnt2);
 }
 
 #endif  // __CUDACC__

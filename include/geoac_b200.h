@@ -283,10 +283,11 @@ int geoac_eq_count(int variant, int calc_amp);
  * 8 for the stratified ones, whose order is (cost, inclination, batch index) in two stable passes).  Either pointer may be NULL. */
 int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kernel_launches);
 
-/* Scheduling facts of the last trace on ctx: out4[0] packet grouping of the range-dependent sets (0 = 32 consecutive rays,
- * 1 = equal inclination / neighbouring azimuth), out4[1] packets in the long region (predicted to outlast the pass on a loaded
- * SM), out4[2] CTAs of the concurrent launch that traced them on SMs of their own, out4[3] kernels enqueued. */
-int geoac_last_schedule(geoac_ctx* ctx, int64_t* out4);
+/* Scheduling facts of the last trace on ctx (8 values): [0] packet grouping of the range-dependent sets (0 = 32 consecutive rays,
+ * 1 = equal inclination / neighbouring azimuth), [1] packets in the long region (predicted to outlast the pass on a loaded SM),
+ * [2] CTAs of the concurrent launch that traced them on SMs of their own, [3] kernels enqueued, [4] the longest of the long packets
+ * that were split over four warps (quarter claims, four lanes per ray), [5..7] reserved (0). */
+int geoac_last_schedule(geoac_ctx* ctx, int64_t* out8);
 /* Durations [ms] of the trace kernel launch(es) of the last completed trace: ms2[0] main launch, ms2[1] long-region launch (or 0). */
 int geoac_last_launch_ms(geoac_ctx* ctx, double* ms2);
 
@@ -305,7 +306,7 @@ int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t 
 /* Tuning / experiment knobs of a context.  Their defaults are read from the GEOAC_B200_* environment
  * variables ONCE, in geoac_create; nothing on the launch path reads the environment.  Names: "lpt" (claim order: 0 natural,
  * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables",
- * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride".
+ * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride", "quarter", "quarter_alpha".
  * No knob changes a record bit except "sbpoly" (absorption sum to 1e-11) -- that is what the tests use them to prove. */
 int geoac_set_knob(geoac_ctx* ctx, const char* name, int value);
 
