@@ -87,7 +87,7 @@ def workload_angles(name, rank=0):
 
 def shard_indices(n, rank, world):
     from geoac_b200 import sharding
-    return sharding.shard_indices(n, rank, world)
+    return sharding.shard_indices(n, rank, world, int(os.environ.get("GEOAC_BENCH_SHARD_BLOCK", sharding.SHARD_BLOCK)))
 
 
 def setup_tracer(name, device):
@@ -573,8 +573,14 @@ def strong_scaling_record(world, rank, local, dev, barrier):
     else:
         tmax = tmin = tsum = t
     tr.close()
+    per_rank = [ms]
+    if world > 1:
+        gathered = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([ms], dtype=torch.float64, device=dev))
+        per_rank = [g.item() for g in gathered]
     secs = tmax[0].item() * 1e-3
     return {"workload": DESCRIPTIONS["config5"], "scaling": "strong", "n_gpus": world, "passes": 1, "ms": tmax[0].item(), "ms_fastest_rank": tmin[0].item(),
+            "ms_per_rank": [round(x, 1) for x in per_rank],
             "rays": int(tsum[2].item()), "rays_per_sec": tsum[2].item() / secs, "rk4_steps": int(tsum[1].item()), "rk4_steps_per_sec": tsum[1].item() / secs,
             "arrival_records": int(tsum[3].item()), "n_steps_checksum": int(tsum[4].item()),
             "lane_occupancy_min_rank": tmin[5].item(), "setup_s_rank0": setup_s,

@@ -47,6 +47,8 @@ struct Knobs {
     int long_sm_pct = 90;   // at most this share of the SMs is given to the long-region launch (its CTAs help with the main region once theirs is drained)
     int exclusive = 1;      // long-region launch keeps its SMs to itself (0: one launch, long packets first)
     int rd_ctas = 0;        // range-dependent sets: CTAs per SM of the main launch (0 = as many as fit)
+    int refine = 0;         // range-dependent sets: rays the cost scout finds long are scouted again at a quarter of its step multiple (measured on the
+                            // config-5 share of one of 8 GPUs: +8 s for the second pass, no change of the long launch -- off)
     int quarter = 1;        // the longest long-region packets are claimed as quarter packets while the exclusive SMs have warps to spare
     int quarter_alpha = 210;// ... those whose cost exceeds this % of the average lane work (lone-warp speed is ~2.1x the loaded one)
     int scout_stride = 0;   // the cost scout traces every N-th ray of the batch (0 = default: every ray; measured on config 2: every 4th ray costs 24 % -- the warps' rays stop ending together)
@@ -62,7 +64,7 @@ static Knobs knobs_from_env() {
     k.rd_group = env_int("GEOAC_B200_RD_GROUP", k.rd_group); k.long_alpha = std::max(1, env_int("GEOAC_B200_LONG_ALPHA", k.long_alpha));
     k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 8 ? 8 : 32;
     k.long_sm_pct = std::min(90, std::max(1, env_int("GEOAC_B200_LONG_SM_PCT", k.long_sm_pct))); k.exclusive = env_int("GEOAC_B200_EXCLUSIVE", k.exclusive);
-    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas)); k.quarter = env_int("GEOAC_B200_QUARTER", k.quarter); k.quarter_alpha = std::max(1, env_int("GEOAC_B200_QUARTER_ALPHA", k.quarter_alpha));
+    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas)); k.quarter = env_int("GEOAC_B200_QUARTER", k.quarter); k.refine = env_int("GEOAC_B200_REFINE", k.refine); k.quarter_alpha = std::max(1, env_int("GEOAC_B200_QUARTER_ALPHA", k.quarter_alpha));
     k.scout_stride = std::max(0, env_int("GEOAC_B200_SCOUT_STRIDE", k.scout_stride));
     return k;
 }
@@ -88,6 +90,7 @@ struct geoac_ctx {
     double* d_prev = nullptr; size_t cap_prev = 0; // y_{k-1} scratch of the trace kernel
     double* d_path = nullptr; size_t cap_path = 0; int32_t* d_path_rows = nullptr; size_t cap_path_rows = 0;   // raypath capture staging
     double* d_caus = nullptr; size_t cap_caus = 0; int32_t* d_caus_rows = nullptr; size_t cap_caus_rows = 0;   // caustic event staging
+    uint32_t* d_refine = nullptr; int64_t cap_refine = 0;    // rays scouted a second time
     uint32_t *d_cost = nullptr, *d_order = nullptr, *d_hist = nullptr, *d_blockhist = nullptr, *d_order2 = nullptr; uint8_t* d_keys = nullptr; int64_t cap_order = 0, cap_keys = 0;   // longest-ray-first scheduling
     int last_launches = 0;
     // staging for the host-buffer entry point
@@ -156,7 +159,7 @@ extern "C" geoac_ctx* geoac_create(int variant, int device, int* status) {
            && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming) == cudaSuccess
            && cudaEventCreate(&ctx->ev_m0) == cudaSuccess && cudaEventCreate(&ctx->ev_m1) == cudaSuccess && cudaEventCreate(&ctx->ev_l0) == cudaSuccess && cudaEventCreate(&ctx->ev_l1) == cudaSuccess
            && cudaMalloc(&ctx->d_consts, sizeof(LaunchConsts)) == cudaSuccess
-           && cudaMalloc(&ctx->d_counters, 6 * sizeof(unsigned long long)) == cudaSuccess;
+           && cudaMalloc(&ctx->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess;
     if (!ok) { std::string m = cudaGetErrorString(cudaGetLastError()); delete ctx; return bail(GEOAC_ERR_CUDA, "context allocation failed: " + m); }
     if (status) *status = GEOAC_OK;
     return ctx;
@@ -166,7 +169,7 @@ extern "C" void geoac_destroy(geoac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaFree(ctx->d_table); cudaFree(ctx->d_sbpoly); cudaFree(ctx->d_consts); cudaFree(ctx->d_counters); cudaFree(ctx->d_prev);
-    cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_blockhist); cudaFree(ctx->d_order2); cudaFree(ctx->d_keys); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows); cudaFree(ctx->d_caus); cudaFree(ctx->d_caus_rows);
+    cudaFree(ctx->d_refine); cudaFree(ctx->d_cost); cudaFree(ctx->d_order); cudaFree(ctx->d_hist); cudaFree(ctx->d_blockhist); cudaFree(ctx->d_order2); cudaFree(ctx->d_keys); cudaFree(ctx->d_path); cudaFree(ctx->d_path_rows); cudaFree(ctx->d_caus); cudaFree(ctx->d_caus_rows);
     cudaFree(ctx->d_tuv); cudaFree(ctx->d_rho); cudaFree(ctx->d_ax);
     cudaFree(ctx->d_theta); cudaFree(ctx->d_phi); cudaFree(ctx->d_rec); cudaFree(ctx->d_status); cudaFree(ctx->d_nsteps);
     cudaFreeHost(ctx->pin_theta.p); cudaFreeHost(ctx->pin_phi.p); cudaFreeHost(ctx->pin_rec.p); cudaFreeHost(ctx->pin_status.p); cudaFreeHost(ctx->pin_nsteps.p);
@@ -202,7 +205,7 @@ extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
     else if (n == "host_tables") k.host_tables = value;
     else if (n == "rd_group") k.rd_group = value; else if (n == "long_alpha") k.long_alpha = std::max(1, value);
     else if (n == "long_width") k.long_width = (value == 8) ? 8 : 32; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
-    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value); else if (n == "quarter") k.quarter = value; else if (n == "quarter_alpha") k.quarter_alpha = std::max(1, value);
+    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value); else if (n == "quarter") k.quarter = value; else if (n == "refine") k.refine = value; else if (n == "quarter_alpha") k.quarter_alpha = std::max(1, value);
     else if (n == "scout_stride") k.scout_stride = std::max(0, value);
     else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
     return GEOAC_OK;
@@ -569,8 +572,24 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
             const int sblocks = (int)std::min<int64_t>((int64_t)ctx->sm_count * std::max(1, s_per_sm), s_need);
             unsigned long long* scounter = ctx->d_counters + 3;
             int coarse = ctx->knobs.scout_coarse > 0 ? ctx->knobs.scout_coarse : (kGrid ? kScoutCoarse : 2 * kScoutCoarse);   // stratified: 32x measured best (404.8 vs 421.0 / 443.3 ms at 16x / 64x)
-            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse, (void*)&stride };
+            const uint32_t* no_list = nullptr; const unsigned long long* no_count = nullptr;
+            void* sargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&scounter, (void*)&coarse, (void*)&stride, (void*)&no_list, (void*)&no_count };
             CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), sargs, s_smem, st));
+            if (kGrid && ctx->knobs.refine && coarse > 1) {
+                // second look at the rays the first pass found long, at a quarter of its step multiple (a few per cent of the rays)
+                if (n_entries > ctx->cap_refine) {
+                    cudaFree(ctx->d_refine); ctx->d_refine = nullptr; ctx->cap_refine = 0;
+                    CK(cudaMalloc(&ctx->d_refine, sizeof(uint32_t) * n_entries));
+                    ctx->cap_refine = n_entries;
+                }
+                unsigned long long* n_list = ctx->d_counters + 6; unsigned long long* rcounter = ctx->d_counters + 7;
+                refine_select_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, cost_sum, (long long)grid * BLOCK, ctx->knobs.long_alpha, ctx->d_refine, n_list);
+                int coarse2 = std::max(1, coarse / 4), one = 1;
+                const uint32_t* lst = ctx->d_refine; const unsigned long long* cnt = n_list;
+                void* rargs[] = { (void*)&a, (void*)&ctx->d_cost, (void*)&cmax, (void*)&cost_sum, (void*)&rcounter, (void*)&coarse2, (void*)&one, (void*)&lst, (void*)&cnt };
+                CK(cudaLaunchKernel(sfn, dim3(sblocks), dim3(kScoutBlock), rargs, s_smem, st));
+                ctx->last_launches += 2;
+            }
         }
         // Range-dependent sets: which 32 rays make a packet (trace_kernel.cuh: grid_shape_kernel).  The choice only schedules.
         bool by_theta = !PacketMode<EQ>::value;
@@ -722,7 +741,7 @@ static int enqueue_trace(geoac_ctx* ctx, int64_t n_rays, const double* d_theta, 
     }
     const int n_rec = ctx->prm.bounces + 1;
     const int64_t n_slots = n_rays * n_rec;
-    CK(cudaMemsetAsync(ctx->d_counters, 0, 6 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(ctx->d_counters, 0, 8 * sizeof(unsigned long long), st));
     CK(cudaMemsetAsync(d_rec, 0, sizeof(double) * GEOAC_NFIELDS * n_slots, st));
     CK(cudaMemsetAsync(d_status, 0, sizeof(int32_t) * n_slots, st));
     CK(cudaMemsetAsync(d_n_steps, 0, sizeof(int32_t) * n_slots, st));

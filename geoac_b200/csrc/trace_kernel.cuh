@@ -629,7 +629,8 @@ template <class EQ> struct ScoutBlock { static constexpr int value = std::is_sam
 // in registers.
 template <class EQ, bool TABLE_IN_SMEM>
 __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const __grid_constant__ TraceArgs a, uint32_t* cost, uint32_t* cost_max,
-                                                               unsigned long long* cost_sum, unsigned long long* counter, int coarse, int stride) {
+                                                               unsigned long long* cost_sum, unsigned long long* counter, int coarse, int stride,
+                                                               const uint32_t* list, const unsigned long long* n_list) {
     constexpr int NEQ = EQ::NEQ;
     constexpr bool kGrid = std::is_same<typename EQ::Atmo, Grid3D>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -663,7 +664,9 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
             if (want) {
                 // every `stride`-th ray is scouted; its neighbours in the batch (neighbouring launch angles) inherit the estimate --
                 // the cost only orders the claims, and it varies smoothly along the launch grid
-                ray = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u))) * stride;
+                // (refinement pass: the rays named in `list` -- the ones the first pass found long -- are scouted again at a finer step)
+                const int64_t item = (int64_t)(base + __popc(wmask & ((1u << lane) - 1u)));
+                ray = list ? ((unsigned long long)item < *n_list ? (int64_t)list[item] : a.n_rays) : item * stride;
                 if (ray < a.n_rays) {
                     cur = typename EQ::Cursor{};
                     EQ::init(L, T, a.theta[ray], a.phi[ray], rc, y, cur);
@@ -699,7 +702,8 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
             }
         }
         if (done) {
-            for (int j = 0; j < stride && ray + j < a.n_rays; j++) { cost[ray + j] = est; total += est; }
+            if (list) { total += (unsigned long long)est - (unsigned long long)cost[ray]; cost[ray] = est; }      // replaces the first estimate (the sum wraps correctly)
+            else for (int j = 0; j < stride && ray + j < a.n_rays; j++) { cost[ray + j] = est; total += est; }
             worst = max(worst, est); have_ray = false;
         }
         else {
@@ -710,6 +714,16 @@ __global__ void __launch_bounds__(ScoutBlock<EQ>::value, 1) scout_kernel(const _
     worst = __reduce_max_sync(0xffffffffu, worst);
     for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(0xffffffffu, total, off);
     if (lane == 0 && worst) { atomicMax(cost_max, worst); atomicAdd(cost_sum, total); }
+}
+
+// rays whose first estimate exceeds alpha % of the average lane work: candidates for the long region, scouted again at a finer step
+// (they are a few per cent of the rays; a long packet that the coarse scout underestimates is traced as a whole packet instead of
+// four quarters and then sets the length of the pass -- measured: one rank in eight, 27 s instead of 22.5 s)
+__global__ void refine_select_kernel(const uint32_t* cost, int64_t n, const unsigned long long* cost_sum, long long lanes, int alpha_pct,
+                                     uint32_t* list, unsigned long long* n_list) {
+    const unsigned long long thr = (*cost_sum / (unsigned long long)lanes) * (unsigned long long)alpha_pct / 100ull;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        if ((unsigned long long)cost[i] > thr) list[atomicAdd(n_list, 1ull)] = (uint32_t)i;
 }
 
 // counting sort by predicted cost, descending: hist[b] of bucket(cost) -> start offsets -> scatter.  The sorted items are

@@ -306,7 +306,7 @@ int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t 
 /* Tuning / experiment knobs of a context.  Their defaults are read from the GEOAC_B200_* environment
  * variables ONCE, in geoac_create; nothing on the launch path reads the environment.  Names: "lpt" (claim order: 0 natural,
  * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables",
- * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride", "quarter", "quarter_alpha".
+ * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride", "quarter", "quarter_alpha", "refine".
  * No knob changes a record bit except "sbpoly" (absorption sum to 1e-11) -- that is what the tests use them to prove. */
 int geoac_set_knob(geoac_ctx* ctx, const char* name, int value);
 
