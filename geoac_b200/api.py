@@ -70,6 +70,7 @@ def lib():
         L.geoac_set_knob.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.geoac_last_schedule.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         L.geoac_last_launch_ms.argtypes = [C.c_void_p, _dp]
+        L.geoac_get_costs.argtypes = [C.c_void_p, C.c_int64, C.POINTER(C.c_uint32)]
         _cp = C.POINTER(C.c_void_p)
         L.geoac_create_multi.argtypes = [C.c_int, C.POINTER(C.c_int), C.c_int, _cp, C.POINTER(C.c_int)]
         L.geoac_multi_set_atmosphere_1d.argtypes = [_cp, C.c_int, C.c_int, _dp, _dp, _dp, _dp, _dp]
@@ -87,7 +88,7 @@ EXPORTED_SYMBOLS = [
     "geoac_set_atmosphere_3d", "geoac_get_params", "geoac_set_params", "geoac_trace", "geoac_trace_paths", "geoac_trace_device",
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
     "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_eigenray_direct", "geoac_get_variant", "geoac_source_state",
-    "geoac_set_knob", "geoac_last_schedule", "geoac_last_launch_ms", "geoac_trace_paths_compact",
+    "geoac_set_knob", "geoac_last_schedule", "geoac_last_launch_ms", "geoac_trace_paths_compact", "geoac_get_costs",
     "geoac_create_multi", "geoac_multi_set_atmosphere_1d", "geoac_multi_set_atmosphere_3d", "geoac_multi_set_params", "geoac_trace_multi",
 ]
 
@@ -339,6 +340,12 @@ class Tracer:
         ms = np.zeros(2)
         lib().geoac_last_launch_ms(self._h, _p(ms))
         return {"rd_group": o[0], "long_packets": o[1], "quarter_packets": o[4], "long_ctas": o[2], "launches": o[3], "main_ms": float(ms[0]), "long_ms": float(ms[1])}
+
+    def predicted_costs(self, n):
+        """RK4 step counts the cost scout predicted for the n rays of the last trace (diagnosis hook)."""
+        c = np.zeros(n, dtype=np.uint32)
+        self._check(lib().geoac_get_costs(self._h, n, c.ctypes.data_as(C.POINTER(C.c_uint32))), "geoac_get_costs")
+        return c
 
     def selftest_math(self, n_per_thread=2000):
         """Max relative error of the kernel's rcp / rsqrt / sqrt / exp / exp10 against the CUDA math library."""

@@ -47,6 +47,8 @@ struct Knobs {
     int long_sm_pct = 90;   // at most this share of the SMs is given to the long-region launch (its CTAs help with the main region once theirs is drained)
     int exclusive = 1;      // long-region launch keeps its SMs to itself (0: one launch, long packets first)
     int rd_ctas = 0;        // range-dependent sets: CTAs per SM of the main launch (0 = as many as fit)
+    int dilate = 400;       // range-dependent sets: the ordering cost of a ray is the maximum over its inclination neighbours within this many
+                            // millidegrees (0 = off): the edge of a long ray family is scheduled as long
     int refine = 0;         // range-dependent sets: rays the cost scout finds long are scouted again at a quarter of its step multiple (measured on the
                             // config-5 share of one of 8 GPUs: +8 s for the second pass, no change of the long launch -- off)
     int quarter = 1;        // the longest long-region packets are claimed as quarter packets while the exclusive SMs have warps to spare
@@ -64,7 +66,7 @@ static Knobs knobs_from_env() {
     k.rd_group = env_int("GEOAC_B200_RD_GROUP", k.rd_group); k.long_alpha = std::max(1, env_int("GEOAC_B200_LONG_ALPHA", k.long_alpha));
     k.long_width = env_int("GEOAC_B200_LONG_WIDTH", k.long_width) == 8 ? 8 : 32;
     k.long_sm_pct = std::min(90, std::max(1, env_int("GEOAC_B200_LONG_SM_PCT", k.long_sm_pct))); k.exclusive = env_int("GEOAC_B200_EXCLUSIVE", k.exclusive);
-    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas)); k.quarter = env_int("GEOAC_B200_QUARTER", k.quarter); k.refine = env_int("GEOAC_B200_REFINE", k.refine); k.quarter_alpha = std::max(1, env_int("GEOAC_B200_QUARTER_ALPHA", k.quarter_alpha));
+    k.rd_ctas = std::max(0, env_int("GEOAC_B200_RD_CTAS", k.rd_ctas)); k.quarter = env_int("GEOAC_B200_QUARTER", k.quarter); k.refine = env_int("GEOAC_B200_REFINE", k.refine); k.dilate = std::max(0, env_int("GEOAC_B200_DILATE", k.dilate)); k.quarter_alpha = std::max(1, env_int("GEOAC_B200_QUARTER_ALPHA", k.quarter_alpha));
     k.scout_stride = std::max(0, env_int("GEOAC_B200_SCOUT_STRIDE", k.scout_stride));
     return k;
 }
@@ -205,7 +207,7 @@ extern "C" int geoac_set_knob(geoac_ctx* ctx, const char* name, int value) {
     else if (n == "host_tables") k.host_tables = value;
     else if (n == "rd_group") k.rd_group = value; else if (n == "long_alpha") k.long_alpha = std::max(1, value);
     else if (n == "long_width") k.long_width = (value == 8) ? 8 : 32; else if (n == "long_sm_pct") k.long_sm_pct = std::min(90, std::max(1, value));
-    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value); else if (n == "quarter") k.quarter = value; else if (n == "refine") k.refine = value; else if (n == "quarter_alpha") k.quarter_alpha = std::max(1, value);
+    else if (n == "exclusive") k.exclusive = value; else if (n == "rd_ctas") k.rd_ctas = std::max(0, value); else if (n == "quarter") k.quarter = value; else if (n == "refine") k.refine = value; else if (n == "dilate") k.dilate = std::max(0, value); else if (n == "quarter_alpha") k.quarter_alpha = std::max(1, value);
     else if (n == "scout_stride") k.scout_stride = std::max(0, value);
     else return fail(ctx, GEOAC_ERR_BAD_ARG, "unknown knob " + n);
     return GEOAC_OK;
@@ -591,6 +593,18 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
                 ctx->last_launches += 2;
             }
         }
+        const uint32_t* d_cost_used = ctx->d_cost;
+        if (kGrid && ctx->knobs.dilate > 0) {
+            // the estimate used for the claim order: maximum over the inclination neighbours (trace_kernel.cuh: cost_dilate_kernel)
+            if (n_entries > ctx->cap_refine) {
+                cudaFree(ctx->d_refine); ctx->d_refine = nullptr; ctx->cap_refine = 0;
+                CK(cudaMalloc(&ctx->d_refine, sizeof(uint32_t) * n_entries));
+                ctx->cap_refine = n_entries;
+            }
+            cost_dilate_kernel<<<ctx->sm_count * 2, 256, 0, st>>>(ctx->d_cost, a.theta, a.n_rays, ctx->knobs.dilate * 1e-3 * kPi / 180.0, 16, ctx->d_refine);
+            d_cost_used = ctx->d_refine;
+            ctx->last_launches += 1;
+        }
         // Range-dependent sets: which 32 rays make a packet (trace_kernel.cuh: grid_shape_kernel).  The choice only schedules.
         bool by_theta = !PacketMode<EQ>::value;
         if (PacketMode<EQ>::value) {
@@ -630,12 +644,12 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
                 stable_scatter_kernel<<<nblk, 32, 0, st>>>(key, src, n, chunk, ctx->d_blockhist, dst);
             };
             if (PacketMode<EQ>::value) {           // 16-bit inclination key: a packet holds ONE inclination wherever a row of the grid is long enough
-                order_keys16_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_t2, key_c, cost_shift);
+                order_keys16_kernel<<<ctx->sm_count, 256, 0, st>>>(d_cost_used, a.theta, n, cmax, trange, key_t, key_t2, key_c, cost_shift);
                 pass(key_t, nullptr, ctx->d_order);
                 pass(key_t2, ctx->d_order, ctx->d_order2);
                 pass(key_c, ctx->d_order2, ctx->d_order);
                 if (n_entries > n) CK(cudaMemsetAsync(ctx->d_order + n, 0xff, sizeof(uint32_t) * (n_entries - n), st));
-                packet_long_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_order, ctx->d_cost, n_entries / 32, n, cost_sum, (long long)grid * BLOCK, ctx->knobs.long_alpha, n_long, n_quarter, ctx->knobs.quarter_alpha);
+                packet_long_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_order, d_cost_used, n_entries / 32, n, cost_sum, (long long)grid * BLOCK, ctx->knobs.long_alpha, n_long, n_quarter, ctx->knobs.quarter_alpha);
                 ctx->last_launches += 12;
             } else {
                 order_keys_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.theta, n, cmax, trange, key_t, key_c, cost_shift);
@@ -645,9 +659,9 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
                 if (ctx->knobs.packet < 0) a.packet_refill = 1;
             }
         } else {
-            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long, ctx->knobs.long_alpha, n_quarter, ctx->knobs.quarter_alpha);
+            order_hist_kernel<<<ctx->sm_count, 256, 0, st>>>(d_cost_used, a.n_rays, group, cmax, ctx->d_hist, cost_sum, (long long)grid * BLOCK, n_long, ctx->knobs.long_alpha, n_quarter, ctx->knobs.quarter_alpha);
             order_scan_kernel<<<1, kCostBuckets, 0, st>>>(ctx->d_hist);
-            order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(ctx->d_cost, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
+            order_scatter_kernel<<<ctx->sm_count, 256, 0, st>>>(d_cost_used, a.n_rays, group, cmax, ctx->d_hist, ctx->d_order);
             ctx->last_launches += 3;
         }
         CK(cudaGetLastError());
@@ -1006,6 +1020,16 @@ extern "C" int geoac_last_schedule(geoac_ctx* ctx, int64_t* out8) {
     out8[4] = ctx->last_quarter_packets;
     return GEOAC_OK;
 }
+// Test / diagnosis hook: the cost scout's predicted RK4 step counts of the last trace's rays (n entries, batch order); zeros if no
+// claim order was built.
+extern "C" int geoac_get_costs(geoac_ctx* ctx, int64_t n, uint32_t* cost) {
+    if (!ctx || !cost || n < 0) return GEOAC_ERR_BAD_ARG;
+    if (!ctx->d_cost || n > ctx->cap_order) return fail(ctx, GEOAC_ERR_BAD_ARG, "geoac_get_costs: no claim order of that size was built");
+    cudaSetDevice(ctx->device);
+    CK(cudaMemcpy(cost, ctx->d_cost, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost));
+    return GEOAC_OK;
+}
+
 // Durations [ms] of the trace kernel launch(es) of the last trace, valid once the trace has completed: ms2[0] the main launch,
 // ms2[1] the concurrent long-region launch (0 if there was none).
 extern "C" int geoac_last_launch_ms(geoac_ctx* ctx, double* ms2) {

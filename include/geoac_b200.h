@@ -288,6 +288,8 @@ int geoac_last_trace_counters(geoac_ctx* ctx, int64_t* warp_trips, int64_t* kern
  * [2] CTAs of the concurrent launch that traced them on SMs of their own, [3] kernels enqueued, [4] the longest of the long packets
  * that were split over four warps (quarter claims, four lanes per ray), [5..7] reserved (0). */
 int geoac_last_schedule(geoac_ctx* ctx, int64_t* out8);
+/* Test / diagnosis hook: the RK4 step counts the cost scout PREDICTED for the rays of the last trace (n entries, batch order). */
+int geoac_get_costs(geoac_ctx* ctx, int64_t n, uint32_t* cost);
 /* Durations [ms] of the trace kernel launch(es) of the last completed trace: ms2[0] main launch, ms2[1] long-region launch (or 0). */
 int geoac_last_launch_ms(geoac_ctx* ctx, double* ms2);
 
@@ -306,7 +308,7 @@ int geoac_get_grid_tables(geoac_ctx* ctx, int64_t cap_tuv, double* tuv, int64_t 
 /* Tuning / experiment knobs of a context.  Their defaults are read from the GEOAC_B200_* environment
  * variables ONCE, in geoac_create; nothing on the launch path reads the environment.  Names: "lpt" (claim order: 0 natural,
  * 1 automatic, 2 always), "packet", "scout_coarse", "stable", "cost_shift", "coop", "sbpoly", "block3d", "host_tables",
- * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride", "quarter", "quarter_alpha", "refine".
+ * "rd_group", "long_alpha", "long_width", "long_sm_pct", "exclusive", "rd_ctas", "scout_stride", "quarter", "quarter_alpha", "refine", "dilate".
  * No knob changes a record bit except "sbpoly" (absorption sum to 1e-11) -- that is what the tests use them to prove. */
 int geoac_set_knob(geoac_ctx* ctx, const char* name, int value);
 
