@@ -699,8 +699,9 @@ static int launch_trace(geoac_ctx* ctx, TraceArgs a, cudaStream_t st) {
         // Two concurrent launches.  The long region -- packets that would outlast the pass on a loaded SM -- goes to CTAs that
         // keep their SM to themselves (their shared-memory request leaves no room for a main CTA), launched first on a
         // high-priority stream; the main launch fills the other SMs, and its surplus CTAs start as SMs free up.  Each side
-        // drains its own region first and then helps with the other.  knob long_width = 8 (default): the cooperative kernel
-        // (four lanes per ray, the ray's cell in shared memory via TMA: trace_kernel.cuh); 32: the same one-thread-per-ray kernel.
+        // drains its own region first and then helps with the other.  knob long_width = 32 (default): the same one-thread-per-ray
+        // kernel; 8: the cooperative kernel (four lanes per ray, the ray's cell in shared memory via TMA: trace_kernel.cuh), which
+        // measured at half the throughput and is kept for A/B runs.
         const bool coop = ctx->knobs.long_width == 8;
         const void* fn_long = fn; size_t smem_long = 0; int block_long = BLOCK; size_t lanes_long = (size_t)grid_long * BLOCK;
         if constexpr (PacketMode<EQ>::value) {
