@@ -53,6 +53,10 @@ def lib():
                                                 C.c_int64, C.c_int64, _dp, _lp]
         L.geoac_trace_device.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.geoac_reserve.argtypes = [C.c_void_p, C.c_int64]
+        L.geoac_host_alloc.restype = C.c_void_p
+        L.geoac_host_alloc.argtypes = [C.c_size_t]
+        L.geoac_host_free.restype = None
+        L.geoac_host_free.argtypes = [C.c_void_p]
         L.geoac_last_trace_stats.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_double)]
         L.geoac_load_met_1d.argtypes = [C.c_char_p, C.c_char_p, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int), _dp, _dp, _dp, _dp, _dp]
         L.geoac_load_met_grid.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -89,6 +93,7 @@ EXPORTED_SYMBOLS = [
     "geoac_reserve", "geoac_last_trace_stats", "geoac_last_trace_counters", "geoac_selftest_math", "geoac_load_met_1d", "geoac_load_met_grid", "geoac_eq_count", "geoac_measure_fp64_peak",
     "geoac_get_grid_tables", "geoac_default_eig_opts", "geoac_eigenray_search", "geoac_eigenray_direct", "geoac_get_variant", "geoac_source_state",
     "geoac_set_knob", "geoac_last_schedule", "geoac_last_launch_ms", "geoac_trace_paths_compact", "geoac_get_costs",
+    "geoac_host_alloc", "geoac_host_free",
     "geoac_create_multi", "geoac_multi_set_atmosphere_1d", "geoac_multi_set_atmosphere_3d", "geoac_multi_set_params", "geoac_trace_multi",
 ]
 
@@ -121,6 +126,33 @@ def load_met_grid(prefix, loc0, loc1, fmt="zTuvdp", is_global=False):
     if rc != abi.GEOAC_OK or (n0.value, n1.value, nz.value) != (n0g, n1g, nzg):
         raise GeoAcError(f"geoac_load_met_grid({prefix}) failed with status {rc}")
     return [ax0, ax1, axz] + [f.reshape(n0g, n1g, nzg) for f in fields]
+
+
+class PinnedArray:
+    """A numpy array on page-locked host memory from geoac_host_alloc (the buffers a C++ front end would hand to geoac_trace):
+    `.array` is the view; the memory is released by close() / when the object is collected -- keep it alive while the view is used."""
+
+    def __init__(self, shape, dtype=np.float64):
+        dt = np.dtype(dtype)
+        n = int(np.prod(shape, dtype=np.int64))
+        self._nbytes = max(1, n * dt.itemsize)
+        self._p = lib().geoac_host_alloc(self._nbytes)
+        if not self._p:
+            raise GeoAcError(f"geoac_host_alloc({self._nbytes}) failed (no CUDA device or out of page-locked memory)")
+        buf = (C.c_char * self._nbytes).from_address(self._p)
+        self.array = np.frombuffer(buf, dtype=dt, count=n).reshape(shape)
+
+    def close(self):
+        if getattr(self, "_p", None):
+            self.array = None
+            lib().geoac_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def default_params(variant):

@@ -828,6 +828,13 @@ static int reserve_staging(geoac_ctx* ctx, int64_t n_rays) {
     return GEOAC_OK;
 }
 
+extern "C" void* geoac_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void geoac_host_free(void* p) { if (p) { cudaFreeHost(p); cudaGetLastError(); } }
+
 extern "C" int geoac_reserve(geoac_ctx* ctx, int64_t n_rays) {
     if (!ctx || n_rays < 0) return GEOAC_ERR_BAD_ARG;
     cudaSetDevice(ctx->device);

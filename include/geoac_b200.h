@@ -17,6 +17,7 @@
 #ifndef GEOAC_B200_H_
 #define GEOAC_B200_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -196,6 +197,15 @@ int geoac_multi_set_atmosphere_3d(geoac_ctx* const* ctxs, int n_ctx, int n0, int
 int geoac_multi_set_params(geoac_ctx* const* ctxs, int n_ctx, const geoac_params* p);
 int geoac_trace_multi(geoac_ctx* const* ctxs, int n_ctx, int64_t n_rays, const double* theta, const double* phi,
                       double* rec, int32_t* status, int32_t* n_steps);
+
+/* Optional: page-locked host memory for the arrays handed to geoac_trace / geoac_trace_paths* / geoac_trace_multi (launch angles,
+ * records, status, step counts, raypath rows).  The reference keeps its results in `new double*[...]` arrays
+ * (GeoAc_BuildSolutionArray, Code/GeoAc/GeoAc.Interface.cpp:53-58), i.e. pageable memory, which the CUDA driver copies through
+ * its own staging at a fraction of the PCIe rate; with buffers from geoac_host_alloc the 151 MB of records of a config-2 pass
+ * cross at full rate (what bench.py's `e2e` leg measures with pinned buffers).  Any host memory works; this is the fast kind.
+ * Returns NULL on failure (no device, out of memory).  geoac_host_free(NULL) is a no-op. */
+void* geoac_host_alloc(size_t bytes);
+void  geoac_host_free(void* p);
 
 /* Optional: allocate the device staging geoac_trace() needs for batches of up to n_rays rays (with the current
  * `bounces`) ahead of time, so that the first trace call does not pay for it.  geoac_trace() grows it on demand anyway. */

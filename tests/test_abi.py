@@ -114,3 +114,19 @@ def test_synthetic_grids_match_their_node_files(built_lib, tmp_path):
                 assert np.allclose(a, b, rtol=2e-6, atol=0.0), nm                   # %.6e text
             else:
                 assert np.allclose(a, b, rtol=0.0, atol=atol[nm]), (nm, float(np.abs(a - b).max()))
+
+
+def test_pinned_host_allocation_binding(built_lib):
+    """geoac_host_alloc / geoac_host_free: NULL (and a GeoAcError from the wrapper) without a device, a usable buffer with one."""
+    p = api.lib().geoac_host_alloc(4096)
+    if p:                                   # a GPU box
+        api.lib().geoac_host_free(p)
+        a = api.PinnedArray((4, 8), np.int32)
+        a.array[:] = 7
+        assert a.array.sum() == 7 * 32 and a.array.flags["WRITEABLE"] and a.array.flags["C_CONTIGUOUS"]
+        a.close()
+    else:
+        with pytest.raises(api.GeoAcError):
+            api.PinnedArray((4, 8), np.int32)
+    api.lib().geoac_host_free(None)         # no-op
+    assert not api.lib().geoac_host_alloc(0)
